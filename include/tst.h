@@ -1,0 +1,166 @@
+/*
+ * include/tst.h -- C ABI of libtst.so, the B200-native TsT Random-Forest diagnostic.
+ *
+ * Drop-in boundary.  The reference repository ships no code
+ * (REF/README.md:38-39 "Code: Coming soon!"), so there is no reference FFI to mirror;
+ * every entry point below cites the sentence of REF/README.md that names the step and
+ * the scikit-learn 1.9.0 code (SK/ = site-packages/sklearn) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the boundary.
+ *   - *_dev pointers are caller-owned device memory (e.g. a torch tensor's data_ptr())
+ *     valid for the duration of the call; *_host pointers are host memory.
+ *   - every call returns 0 or a negative tst_status; the message is available from the
+ *     thread-local tst_last_error().  No C++ exception crosses the ABI, CUDA errors are
+ *     mapped, nothing calls abort().
+ *   - work is enqueued on the caller's cudaStream_t (`stream`, may be NULL = default
+ *     stream).  tst_fit_oof / tst_ibp synchronise that stream internally at tree-level
+ *     boundaries (they read back queue counters), so they return with the work done.
+ *   - a handle is not thread-safe: one handle per (process, device).
+ *   - there is NO CPU fallback: every call fails with TST_ERR_CUDA when no device is present.
+ */
+#ifndef TST_H_
+#define TST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TST_ABI_VERSION 1
+#define TST_MAX_EDGES 255        /* per feature; bins 0..254 + bin 255 for NaN */
+#define TST_MAX_CLASSES 32
+#define TST_MAX_FEATURES 1024
+#define TST_MAX_ROWS (1 << 24)   /* row id is packed in 24 bits next to the 8-bit multiplicity */
+#define TST_FOLD_TRAIN_ONLY 254  /* row trains every tree, is never held out (plain fit) */
+#define TST_FOLD_INACTIVE 255    /* row pruned by IBP / not in the table */
+
+typedef enum {
+    TST_OK = 0,
+    TST_ERR_INVALID = -1,     /* bad argument */
+    TST_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    TST_ERR_NOMEM = -3,       /* device allocation failed / forest too large to keep */
+    TST_ERR_STATE = -4,       /* call order (e.g. fit before bin) */
+    TST_ERR_OVERFLOW = -5,    /* bootstrap multiplicity > 255 or a work queue overflowed */
+    TST_ERR_UNSUPPORTED = -6
+} tst_status;
+
+typedef struct tst_handle tst_handle;
+
+/* Growth parameters; names and defaults follow RandomForestClassifier
+ * (SK/ensemble/_forest.py:1515-1537, SK/tree/_classes.py:315-345). */
+typedef struct {
+    int32_t max_depth;          /* <= 0: unlimited */
+    int32_t min_samples_split;  /* >= 2, on bootstrap-weighted counts */
+    int32_t min_samples_leaf;   /* >= 1, on bootstrap-weighted counts */
+    int32_t max_features;       /* m in [1, d]; host resolves "sqrt" -> max(1, floor(sqrt(d))) */
+    int32_t trees_in_flight;    /* <= 0: sized from free HBM */
+    int32_t keep_forest;        /* != 0: node arrays stay resident for tst_export_tree / tst_predict */
+    int32_t reserved[2];
+} tst_params;
+
+typedef struct {
+    uint64_t row_visits_big;    /* distinct in-bag rows summed over nodes searched by the per-node CTA kernel */
+    uint64_t row_visits_small;  /* ... by the warp-per-subtree kernel */
+    uint64_t nodes, leaves, searched, fallback;
+    uint64_t inbag_rows, trees, oof_steps;
+    uint64_t kernel_launches;   /* kernels launched by this handle since the last tst_reset_stats */
+    uint64_t levels;            /* level-synchronous rounds */
+    uint32_t max_depth;
+    uint32_t pad;
+    double ms_grow_big;         /* CUDA-event time spent in the dominant kernel (k_grow_big) */
+    double ms_grow_small;
+    double ms_prep;             /* bootstrap + compaction */
+    double ms_infer;
+    uint64_t launches_grow_big;
+    uint64_t launches_grow_small;
+} tst_stats;
+
+/* Canonical tree export: nodes in breadth-first order, i.e. sorted by (depth, begin). */
+typedef struct {
+    int32_t left, right;   /* node indices, -1 for leaves */
+    int32_t feature;       /* original feature index, -1 for leaves */
+    int32_t bin;           /* row goes left iff bin[row][feature] <= bin; raw threshold = edges[feature][bin] */
+    uint32_t begin, end;   /* segment of the tree's in-bag row list */
+    uint32_t depth;
+    uint32_t n_weighted;   /* sum of bootstrap multiplicities */
+} tst_node;
+
+int tst_abi_version(void);
+const char* tst_last_error(void);
+
+/* nccl_unique_id: reserved (NULL).  The vote exchange is done by the host with one NCCL
+ * all-gather (torch.distributed) followed by tst_reduce_votes; see INTEGRATION.md. */
+int tst_create(tst_handle** out, int device, int rank, int world, const void* nccl_unique_id);
+int tst_destroy(tst_handle* h);
+
+/* (1) Quantile binning -- "hand-crafted features" table ingest (REF/README.md:35); replaces
+ * SK/ensemble/_hist_gradient_boosting/_binning.pyx:50-85 (map) given edges computed as
+ * binning.py:31-111.  X_dev: [n, d] row-major float32.  edges_host: [d][TST_MAX_EDGES] float64.
+ * Builds both the column-major [d][ld] and row-major [n][stride] uint8 tables in HBM. */
+int tst_bin(tst_handle* h, const float* X_dev, int64_t n, int32_t d, const double* edges_host,
+            const int32_t* n_edges_host, void* stream);
+/* Same, from an already binned column-major table [d][n] on the device (tests, pre-binned data). */
+int tst_set_bins(tst_handle* h, const uint8_t* bins_cm_dev, int64_t n, int32_t d, void* stream);
+/* Copy the column-major table out: out_dev [d][n]. */
+int tst_get_bins(tst_handle* h, uint8_t* out_dev, void* stream);
+
+/* (A3) Stratified k-fold assignment on the device -- "k-fold cross-validation" (REF/README.md:35);
+ * replaces SK/model_selection/_split.py:774-840.  group_dev may be NULL (one group). */
+int tst_assign_folds(tst_handle* h, const uint8_t* y_dev, const uint8_t* active_dev, const int32_t* group_dev,
+                     int32_t n_groups, int32_t k, int32_t n_classes, uint8_t* fold_dev, void* stream);
+
+/* (2)-(6) Fit this rank's share of the k-fold x n_trees forests and accumulate the out-of-fold
+ * Q0.16 votes of the trees it built into votes_dev [n, C] uint32 (not zeroed here).  Replaces
+ * RandomForestClassifier.fit / predict_proba per fold (SK/ensemble/_forest.py:303-522,921-967,
+ * SK/tree/_tree.pyx:139-337,939-996, _splitter.pyx:262-504, _criterion.pyx:147-199,302-486).
+ * Trees are (part = group*k + fold, t), t in [t0, t1); RNG id = gid_base + part*n_trees + t; the
+ * rank owns the trees with (part*n_trees + t) % world == rank. */
+int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* fold_dev, const int32_t* group_dev,
+                int32_t n_groups, int32_t k, int32_t n_trees, int32_t n_classes, const tst_params* params,
+                uint64_t seed, uint32_t gid_base, int32_t t0, int32_t t1, uint32_t* votes_dev, void* stream);
+
+/* (C1/K9) Sum `world` gathered vote tensors [world][n*C] in rank order into votes_out_dev. */
+int tst_reduce_votes(tst_handle* h, const uint32_t* gathered_dev, int32_t world, int64_t n_values,
+                     uint32_t* votes_out_dev, void* stream);
+
+/* (6) s(x) -- "assign each sample a bias score s(x)" (REF/README.md:35); replaces
+ * SK/ensemble/_forest.py:961-962.  s_dev [n] float32 (-1 for rows not held out);
+ * correct_dev / total_dev [n_groups*k] uint32 are zeroed then filled (may be NULL). */
+int tst_finalize(tst_handle* h, const uint32_t* votes_dev, const uint8_t* y_dev, const uint8_t* fold_dev,
+                 const int32_t* group_dev, int32_t n_groups, int32_t k, int32_t n_trees, int32_t n_classes,
+                 float* s_dev, uint32_t* correct_dev, uint32_t* total_dev, void* stream);
+
+/* (7) One IBP prune step on the device -- "filtering high-bias samples" (REF/README.md:35):
+ * clear from active_dev the `batch` rows with the largest v = votes[i][y_i] >= vmin
+ * (ties -> lowest row id); *removed_host receives the count. */
+int tst_ibp_select(tst_handle* h, const uint32_t* votes_dev, const uint8_t* y_dev, const uint8_t* fold_dev,
+                   int32_t k, int32_t n_classes, uint64_t vmin, int64_t batch, uint8_t* active_dev,
+                   int64_t* removed_host, void* stream);
+
+/* (7) Whole IBP loop kept on the device (single rank): rounds x (folds, fit, s, prune).
+ * removed_host [rounds]; s_per_round_dev [rounds][n] float32 or NULL. */
+int tst_ibp(tst_handle* h, const uint8_t* y_dev, uint8_t* active_dev, const int32_t* group_dev, int32_t n_groups,
+            int32_t k, int32_t n_trees, int32_t n_classes, const tst_params* params, uint64_t seed,
+            int32_t rounds, double tau, int64_t batch, int64_t* removed_host, float* s_per_round_dev,
+            void* stream);
+
+/* Kept forest (params.keep_forest): votes of every kept tree for new rows X_dev [n, d]
+ * (binned with the handle's edges), accumulated into votes_dev [n, C].  Replaces
+ * RandomForestClassifier.predict_proba (SK/ensemble/_forest.py:921-967). */
+int tst_predict(tst_handle* h, const float* X_dev, int64_t n, uint32_t* votes_dev, void* stream);
+
+/* Kept forest: canonical export of tree (part, t) for bit-exact comparison with the oracle.
+ * nodes_host [cap], counts_host [cap][C]; *n_nodes receives the node count (also when cap is too small,
+ * in which case TST_ERR_INVALID is returned and nothing is written). */
+int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node* nodes_host, uint32_t* counts_host,
+                    int64_t cap, int64_t* n_nodes);
+
+int tst_get_stats(tst_handle* h, tst_stats* out);
+int tst_reset_stats(tst_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TST_H_ */

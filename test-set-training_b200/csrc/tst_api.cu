@@ -1,0 +1,652 @@
+// tst_api.cu -- host side of libtst.so: the C ABI declared in include/tst.h.
+// One translation unit; kernels live in the .cuh files next to it.  sm_100a only, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tst_common.cuh"
+#include "tst_grow.cuh"
+#include "tst_prep.cuh"
+
+// --------------------------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(TST_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+            if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; return -1; }
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+#define ENSURE(buf, bytes)                                                                  \
+    do {                                                                                    \
+        if ((buf).ensure(bytes)) return fail(TST_ERR_NOMEM, std::string("cudaMalloc of ") + std::to_string((size_t)(bytes)) + " bytes for " #buf " failed"); \
+    } while (0)
+
+struct KeptTree { int32_t part, t; uint32_t arena, n_inbag; };
+
+struct tst_handle {
+    int device = 0, rank = 0, world = 1;
+    int sm_count = 148;
+    // binned table
+    int64_t n = 0, ld = 0;
+    int32_t d = 0;
+    uint32_t dstride = 0;
+    bool have_edges = false;
+    DevBuf bins_cm, bins_rm, edges, n_edges;
+    // per-fit scratch
+    DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
+        qsmall, counters, dstats, infer_parts;
+    // kept forest
+    DevBuf keep_nodes, keep_leafc, keep_arenas;
+    std::vector<KeptTree> kept;
+    int32_t kept_C = 0, kept_n_trees = 0;
+    uint64_t kept_node_stride = 0, kept_leafc_stride = 0;
+    // ibp / predict scratch
+    DevBuf ibp_fold, ibp_votes, ibp_removed, pred_cm, pred_rm;
+    uint32_t* h_pinned = nullptr;  // 16 words
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    tst_stats stats;
+    bool attrs_set = false;
+};
+
+static const int BIG_THREADS = 256;
+static const int SMALL_WARPS = 4;
+static const size_t BIG_SMEM_BUDGET = 64 * 1024;
+
+extern "C" int tst_abi_version(void) { return TST_ABI_VERSION; }
+extern "C" const char* tst_last_error(void) { return g_err.c_str(); }
+
+extern "C" int tst_create(tst_handle** out, int device, int rank, int world, const void* nccl_unique_id) {
+    if (!out || world < 1 || rank < 0 || rank >= world) return fail(TST_ERR_INVALID, "tst_create: bad arguments");
+    (void)nccl_unique_id;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(TST_ERR_CUDA, std::string("tst_create: no CUDA device (") + cudaGetErrorString(e) + "); libtst has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(TST_ERR_INVALID, "tst_create: device out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(TST_ERR_UNSUPPORTED, "tst_create: libtst is built for sm_100a (B200) only");
+    tst_handle* h = new tst_handle();
+    h->device = device; h->rank = rank; h->world = world; h->sm_count = prop.multiProcessorCount;
+    memset(&h->stats, 0, sizeof(h->stats));
+    CK(cudaMallocHost((void**)&h->h_pinned, 64));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    *out = h;
+    return TST_OK;
+}
+
+extern "C" int tst_destroy(tst_handle* h) {
+    if (!h) return TST_OK;
+    cudaSetDevice(h->device);
+    DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
+                      &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
+                      &h->qsmall, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm};
+    for (DevBuf* b : bufs) b->release();
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return TST_OK;
+}
+
+static int set_kernel_attrs(tst_handle* h) {
+    if (h->attrs_set) return 0;
+    CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET));
+    CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_bin_map, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(k_cm_to_rm, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    h->attrs_set = true;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------- binning
+static int alloc_table(tst_handle* h, int64_t n, int32_t d) {
+    if (n < 1 || n >= TST_MAX_ROWS) return fail(TST_ERR_INVALID, "table: need 1 <= n < 2^24 rows");
+    if (d < 1 || d > TST_MAX_FEATURES) return fail(TST_ERR_INVALID, "table: need 1 <= d <= 1024 features");
+    h->n = n; h->d = d;
+    h->ld = (n + 15) / 16 * 16;
+    h->dstride = (uint32_t)((d + 15) / 16 * 16);
+    ENSURE(h->bins_cm, (size_t)h->ld * d);
+    ENSURE(h->bins_rm, (size_t)n * h->dstride);
+    return 0;
+}
+
+extern "C" int tst_bin(tst_handle* h, const float* X_dev, int64_t n, int32_t d, const double* edges_host,
+                       const int32_t* n_edges_host, void* stream) {
+    if (!h || !X_dev || !edges_host || !n_edges_host) return fail(TST_ERR_INVALID, "tst_bin: null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = alloc_table(h, n, d);
+    if (rc) return rc;
+    if ((rc = set_kernel_attrs(h))) return rc;
+    for (int f = 0; f < d; ++f)
+        if (n_edges_host[f] < 0 || n_edges_host[f] > TST_MAX_EDGES) return fail(TST_ERR_INVALID, "tst_bin: n_edges out of range");
+    ENSURE(h->edges, (size_t)d * TST_MAX_EDGES * sizeof(double));
+    ENSURE(h->n_edges, (size_t)d * sizeof(int32_t));
+    CK(cudaMemcpyAsync(h->edges.p, edges_host, (size_t)d * TST_MAX_EDGES * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->n_edges.p, n_edges_host, (size_t)d * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(h->bins_rm.p, 0, (size_t)n * h->dstride, st));
+    unsigned grid = (unsigned)((n + BIN_TILE - 1) / BIN_TILE);
+    size_t smem = (size_t)d * (BIN_TILE + 4);
+    k_bin_map<<<grid, 256, smem, st>>>(X_dev, n, d, h->edges.as<double>(), h->n_edges.as<int>(), h->bins_cm.as<uint8_t>(), h->ld,
+                                       h->bins_rm.as<uint8_t>(), h->dstride);
+    CKL();
+    h->stats.kernel_launches++;
+    h->have_edges = true;
+    return TST_OK;
+}
+
+extern "C" int tst_set_bins(tst_handle* h, const uint8_t* bins_cm_dev, int64_t n, int32_t d, void* stream) {
+    if (!h || !bins_cm_dev) return fail(TST_ERR_INVALID, "tst_set_bins: null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = alloc_table(h, n, d);
+    if (rc) return rc;
+    if ((rc = set_kernel_attrs(h))) return rc;
+    CK(cudaMemsetAsync(h->bins_rm.p, 0, (size_t)n * h->dstride, st));
+    unsigned grid = (unsigned)((n + BIN_TILE - 1) / BIN_TILE);
+    size_t smem = (size_t)d * (BIN_TILE + 4);
+    k_cm_to_rm<<<grid, 256, smem, st>>>(bins_cm_dev, n, d, n, h->bins_cm.as<uint8_t>(), h->ld, h->bins_rm.as<uint8_t>(), h->dstride);
+    CKL();
+    h->stats.kernel_launches++;
+    h->have_edges = false;
+    return TST_OK;
+}
+
+extern "C" int tst_get_bins(tst_handle* h, uint8_t* out_dev, void* stream) {
+    if (!h || !out_dev) return fail(TST_ERR_INVALID, "tst_get_bins: null argument");
+    if (!h->n) return fail(TST_ERR_STATE, "tst_get_bins: no table");
+    CK(cudaSetDevice(h->device));
+    int64_t tot = h->n * h->d;
+    k_copy_cm<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->bins_cm.as<uint8_t>(), h->n, h->d, h->ld, out_dev);
+    CKL();
+    h->stats.kernel_launches++;
+    return TST_OK;
+}
+
+// --------------------------------------------------------------------------------------------- folds
+extern "C" int tst_assign_folds(tst_handle* h, const uint8_t* y_dev, const uint8_t* active_dev, const int32_t* group_dev,
+                                int32_t n_groups, int32_t k, int32_t C, uint8_t* fold_dev, void* stream) {
+    if (!h || !y_dev || !active_dev || !fold_dev) return fail(TST_ERR_INVALID, "tst_assign_folds: null argument");
+    if (!h->n) return fail(TST_ERR_STATE, "tst_assign_folds: bin the table first");
+    if (k < 1 || k > 250 || C < 1 || C > TST_MAX_CLASSES || n_groups < 1) return fail(TST_ERR_INVALID, "tst_assign_folds: bad k / classes / groups");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(fold_dev, TST_FOLD_INACTIVE, (size_t)h->n, st));
+    k_assign_folds<1024><<<n_groups, 1024, 0, st>>>(y_dev, active_dev, group_dev, h->n, k, C, fold_dev);
+    CKL();
+    h->stats.kernel_launches++;
+    return TST_OK;
+}
+
+// --------------------------------------------------------------------------------------------- fit + OOF
+struct HostTree { uint32_t part, t; };
+
+static int pull_stats(tst_handle* h, cudaStream_t st) {
+    DevStats ds;
+    CK(cudaMemcpyAsync(&ds, h->dstats.p, sizeof(ds), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->stats.row_visits_big += ds.row_visits_big; h->stats.row_visits_small += ds.row_visits_small;
+    h->stats.nodes += ds.nodes; h->stats.leaves += ds.leaves; h->stats.searched += ds.searched; h->stats.fallback += ds.fallback;
+    h->stats.inbag_rows += ds.inbag_rows; h->stats.oof_steps += ds.oof_steps;
+    h->stats.max_depth = std::max(h->stats.max_depth, ds.max_depth);
+    CK(cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats), st));
+    if (ds.error == 1) return fail(TST_ERR_OVERFLOW, "bootstrap multiplicity exceeded 255 (byte counter wrapped)");
+    if (ds.error == 2) return fail(TST_ERR_OVERFLOW, "node work queue overflowed");
+    if (ds.error == 4) return fail(TST_ERR_STATE, "internal: a chosen split left one side empty");
+    if (ds.error) return fail(TST_ERR_OVERFLOW, "device error flag " + std::to_string(ds.error));
+    return 0;
+}
+
+extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* fold_dev, const int32_t* group_dev,
+                           int32_t n_groups, int32_t k, int32_t n_trees, int32_t C, const tst_params* prm, uint64_t seed,
+                           uint32_t gid_base, int32_t t0, int32_t t1, uint32_t* votes_dev, void* stream) {
+    if (!h || !y_dev || !fold_dev || !prm) return fail(TST_ERR_INVALID, "tst_fit_oof: null argument");
+    if (!h->n) return fail(TST_ERR_STATE, "tst_fit_oof: bin the table first (tst_bin / tst_set_bins)");
+    const int64_t n = h->n;
+    const int32_t d = h->d;
+    if (k < 1 || k > 250 || n_groups < 1 || n_trees < 1 || n_trees > 65535 || C < 1 || C > TST_MAX_CLASSES || t0 < 0 || t1 > n_trees || t0 > t1)
+        return fail(TST_ERR_INVALID, "tst_fit_oof: bad k / n_trees / classes / tree range");
+    if (prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2)
+        return fail(TST_ERR_INVALID, "tst_fit_oof: bad growth parameters");
+    if ((uint64_t)n_groups * k * n_trees + gid_base > 0xFFFFFFFFull) return fail(TST_ERR_INVALID, "tst_fit_oof: tree id overflows 32 bits");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = set_kernel_attrs(h);
+    if (rc) return rc;
+
+    // ---- partitions: rows sorted by (group, fold slot, row)
+    const int np = n_groups * (k + 1);
+    ENSURE(h->part_count, (size_t)np * 4);
+    ENSURE(h->part_start, (size_t)(np + 1) * 4);
+    ENSURE(h->sorted, (size_t)n * 4);
+    ENSURE(h->dstats, sizeof(DevStats));
+    ENSURE(h->counters, 64);
+    CK(cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats), st));
+    k_part_count<1024><<<np, 1024, 0, st>>>(fold_dev, group_dev, n, k, h->part_count.as<uint32_t>());
+    CKL();
+    k_part_scan<<<1, 32, 0, st>>>(h->part_count.as<uint32_t>(), np, h->part_start.as<uint32_t>());
+    CKL();
+    k_part_scatter<1024><<<np, 1024, 0, st>>>(fold_dev, group_dev, n, k, h->part_start.as<uint32_t>(), h->sorted.as<uint32_t>());
+    CKL();
+    h->stats.kernel_launches += 3;
+    std::vector<uint32_t> ps(np + 1);
+    CK(cudaMemcpyAsync(ps.data(), h->part_start.p, (size_t)(np + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+
+    // ---- this rank's trees, ordered by partition
+    std::vector<TreeDesc> all;
+    std::vector<HostTree> all_id;
+    uint32_t max_train = 0;
+    for (int part = 0; part < n_groups * k; ++part) {
+        int g = part / k, f = part % k;
+        uint32_t gs = ps[(size_t)g * (k + 1)], ge = ps[(size_t)(g + 1) * (k + 1)];
+        uint32_t fs = ps[(size_t)g * (k + 1) + f], fe = ps[(size_t)g * (k + 1) + f + 1];
+        for (int t = t0; t < t1; ++t) {
+            uint32_t lid = (uint32_t)part * (uint32_t)n_trees + (uint32_t)t;
+            if ((int)(lid % (uint32_t)h->world) != h->rank) continue;
+            TreeDesc td;
+            memset(&td, 0, sizeof(td));
+            td.gid = gid_base + lid; td.part = (uint32_t)part; td.gs = gs; td.a = fs - gs; td.fsz = fe - fs;
+            td.n_train = (ge - gs) - (fe - fs); td.fs = fs;
+            max_train = std::max(max_train, td.n_train);
+            all.push_back(td);
+            all_id.push_back({(uint32_t)part, (uint32_t)t});
+        }
+    }
+    const size_t total_trees = all.size();
+    h->kept.clear();
+    if (total_trees == 0) return TST_OK;
+
+    // ---- sizes (everything for B trees in flight stays resident in HBM)
+    const uint64_t n_cap = std::max<uint64_t>(4, ((uint64_t)max_train + 3) / 4 * 4);
+    const uint64_t n_pad = (uint64_t)h->ld;
+    const uint32_t n_chunks = (uint32_t)((n_pad + BOOT_CHUNK - 1) / BOOT_CHUNK);
+    const uint64_t node_stride = 2 * n_cap;
+    const uint64_t leafc_stride = (n_cap / 2 + 1) * (uint64_t)C;
+    const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / 8 + 2;
+    const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 2 * n_cap * 4 + (2 * qbig_per + qsmall_per) * sizeof(Task) + sizeof(TreeDesc);
+    const bool keep = prm->keep_forest != 0;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
+                     h->qbig0.cap + h->qbig1.cap + h->qsmall.cap + h->keep_nodes.cap + h->keep_leafc.cap;
+    size_t budget = (size_t)((free_b + reclaim) * 0.6);
+    if (keep) {
+        size_t need = total_trees * arena_bytes;
+        if (need > budget) return fail(TST_ERR_NOMEM, "keep_forest: node arrays of " + std::to_string(total_trees) + " trees (" + std::to_string(need >> 20) + " MiB) do not fit");
+        budget -= need;
+    }
+    size_t per_tree = work_bytes + (keep ? 0 : arena_bytes);
+    size_t B = std::min<size_t>(total_trees, std::max<size_t>(1, budget / per_tree));
+    B = std::min<size_t>(B, 4096);
+    if (prm->trees_in_flight > 0) B = std::min<size_t>(B, (size_t)prm->trees_in_flight);
+
+    ENSURE(h->trees, B * sizeof(TreeDesc));
+    ENSURE(h->counts8, B * n_pad);
+    ENSURE(h->chunk_cnt, B * (size_t)n_chunks * 4);
+    ENSURE(h->chunk_sum, B * (size_t)n_chunks * 4);
+    ENSURE(h->entA, B * n_cap * 4);
+    ENSURE(h->entB, B * n_cap * 4);
+    ENSURE(h->qbig0, B * qbig_per * sizeof(Task));
+    ENSURE(h->qbig1, B * qbig_per * sizeof(Task));
+    ENSURE(h->qsmall, B * qsmall_per * sizeof(Task));
+    ENSURE(h->infer_parts, (size_t)n_groups * k * sizeof(InferPart));
+    uint2* nodes_p; uint32_t* leafc_p;
+    if (keep) {
+        ENSURE(h->keep_nodes, total_trees * node_stride * sizeof(uint2));
+        ENSURE(h->keep_leafc, total_trees * leafc_stride * 4);
+        nodes_p = h->keep_nodes.as<uint2>(); leafc_p = h->keep_leafc.as<uint32_t>();
+        h->kept_C = C; h->kept_n_trees = n_trees; h->kept_node_stride = node_stride; h->kept_leafc_stride = leafc_stride;
+    } else {
+        ENSURE(h->nodes, B * node_stride * sizeof(uint2));
+        ENSURE(h->leafc, B * leafc_stride * 4);
+        nodes_p = h->nodes.as<uint2>(); leafc_p = h->leafc.as<uint32_t>();
+    }
+
+    GrowCtx g;
+    memset(&g, 0, sizeof(g));
+    g.bins_rm = h->bins_rm.as<uint8_t>(); g.y = y_dev; g.dstride = h->dstride; g.d = d; g.C = C; g.m = prm->max_features;
+    g.max_depth = prm->max_depth; g.mss = (uint32_t)prm->min_samples_split; g.msl = (uint32_t)prm->min_samples_leaf;
+    g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
+    g.entA = h->entA.as<uint32_t>(); g.entB = h->entB.as<uint32_t>(); g.n_cap = n_cap;
+    g.nodes = nodes_p; g.node_stride = node_stride; g.leafc = leafc_p; g.leafc_stride = leafc_stride;
+    g.trees = h->trees.as<TreeDesc>();
+    g.qsmall = h->qsmall.as<Task>();
+    g.stats = h->dstats.as<DevStats>();
+    g.FS = 32 * (8 * C + 1);
+    g.MB = (int)std::min<size_t>(std::min<size_t>(32, (size_t)g.m), std::max<size_t>(1, BIG_SMEM_BUDGET / ((size_t)g.FS * 4)));
+    const size_t big_smem = (size_t)g.MB * g.FS * 4;
+    if (big_smem > BIG_SMEM_BUDGET) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
+    const uint32_t small_per_warp = (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
+    const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
+    uint32_t* counters = h->counters.as<uint32_t>();  // [0],[1] big queue counts, [2] small count
+
+    for (size_t b0 = 0; b0 < total_trees; b0 += B) {
+        const uint32_t nb = (uint32_t)std::min(B, total_trees - b0);
+        for (uint32_t i = 0; i < nb; ++i) all[b0 + i].arena = keep ? (uint32_t)(b0 + i) : i;
+        CK(cudaMemcpyAsync(h->trees.p, all.data() + b0, (size_t)nb * sizeof(TreeDesc), cudaMemcpyHostToDevice, st));
+        g.qbig_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qbig_per);
+        g.qsmall_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qsmall_per);
+
+        // ---- bootstrap + compaction
+        CK(cudaEventRecord(h->ev0, st));
+        CK(cudaMemsetAsync(h->counts8.p, 0, (size_t)nb * n_pad, st));
+        CK(cudaMemsetAsync(counters, 0, 64, st));
+        {
+            uint32_t blocks4 = (max_train + 3) / 4;
+            dim3 grid((blocks4 + 255) / 256, nb);
+            if (grid.x) k_boot_draw<<<grid, 256, 0, st>>>(g.trees, h->sorted.as<uint32_t>(), h->counts8.as<uint32_t>(), n_pad, g.k0, g.k1);
+            CKL();
+            dim3 gridc(n_chunks, nb);
+            k_boot_count<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), h->chunk_sum.as<uint32_t>());
+            CKL();
+            k_boot_scan<<<nb, 256, 0, st>>>(g.trees, n_chunks, h->chunk_cnt.as<uint32_t>(), h->chunk_sum.as<uint32_t>(), g.stats);
+            CKL();
+            k_boot_scatter<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), g.entA, n_cap);
+            CKL();
+            g.qnext = nullptr; g.qnext_count = nullptr;
+            k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb, h->qbig0.as<Task>(), counters + 0);
+            CKL();
+            h->stats.kernel_launches += 5;
+        }
+        CK(cudaEventRecord(h->ev1, st));
+        CK(cudaMemcpyAsync(h->h_pinned, counters, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_prep += ms; }
+
+        // ---- level-synchronous growth of the nodes with > 32 rows
+        int cur = 0;
+        uint64_t level_guard = 0;
+        uint32_t nbig = h->h_pinned[0];
+        while (nbig > 0) {
+            Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
+            g.qnext = cur ? h->qbig0.as<Task>() : h->qbig1.as<Task>();
+            g.qnext_count = counters + (cur ^ 1);
+            CK(cudaMemsetAsync(g.qnext_count, 0, 4, st));
+            CK(cudaEventRecord(h->ev0, st));
+            k_grow_big<BIG_THREADS><<<nbig, BIG_THREADS, big_smem, st>>>(g, qcur, nbig);
+            CKL();
+            CK(cudaEventRecord(h->ev1, st));
+            CK(cudaMemcpyAsync(h->h_pinned, counters, 16, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_big += ms; }
+            h->stats.kernel_launches++; h->stats.launches_grow_big++; h->stats.levels++;
+            cur ^= 1;
+            nbig = h->h_pinned[cur];
+            if (++level_guard > n_cap + 2) return fail(TST_ERR_STATE, "tree growth did not terminate");
+            if (nbig > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "big-node queue overflowed");
+        }
+        // ---- subtrees with <= 32 rows: one warp each
+        const uint32_t nsmall = h->h_pinned[2];
+        if (nsmall > g.qsmall_cap) return fail(TST_ERR_OVERFLOW, "small-node queue overflowed");
+        if (nsmall) {
+            uint32_t blocks = (nsmall + SMALL_WARPS - 1) / SMALL_WARPS;
+            blocks = std::min<uint32_t>(blocks, (uint32_t)h->sm_count * 64u);
+            CK(cudaEventRecord(h->ev0, st));
+            k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            CKL();
+            CK(cudaEventRecord(h->ev1, st));
+            h->stats.kernel_launches++; h->stats.launches_grow_small++;
+        }
+        // ---- OOF inference of this batch's trees on their held-out rows
+        std::vector<InferPart> ips;
+        uint32_t max_fsz = 0;
+        for (uint32_t i = 0; i < nb;) {
+            uint32_t j = i;
+            while (j < nb && all[b0 + j].part == all[b0 + i].part) ++j;
+            if (all[b0 + i].fsz) {
+                ips.push_back({all[b0 + i].fs, all[b0 + i].fsz, i, j});
+                max_fsz = std::max(max_fsz, all[b0 + i].fsz);
+            }
+            i = j;
+        }
+        cudaEvent_t evi0 = nullptr, evi1 = nullptr;
+        if (votes_dev && !ips.empty()) {
+            CK(cudaMemcpyAsync(h->infer_parts.p, ips.data(), ips.size() * sizeof(InferPart), cudaMemcpyHostToDevice, st));
+            CK(cudaEventCreate(&evi0)); CK(cudaEventCreate(&evi1));
+            CK(cudaEventRecord(evi0, st));
+            dim3 grid((max_fsz + 255) / 256, (unsigned)ips.size());
+            k_oof_infer<<<grid, 256, 0, st>>>(g, h->infer_parts.as<InferPart>(), h->sorted.as<uint32_t>(), votes_dev);
+            CKL();
+            CK(cudaEventRecord(evi1, st));
+            h->stats.kernel_launches++;
+        }
+        CK(cudaStreamSynchronize(st));
+        if (nsmall) { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_small += ms; }
+        if (evi0) {
+            float ms = 0; cudaEventElapsedTime(&ms, evi0, evi1); h->stats.ms_infer += ms;
+            cudaEventDestroy(evi0); cudaEventDestroy(evi1);
+        }
+        if (keep) {
+            std::vector<TreeDesc> back(nb);
+            CK(cudaMemcpy(back.data(), h->trees.p, (size_t)nb * sizeof(TreeDesc), cudaMemcpyDeviceToHost));
+            for (uint32_t i = 0; i < nb; ++i)
+                h->kept.push_back({(int32_t)all_id[b0 + i].part, (int32_t)all_id[b0 + i].t, back[i].arena, back[i].n_inbag});
+        }
+        h->stats.trees += nb;
+        if ((rc = pull_stats(h, st))) return rc;
+    }
+    return TST_OK;
+}
+
+// --------------------------------------------------------------------------------------------- votes -> s(x)
+extern "C" int tst_reduce_votes(tst_handle* h, const uint32_t* gathered_dev, int32_t world, int64_t nv, uint32_t* out_dev, void* stream) {
+    if (!h || !gathered_dev || !out_dev || world < 1 || nv < 0) return fail(TST_ERR_INVALID, "tst_reduce_votes: bad argument");
+    CK(cudaSetDevice(h->device));
+    if (nv) k_reduce_votes<<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gathered_dev, world, nv, out_dev);
+    CKL();
+    h->stats.kernel_launches++;
+    return TST_OK;
+}
+
+extern "C" int tst_finalize(tst_handle* h, const uint32_t* votes_dev, const uint8_t* y_dev, const uint8_t* fold_dev,
+                            const int32_t* group_dev, int32_t n_groups, int32_t k, int32_t n_trees, int32_t C, float* s_dev,
+                            uint32_t* correct_dev, uint32_t* total_dev, void* stream) {
+    if (!h || !votes_dev || !y_dev || !fold_dev) return fail(TST_ERR_INVALID, "tst_finalize: null argument");
+    if (!h->n) return fail(TST_ERR_STATE, "tst_finalize: no table");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (correct_dev) CK(cudaMemsetAsync(correct_dev, 0, (size_t)n_groups * k * 4, st));
+    if (total_dev) CK(cudaMemsetAsync(total_dev, 0, (size_t)n_groups * k * 4, st));
+    double denom = (double)n_trees * 65536.0;
+    k_finalize<<<(unsigned)((h->n + 255) / 256), 256, 0, st>>>(votes_dev, y_dev, fold_dev, group_dev, h->n, C, k, denom, s_dev, correct_dev, total_dev);
+    CKL();
+    h->stats.kernel_launches++;
+    return TST_OK;
+}
+
+// --------------------------------------------------------------------------------------------- IBP
+extern "C" int tst_ibp_select(tst_handle* h, const uint32_t* votes_dev, const uint8_t* y_dev, const uint8_t* fold_dev, int32_t k,
+                              int32_t C, uint64_t vmin, int64_t batch, uint8_t* active_dev, int64_t* removed_host, void* stream) {
+    if (!h || !votes_dev || !y_dev || !fold_dev || !active_dev || !removed_host) return fail(TST_ERR_INVALID, "tst_ibp_select: null argument");
+    if (!h->n) return fail(TST_ERR_STATE, "tst_ibp_select: no table");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ENSURE(h->ibp_removed, 8);
+    k_ibp_select<1024><<<1, 1024, 0, st>>>(votes_dev, y_dev, fold_dev, h->n, C, k, (unsigned long long)vmin, (long long)batch, active_dev,
+                                          h->ibp_removed.as<long long>());
+    CKL();
+    h->stats.kernel_launches++;
+    long long r = 0;
+    CK(cudaMemcpyAsync(&r, h->ibp_removed.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *removed_host = r;
+    return TST_OK;
+}
+
+__global__ void k_fill_f32(float* p, int64_t n, float v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+extern "C" int tst_ibp(tst_handle* h, const uint8_t* y_dev, uint8_t* active_dev, const int32_t* group_dev, int32_t n_groups,
+                       int32_t k, int32_t n_trees, int32_t C, const tst_params* prm, uint64_t seed, int32_t rounds, double tau,
+                       int64_t batch, int64_t* removed_host, float* s_per_round_dev, void* stream) {
+    if (!h || !y_dev || !active_dev || !prm || !removed_host || rounds < 1) return fail(TST_ERR_INVALID, "tst_ibp: bad argument");
+    if (!h->n) return fail(TST_ERR_STATE, "tst_ibp: bin the table first");
+    if (h->world != 1) return fail(TST_ERR_UNSUPPORTED, "tst_ibp: multi-rank IBP is driven by the host (see INTEGRATION.md)");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = h->n;
+    ENSURE(h->ibp_fold, (size_t)n);
+    ENSURE(h->ibp_votes, (size_t)n * C * 4);
+    const uint64_t vmin = (uint64_t)std::ceil(tau * (double)n_trees * 65536.0);
+    const uint64_t per_round = (uint64_t)n_groups * k * n_trees;
+    if (per_round * rounds > 0xFFFFFFFFull) return fail(TST_ERR_INVALID, "tst_ibp: tree id overflows 32 bits");
+    for (int r = 0; r < rounds; ++r) removed_host[r] = 0;
+    if (s_per_round_dev) {
+        int64_t tot = (int64_t)rounds * n;
+        k_fill_f32<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(s_per_round_dev, tot, -1.0f);
+        CKL();
+    }
+    for (int r = 0; r < rounds; ++r) {
+        int rc = tst_assign_folds(h, y_dev, active_dev, group_dev, n_groups, k, C, h->ibp_fold.as<uint8_t>(), stream);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(h->ibp_votes.p, 0, (size_t)n * C * 4, st));
+        rc = tst_fit_oof(h, y_dev, h->ibp_fold.as<uint8_t>(), group_dev, n_groups, k, n_trees, C, prm, seed, (uint32_t)(r * per_round), 0,
+                         n_trees, h->ibp_votes.as<uint32_t>(), stream);
+        if (rc) return rc;
+        if (s_per_round_dev) {
+            rc = tst_finalize(h, h->ibp_votes.as<uint32_t>(), y_dev, h->ibp_fold.as<uint8_t>(), group_dev, n_groups, k, n_trees, C,
+                              s_per_round_dev + (size_t)r * n, nullptr, nullptr, stream);
+            if (rc) return rc;
+        }
+        int64_t took = 0;
+        rc = tst_ibp_select(h, h->ibp_votes.as<uint32_t>(), y_dev, h->ibp_fold.as<uint8_t>(), k, C, vmin, batch, active_dev, &took, stream);
+        if (rc) return rc;
+        removed_host[r] = took;
+        if (!took) break;
+    }
+    return TST_OK;
+}
+
+// --------------------------------------------------------------------------------------------- kept forest
+extern "C" int tst_predict(tst_handle* h, const float* X_dev, int64_t n, uint32_t* votes_dev, void* stream) {
+    if (!h || !X_dev || !votes_dev || n < 1) return fail(TST_ERR_INVALID, "tst_predict: bad argument");
+    if (h->kept.empty()) return fail(TST_ERR_STATE, "tst_predict: no kept forest (fit with keep_forest = 1)");
+    if (!h->have_edges) return fail(TST_ERR_STATE, "tst_predict: the table was not binned by tst_bin, no edges to bin new rows with");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d = h->d;
+    int64_t ld = (n + 15) / 16 * 16;
+    ENSURE(h->pred_cm, (size_t)ld * d);
+    ENSURE(h->pred_rm, (size_t)n * h->dstride);
+    CK(cudaMemsetAsync(h->pred_rm.p, 0, (size_t)n * h->dstride, st));
+    k_bin_map<<<(unsigned)((n + BIN_TILE - 1) / BIN_TILE), 256, (size_t)d * (BIN_TILE + 4), st>>>(
+        X_dev, n, d, h->edges.as<double>(), h->n_edges.as<int>(), h->pred_cm.as<uint8_t>(), ld, h->pred_rm.as<uint8_t>(), h->dstride);
+    CKL();
+    std::vector<uint32_t> arenas;
+    for (auto& kt : h->kept) arenas.push_back(kt.arena);
+    ENSURE(h->keep_arenas, arenas.size() * 4);
+    CK(cudaMemcpyAsync(h->keep_arenas.p, arenas.data(), arenas.size() * 4, cudaMemcpyHostToDevice, st));
+    k_predict<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pred_rm.as<uint8_t>(), h->dstride, n, h->kept_C, h->keep_nodes.as<uint2>(),
+                                                         h->kept_node_stride, h->keep_leafc.as<uint32_t>(), h->kept_leafc_stride,
+                                                         h->keep_arenas.as<uint32_t>(), (uint32_t)arenas.size(), votes_dev);
+    CKL();
+    CK(cudaStreamSynchronize(st));  // `arenas` is a stack-owned staging buffer
+    h->stats.kernel_launches += 2;
+    return TST_OK;
+}
+
+extern "C" int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node* nodes_host, uint32_t* counts_host, int64_t cap,
+                               int64_t* n_nodes) {
+    if (!h || !n_nodes) return fail(TST_ERR_INVALID, "tst_export_tree: null argument");
+    const KeptTree* kt = nullptr;
+    for (auto& x : h->kept) if (x.part == part && x.t == t) { kt = &x; break; }
+    if (!kt) return fail(TST_ERR_STATE, "tst_export_tree: tree not kept (keep_forest = 0, other rank, or out of range)");
+    CK(cudaSetDevice(h->device));
+    const int C = h->kept_C;
+    const uint64_t nslots = std::max<uint64_t>(1, 2ull * kt->n_inbag);
+    const uint64_t nleafc = ((uint64_t)kt->n_inbag / 2 + 1) * C;
+    std::vector<uint2> nodes(nslots);
+    std::vector<uint32_t> leafc(nleafc);
+    CK(cudaMemcpy(nodes.data(), h->keep_nodes.as<uint2>() + (uint64_t)kt->arena * h->kept_node_stride, nslots * sizeof(uint2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(leafc.data(), h->keep_leafc.as<uint32_t>() + (uint64_t)kt->arena * h->kept_leafc_stride, nleafc * 4, cudaMemcpyDeviceToHost));
+    struct Item { uint32_t slot, begin, end, depth; };
+    std::vector<Item> q;
+    q.push_back({0, 0, kt->n_inbag, 0});
+    std::vector<tst_node> out;
+    std::vector<uint32_t> cnt;
+    for (size_t i = 0; i < q.size(); ++i) {
+        Item it = q[i];
+        if (it.slot >= nslots) return fail(TST_ERR_STATE, "tst_export_tree: corrupt node slot");
+        uint2 rec = nodes[it.slot];
+        uint32_t kind = rec.y >> 30;
+        tst_node nd;
+        nd.left = nd.right = -1; nd.feature = -1; nd.bin = -1;
+        nd.begin = it.begin; nd.end = it.end; nd.depth = it.depth; nd.n_weighted = 0;
+        cnt.resize(cnt.size() + C, 0u);
+        uint32_t* c = cnt.data() + i * C;
+        if (kind == KIND_INTERNAL) {
+            uint32_t nl = (rec.x - it.slot) / 2;
+            if (rec.x <= it.slot || nl == 0 || it.begin + nl >= it.end) return fail(TST_ERR_STATE, "tst_export_tree: corrupt internal node");
+            nd.feature = (int32_t)((rec.y >> 8) & 0xFFFFu); nd.bin = (int32_t)(rec.y & 0xFFu);
+            nd.left = (int32_t)q.size(); nd.right = (int32_t)q.size() + 1;
+            q.push_back({it.slot + 1, it.begin, it.begin + nl, it.depth + 1});
+            q.push_back({rec.x, it.begin + nl, it.end, it.depth + 1});
+        } else if (kind == KIND_PURE) {
+            c[rec.y & 0xFFu] = rec.x; nd.n_weighted = rec.x;
+        } else if (kind == KIND_MIXED) {
+            for (int k2 = 0; k2 < C; ++k2) { c[k2] = leafc[(uint64_t)rec.x * C + k2]; nd.n_weighted += c[k2]; }
+        } else {
+            return fail(TST_ERR_STATE, "tst_export_tree: unwritten node slot " + std::to_string(it.slot));
+        }
+        out.push_back(nd);
+    }
+    for (size_t i = out.size(); i-- > 0;) {
+        if (out[i].left >= 0) {
+            for (int k2 = 0; k2 < C; ++k2) cnt[i * C + k2] = cnt[(size_t)out[i].left * C + k2] + cnt[(size_t)out[i].right * C + k2];
+            out[i].n_weighted = out[out[i].left].n_weighted + out[out[i].right].n_weighted;
+        }
+    }
+    *n_nodes = (int64_t)out.size();
+    if (!nodes_host || !counts_host || cap < (int64_t)out.size()) return fail(TST_ERR_INVALID, "tst_export_tree: capacity too small");
+    memcpy(nodes_host, out.data(), out.size() * sizeof(tst_node));
+    memcpy(counts_host, cnt.data(), out.size() * C * 4);
+    return TST_OK;
+}
+
+extern "C" int tst_get_stats(tst_handle* h, tst_stats* out) {
+    if (!h || !out) return fail(TST_ERR_INVALID, "tst_get_stats: null argument");
+    *out = h->stats;
+    return TST_OK;
+}
+
+extern "C" int tst_reset_stats(tst_handle* h) {
+    if (!h) return fail(TST_ERR_INVALID, "tst_reset_stats: null argument");
+    memset(&h->stats, 0, sizeof(h->stats));
+    return TST_OK;
+}

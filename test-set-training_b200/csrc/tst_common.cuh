@@ -1,0 +1,121 @@
+// tst_common.cuh -- shared device-side definitions for libtst.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tst.h"
+
+#define TST_PURPOSE_BOOT 1u
+#define TST_PURPOSE_FEAT 2u
+
+#define KIND_INTERNAL 1u
+#define KIND_PURE 2u
+#define KIND_MIXED 3u
+#define ROW_MASK 0x00FFFFFFu
+#define SMALL_MAX 32u  // nodes with <= 32 distinct rows are finished by one warp (k_grow_small)
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Random123; constants as CUDA/curand_philox4x32_x.h:88-91).  Counter-based:
+// every draw is a pure function of (seed, tree id, node id, purpose), so trees are
+// schedule-independent and identical on the CPU oracle.
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__host__ __device__ __forceinline__ uint32_t pick4(const uint4& v, uint32_t i) {
+    return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+__device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+
+// ---------------------------------------------------------------------------------------------
+struct Task {  // 32 B, one node waiting for a split search
+    uint32_t tree;   // batch-local tree index
+    uint32_t begin;  // segment [begin, end) of the tree's in-bag entry list
+    uint32_t end;
+    uint32_t depth;
+    uint32_t slot;   // node slot: left child = slot + 1, right child = slot + 2 * (distinct rows going left)
+    uint32_t pad0, pad1, pad2;
+};
+
+struct TreeDesc {  // one tree of the batch in flight
+    uint32_t gid;      // RNG id = gid_base + part * n_trees + t
+    uint32_t part;     // group * k + fold
+    uint32_t gs;       // start of the group's rows in `sorted`
+    uint32_t a;        // rows of the group sorted before the held-out fold
+    uint32_t fsz;      // held-out fold size
+    uint32_t n_train;  // bootstrap draws
+    uint32_t fs;       // held-out rows are sorted[fs .. fs + fsz)
+    uint32_t arena;    // node-arena slot (batch-local unless keep_forest)
+    uint32_t n_inbag;  // distinct in-bag rows (written by k_boot_scan)
+    uint32_t pad;
+};
+
+struct DevStats {
+    unsigned long long row_visits_big, row_visits_small, nodes, leaves, searched, fallback, oof_steps, inbag_rows;
+    uint32_t max_depth;
+    uint32_t error;  // sticky: 1 = multiplicity overflow, 2 = queue overflow, 3 = bootstrap weight mismatch
+};
+
+struct GrowCtx {
+    const uint8_t* bins_rm;  // [n][dstride]
+    const uint8_t* y;
+    uint32_t dstride;
+    int32_t d, C, m;
+    int32_t max_depth;
+    uint32_t mss, msl;
+    uint32_t k0, k1;  // Philox key = seed
+    uint32_t* entA;   // [trees][n_cap] ping
+    uint32_t* entB;   // pong
+    uint64_t n_cap;
+    uint2* nodes;     // [arena slots][node_stride]
+    uint64_t node_stride;
+    uint32_t* leafc;  // [arena slots][leafc_stride]
+    uint64_t leafc_stride;
+    TreeDesc* trees;
+    Task* qnext;      // big-node queue for the next level
+    uint32_t* qnext_count;
+    uint32_t qbig_cap;
+    Task* qsmall;
+    uint32_t* qsmall_count;
+    uint32_t qsmall_cap;
+    DevStats* stats;
+    int32_t MB;       // features per shared-histogram batch
+    int32_t FS;       // histogram words per feature = 32 * (8 * C + 1)
+};
+
+__device__ __forceinline__ uint32_t hist_index(uint32_t bin, uint32_t cls, uint32_t C) {
+    // 8 bins per lane, lane stride 8C+1 words: the split scan reads without bank conflicts
+    return (bin >> 3) * (8u * C + 1u) + (bin & 7u) * C + cls;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ double gini_gain(unsigned long long SL, uint32_t NL, unsigned long long SR, uint32_t NR) {
+    // sklearn's Gini proxy (SK/tree/_criterion.pyx:147-163,661-687) minus a per-node constant:
+    // two IEEE divisions and one add -- no multiply, so nothing can be contracted into an FMA.
+    return __dadd_rn(__ddiv_rn(__ull2double_rn(SL), __uint2double_rn(NL)),
+                     __ddiv_rn(__ull2double_rn(SR), __uint2double_rn(NR)));
+}
+
+__device__ __forceinline__ void queue_push(Task* q, uint32_t* count, uint32_t cap, DevStats* st, const Task& t) {
+    uint32_t i = atomicAdd(count, 1u);
+    if (i < cap) q[i] = t; else st->error = 2;
+}

@@ -1,0 +1,480 @@
+// tst_grow.cuh -- tree growth kernels (north_star items 2-5): per-node feature draw, class
+// histogram, Gini split search, row partition, node records.
+//
+//   k_grow_big   one CTA per node with > 32 distinct rows: shared-memory histogram -> warp-shuffle
+//                prefix scan -> fp64 gain -> block partition -> children.  HBM/L2-gather bound.
+//   k_grow_small one warp per node with <= 32 rows: finishes the whole subtree in registers.
+//
+// Arithmetic restated from SK/tree/_splitter.pyx:262-504, _criterion.pyx:147-199,302-486,
+// _partitioner.pyx:248-279, _tree.pyx:139-337 in the histogram form of
+// SK/ensemble/_hist_gradient_boosting/histogram.pyx:336-480 / splitting.pyx:606-716;
+// the normative spec is DESIGN.md section 2, the bit-exact checker is oracle/hist_rf.c.
+#pragma once
+#include "tst_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// leaf / node record helpers
+__device__ __forceinline__ void write_internal(uint2* nodes, uint32_t slot, uint32_t right_slot, uint32_t f, uint32_t b) {
+    nodes[slot] = make_uint2(right_slot, (KIND_INTERNAL << 30) | (f << 8) | b);
+}
+__device__ __forceinline__ void write_pure_leaf(uint2* nodes, uint32_t slot, uint32_t N, uint32_t cls) {
+    nodes[slot] = make_uint2(N, (KIND_PURE << 30) | cls);
+}
+__device__ __forceinline__ void write_mixed_leaf(uint2* nodes, uint32_t slot, uint32_t begin) {
+    nodes[slot] = make_uint2(begin >> 1, (KIND_MIXED << 30));
+}
+
+__device__ __forceinline__ bool stop_rule(const GrowCtx& g, uint32_t N, uint32_t depth, bool pure) {
+    // SK/tree/_tree.pyx:230-240 on bootstrap-weighted counts
+    return pure || N < g.mss || N < 2u * g.msl || (g.max_depth > 0 && depth >= (uint32_t)g.max_depth);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split scan of one feature histogram by one warp.  Lane l owns bins [8l, 8l+8).  Per class: local
+// inclusive prefix, warp-shuffle exclusive scan of the lane totals, then L/R sums of squares are
+// accumulated exactly in uint64.  Returns the warp-wide best (gain, bin) with ties -> lowest bin.
+__device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, int C, uint32_t msl, uint32_t lane,
+                                             double& best_gain, uint32_t& best_bin, uint32_t* tot_out, uint32_t* N_out) {
+    unsigned long long sL[8], sR[8];
+    uint32_t nL[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sL[i] = 0; sR[i] = 0; nL[i] = 0; }
+    uint32_t occ = 0, N = 0;
+    const uint32_t* hl = hf + lane * (8u * C + 1u);
+    for (int c = 0; c < C; ++c) {
+        uint32_t p[8], run = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t h = hl[i * C + c];
+            occ |= (h ? 1u : 0u) << i;
+            run += h;
+            p[i] = run;
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= (uint32_t)off) incl += t;
+        }
+        uint32_t excl = incl - run;
+        uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        N += tot;
+        if (tot_out && lane == 0) tot_out[c] = tot;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t L = excl + p[i], R = tot - L;
+            sL[i] += (unsigned long long)L * L;
+            sR[i] += (unsigned long long)R * R;
+            nL[i] += L;
+        }
+    }
+    if (N_out && lane == 0) *N_out = N;
+    double bg = -1.0;
+    uint32_t bb = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if ((occ >> i) & 1u) {  // an empty bin repeats the previous partition and would lose the tie anyway
+            uint32_t NL = nL[i], NR = N - NL;
+            if (NL >= msl && NR >= msl) {
+                double gn = gini_gain(sL[i], NL, sR[i], NR);
+                if (gn > bg) { bg = gn; bb = lane * 8u + i; }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        double og = __shfl_xor_sync(0xffffffffu, bg, off);
+        uint32_t ob = __shfl_xor_sync(0xffffffffu, bb, off);
+        if (og > bg || (og == bg && ob < bb)) { bg = og; bb = ob; }
+    }
+    best_gain = bg;
+    best_bin = bb;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+    constexpr int NW = THREADS / 32;
+    extern __shared__ uint32_t s_hist[];  // [MB][FS]
+    __shared__ uint16_t s_perm[TST_MAX_FEATURES];
+    __shared__ uint32_t s_tot[TST_MAX_CLASSES];
+    __shared__ uint32_t s_bestL[TST_MAX_CLASSES];
+    __shared__ double s_fgain[32];
+    __shared__ uint32_t s_fbin[32];
+    __shared__ uint32_t s_feat[32];
+    __shared__ uint32_t s_wl[2][NW], s_wr[2][NW];
+    __shared__ double s_bgain;
+    __shared__ uint32_t s_bkey, s_found, s_newj, s_N, s_stop;
+
+    if (blockIdx.x >= ntasks) return;
+    const Task t = tasks[blockIdx.x];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const int C = g.C, d = g.d, m = g.m;
+    const TreeDesc td = g.trees[t.tree];
+    const uint32_t* __restrict__ ent_in = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+    uint32_t* __restrict__ ent_out = ((t.depth & 1u) ? g.entA : g.entB) + (uint64_t)t.tree * g.n_cap;
+    uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
+    uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
+    const uint8_t* __restrict__ bins = g.bins_rm;
+    const uint8_t* __restrict__ y = g.y;
+    const uint32_t dstride = g.dstride;
+
+    for (int f = tid; f < d; f += THREADS) s_perm[f] = (uint16_t)f;
+    if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; }
+    __syncthreads();
+
+    int pos = 0;
+    while (pos < d) {
+        if (pos >= m && s_found) break;
+        const bool primary = pos < m;
+        const int nb = min(g.MB, (primary ? m : d) - pos);
+        // ---- per-node feature draw: partial Fisher-Yates keyed by (begin, depth, tree)
+        if (tid == 0) {
+            uint4 rnd = make_uint4(0, 0, 0, 0);
+            for (int i = pos; i < pos + nb; ++i) {
+                if (i == pos || (i & 3) == 0)
+                    rnd = philox4x32_10(t.begin, t.depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);
+                int j = i + (int)mulhi32(pick4(rnd, i & 3), (uint32_t)(d - i));
+                uint16_t fj = s_perm[j];
+                s_perm[j] = s_perm[i];
+                s_perm[i] = fj;
+                s_feat[i - pos] = fj;
+            }
+            s_newj = 0xFFFFFFFFu;
+            if (pos == m) atomicAdd(&g.stats->fallback, 1ull);
+        }
+        for (int i = tid; i < nb * g.FS; i += THREADS) s_hist[i] = 0;
+        __syncthreads();
+
+        // ---- class histogram: hist[j][bin][class] += multiplicity (SK/.../histogram.pyx:336-425 pattern)
+        {
+            constexpr int U = 4;
+            for (uint32_t base = t.begin + tid; base < t.end; base += THREADS * U) {
+                uint32_t e[U], cls[U];
+                const uint8_t* rp[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    uint32_t idx = base + u * THREADS;
+                    e[u] = idx < t.end ? ent_in[idx] : 0u;  // multiplicity 0 = padding
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    uint32_t row = e[u] & ROW_MASK;
+                    rp[u] = bins + (uint64_t)row * dstride;
+                    cls[u] = e[u] ? y[row] : 0u;
+                }
+                for (int jj = 0; jj < nb; ++jj) {
+                    int j = jj + (int)lane;  // rotate features across lanes: spreads the shared atomics
+                    j = j % nb;
+                    uint32_t f = s_feat[j];
+                    uint32_t b[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) b[u] = e[u] ? rp[u][f] : 0u;
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (e[u]) atomicAdd(&s_hist[j * g.FS + hist_index(b[u], cls[u], C)], e[u] >> 24);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- Gini split search: one warp per feature
+        for (int j = wid; j < nb; j += NW) {
+            double bg; uint32_t bb;
+            bool want_tot = (pos == 0 && j == 0);
+            scan_feature(s_hist + j * g.FS, C, g.msl, lane, bg, bb, want_tot ? s_tot : nullptr, want_tot ? &s_N : nullptr);
+            if (lane == 0) { s_fgain[j] = bg; s_fbin[j] = bb; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (pos == 0) {
+                bool pure = false;
+                for (int c = 0; c < C; ++c) pure |= (s_tot[c] == s_N);
+                if (stop_rule(g, s_N, t.depth, pure)) s_stop = 1;
+            }
+            if (primary) {
+                for (int j = 0; j < nb; ++j) {
+                    if (s_fbin[j] == 0xFFFFFFFFu) continue;
+                    uint32_t key = (s_feat[j] << 8) | s_fbin[j];  // ties: lowest feature, then lowest bin
+                    if (s_fgain[j] > s_bgain || (s_fgain[j] == s_bgain && key < s_bkey)) {
+                        s_bgain = s_fgain[j]; s_bkey = key; s_newj = j; s_found = 1;
+                    }
+                }
+            } else {
+                for (int j = 0; j < nb; ++j) {
+                    if (s_fbin[j] == 0xFFFFFFFFu) continue;
+                    s_bgain = s_fgain[j]; s_bkey = (s_feat[j] << 8) | s_fbin[j]; s_newj = j; s_found = 1;
+                    break;  // fallback: first feature in draw order with a valid split
+                }
+            }
+        }
+        __syncthreads();
+        if (s_stop) break;
+        if (s_newj != 0xFFFFFFFFu) {
+            // left class counts of the new best split, kept because the histogram may be overwritten
+            uint32_t bb = s_bkey & 0xFFu;
+            for (int c = tid; c < C; c += THREADS) {
+                uint32_t L = 0;
+                const uint32_t* hf = s_hist + s_newj * g.FS;
+                for (uint32_t b = 0; b <= bb; ++b) L += hf[hist_index(b, c, C)];
+                s_bestL[c] = L;
+            }
+        }
+        pos += nb;
+        __syncthreads();
+    }
+
+    const uint32_t r = t.end - t.begin;
+    if (s_stop || !s_found) {
+        // leaf: root that needs no split, or no feature separates the rows
+        if (tid == 0) {
+            int pc = -1;
+            for (int c = 0; c < C; ++c) if (s_tot[c] == s_N) pc = c;
+            if (pc >= 0) write_pure_leaf(nodes, t.slot, s_N, (uint32_t)pc);
+            else {
+                for (int c = 0; c < C; ++c) leafc[(uint64_t)(t.begin >> 1) * C + c] = s_tot[c];
+                write_mixed_leaf(nodes, t.slot, t.begin);
+            }
+            atomicAdd(&g.stats->nodes, 1ull);
+            atomicAdd(&g.stats->leaves, 1ull);
+            if (!s_stop) { atomicAdd(&g.stats->searched, 1ull); atomicAdd(&g.stats->row_visits_big, (unsigned long long)r); }
+            atomicMax(&g.stats->max_depth, t.depth);
+        }
+        return;
+    }
+
+    // ---- row partition (SK/tree/_partitioner.pyx:248-279): left rows packed from the front in order,
+    // right rows from the back; tree structure depends only on the sets, not on the order.
+    const uint32_t bf = s_bkey >> 8, bb = s_bkey & 0xFFu;
+    uint32_t lbase = 0, rbase = 0;
+    int par = 0;
+    for (uint32_t c0 = t.begin; c0 < t.end; c0 += THREADS, par ^= 1) {
+        uint32_t idx = c0 + tid;
+        bool valid = idx < t.end;
+        uint32_t e = valid ? ent_in[idx] : 0u;
+        bool goL = valid && bins[(uint64_t)(e & ROW_MASK) * dstride + bf] <= bb;
+        uint32_t balL = __ballot_sync(0xffffffffu, goL);
+        uint32_t balR = __ballot_sync(0xffffffffu, valid && !goL);
+        if (lane == 0) { s_wl[par][wid] = __popc(balL); s_wr[par][wid] = __popc(balR); }
+        __syncthreads();
+        uint32_t pl = 0, pr = 0, tl = 0, tr = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            uint32_t a = s_wl[par][w], b = s_wr[par][w];
+            if (w < (int)wid) { pl += a; pr += b; }
+            tl += a; tr += b;
+        }
+        if (goL) ent_out[t.begin + lbase + pl + __popc(balL & lanemask_lt())] = e;
+        else if (valid) ent_out[t.end - 1u - (rbase + pr + __popc(balR & lanemask_lt()))] = e;
+        lbase += tl; rbase += tr;
+    }
+    const uint32_t nLd = lbase;
+    if (nLd == 0 || nLd == r) {  // cannot happen for a valid split; never loop on it
+        if (tid == 0) g.stats->error = 4;
+        return;
+    }
+
+    // ---- node record + children (leaf children are finished here, the rest are queued)
+    if (tid == 0) {
+        uint32_t NL = 0;
+        for (int c = 0; c < C; ++c) NL += s_bestL[c];
+        const uint32_t NR = s_N - NL;
+        const uint32_t right_slot = t.slot + 2u * nLd;
+        write_internal(nodes, t.slot, right_slot, bf, bb);
+        unsigned long long new_leaves = 0;
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t cb = side ? t.begin + nLd : t.begin, ce = side ? t.end : t.begin + nLd;
+            const uint32_t cslot = side ? right_slot : t.slot + 1u;
+            const uint32_t Nc = side ? NR : NL;
+            int pc = -1;
+            for (int c = 0; c < C; ++c) {
+                uint32_t v = side ? s_tot[c] - s_bestL[c] : s_bestL[c];
+                if (v == Nc) pc = c;
+            }
+            if (stop_rule(g, Nc, t.depth + 1u, pc >= 0)) {
+                if (pc >= 0) write_pure_leaf(nodes, cslot, Nc, (uint32_t)pc);
+                else {
+                    for (int c = 0; c < C; ++c)
+                        leafc[(uint64_t)(cb >> 1) * C + c] = side ? s_tot[c] - s_bestL[c] : s_bestL[c];
+                    write_mixed_leaf(nodes, cslot, cb);
+                }
+                new_leaves++;
+            } else {
+                Task ct;
+                ct.tree = t.tree; ct.begin = cb; ct.end = ce; ct.depth = t.depth + 1u; ct.slot = cslot;
+                ct.pad0 = ct.pad1 = ct.pad2 = 0;
+                if (ce - cb > SMALL_MAX) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
+                else queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
+            }
+        }
+        atomicAdd(&g.stats->nodes, 1ull + new_leaves);
+        if (new_leaves) { atomicAdd(&g.stats->leaves, new_leaves); atomicMax(&g.stats->max_depth, t.depth + 1u); }
+        atomicAdd(&g.stats->searched, 1ull);
+        atomicAdd(&g.stats->row_visits_big, (unsigned long long)r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp finishes the subtree under a node with <= 32 distinct rows.  Lane i holds row i of the
+// node; a candidate threshold is each lane's own bin; class counts left of it are accumulated in a
+// per-lane shared column over a broadcast loop; the partition is a ballot + shuffle permutation.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+    extern __shared__ uint32_t s_mem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int C = g.C, d = g.d, m = g.m;
+    // per-warp shared layout (words): L[C][32] | tot[C] | src[32] | stack[32][3] | perm[(d+1)/2]
+    const uint32_t per_warp = (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
+    uint32_t* s_L = s_mem + warp * per_warp;
+    uint32_t* s_tot = s_L + C * 32;
+    uint32_t* s_src = s_tot + C;
+    uint32_t* s_stack = s_src + 32;
+    uint16_t* s_perm = (uint16_t*)(s_stack + 96);
+    const uint8_t* __restrict__ bins = g.bins_rm;
+    const uint32_t dstride = g.dstride;
+
+    for (uint32_t ti = blockIdx.x * WARPS + warp; ti < ntasks; ti += gridDim.x * WARPS) {
+        const Task t = tasks[ti];
+        const TreeDesc td = g.trees[t.tree];
+        const uint32_t* __restrict__ ent = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+        uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
+        uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
+        const uint32_t r = t.end - t.begin;
+        uint32_t e = lane < r ? ent[t.begin + lane] : 0u;
+        uint32_t cls = lane < r ? (uint32_t)g.y[e & ROW_MASK] : 0u;
+        uint32_t lo = 0, hi = r, depth = t.depth, slot = t.slot, sp = 0;
+        unsigned long long visits = 0, n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0;
+        uint32_t maxd = 0;
+        while (true) {
+            const bool active = lane >= lo && lane < hi;
+            const uint32_t w = active ? (e >> 24) : 0u;
+            const uint32_t abs_begin = t.begin + lo;
+            // node totals (SK/tree/_criterion.pyx:302-370)
+            for (int c = lane; c < C; c += 32) s_tot[c] = 0;
+            __syncwarp();
+            if (active) atomicAdd(&s_tot[cls], w);
+            __syncwarp();
+            uint32_t N = w;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(0xffffffffu, N, off);
+            const uint32_t cls_lo = __shfl_sync(0xffffffffu, cls, lo);
+            const bool pure = s_tot[cls_lo] == N;
+            n_nodes++;
+            maxd = max(maxd, depth);
+            bool found = false;
+            double best_gain = -1.0;
+            uint32_t best_key = 0xFFFFFFFFu;
+            if (!stop_rule(g, N, depth, pure)) {
+                visits += hi - lo;
+                n_search++;
+                for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
+                __syncwarp();
+                uint4 rnd = make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < d; ++i) {
+                    if (i >= m && found) break;
+                    uint32_t f = 0;
+                    if (lane == 0) {
+                        if ((i & 3) == 0)
+                            rnd = philox4x32_10(abs_begin, depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);
+                        int j = i + (int)mulhi32(pick4(rnd, i & 3), (uint32_t)(d - i));
+                        uint16_t fj = s_perm[j];
+                        s_perm[j] = s_perm[i];
+                        s_perm[i] = fj;
+                        f = fj;
+                        if (i == m) n_fb++;
+                    }
+                    f = __shfl_sync(0xffffffffu, f, 0);
+                    const uint32_t b = active ? bins[(uint64_t)(e & ROW_MASK) * dstride + f] : 0u;
+                    const uint32_t packed = b | (cls << 8) | (w << 16);
+                    for (int c = 0; c < C; ++c) s_L[c * 32 + lane] = 0;
+                    for (uint32_t kk = lo; kk < hi; ++kk) {
+                        uint32_t pk = __shfl_sync(0xffffffffu, packed, kk);
+                        if (active && (pk & 0xFFu) <= b) s_L[((pk >> 8) & 0xFFu) * 32 + lane] += pk >> 16;
+                    }
+                    uint32_t NL = 0;
+                    unsigned long long SL = 0, SR = 0;
+                    for (int c = 0; c < C; ++c) {
+                        uint32_t L = s_L[c * 32 + lane], R = s_tot[c] - L;
+                        NL += L;
+                        SL += (unsigned long long)L * L;
+                        SR += (unsigned long long)R * R;
+                    }
+                    const uint32_t NR = N - NL;
+                    double gn = -1.0;
+                    uint32_t gb = 0xFFFFFFFFu;
+                    if (active && NL >= g.msl && NR >= g.msl) { gn = gini_gain(SL, NL, SR, NR); gb = b; }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        double og = __shfl_xor_sync(0xffffffffu, gn, off);
+                        uint32_t ob = __shfl_xor_sync(0xffffffffu, gb, off);
+                        if (og > gn || (og == gn && ob < gb)) { gn = og; gb = ob; }
+                    }
+                    if (gb != 0xFFFFFFFFu) {
+                        uint32_t key = (f << 8) | gb;
+                        if (i < m) {
+                            if (gn > best_gain || (gn == best_gain && key < best_key)) { best_gain = gn; best_key = key; found = true; }
+                        } else {
+                            best_gain = gn; best_key = key; found = true;
+                        }
+                    }
+                }
+            }
+            if (!found) {
+                // leaf
+                n_leaves++;
+                if (pure) {
+                    if (lane == 0) write_pure_leaf(nodes, slot, N, cls_lo);
+                } else {
+                    for (int c = lane; c < C; c += 32) leafc[(uint64_t)(abs_begin >> 1) * C + c] = s_tot[c];
+                    if (lane == 0) write_mixed_leaf(nodes, slot, abs_begin);
+                }
+                if (sp == 0) break;
+                --sp;
+                uint32_t lh = s_stack[sp * 3];
+                lo = lh & 0xFFu; hi = lh >> 8; depth = s_stack[sp * 3 + 1]; slot = s_stack[sp * 3 + 2];
+                __syncwarp();
+                continue;
+            }
+            // partition inside the warp (stable)
+            const uint32_t bf = best_key >> 8, bb = best_key & 0xFFu;
+            const bool goL = active && bins[(uint64_t)(e & ROW_MASK) * dstride + bf] <= bb;
+            const uint32_t balL = __ballot_sync(0xffffffffu, goL);
+            const uint32_t balR = __ballot_sync(0xffffffffu, active && !goL);
+            const uint32_t nLd = __popc(balL);
+            if (nLd == 0 || nLd == hi - lo) {  // cannot happen for a valid split; never loop on it
+                if (lane == 0) g.stats->error = 4;
+                break;
+            }
+            uint32_t dest = lane;
+            if (goL) dest = lo + __popc(balL & lanemask_lt());
+            else if (active) dest = lo + nLd + __popc(balR & lanemask_lt());
+            s_src[dest] = lane;
+            __syncwarp();
+            const uint32_t src = s_src[lane];
+            __syncwarp();
+            e = __shfl_sync(0xffffffffu, e, src);
+            cls = __shfl_sync(0xffffffffu, cls, src);
+            const uint32_t right_slot = slot + 2u * nLd;
+            if (lane == 0) {
+                write_internal(nodes, slot, right_slot, bf, bb);
+                s_stack[sp * 3] = (lo + nLd) | (hi << 8);
+                s_stack[sp * 3 + 1] = depth + 1u;
+                s_stack[sp * 3 + 2] = right_slot;
+            }
+            __syncwarp();
+            sp++;
+            hi = lo + nLd;
+            depth += 1u;
+            slot += 1u;
+        }
+        if (lane == 0) {
+            atomicAdd(&g.stats->row_visits_small, visits);
+            atomicAdd(&g.stats->nodes, n_nodes);
+            atomicAdd(&g.stats->leaves, n_leaves);
+            atomicAdd(&g.stats->searched, n_search);
+            if (n_fb) atomicAdd(&g.stats->fallback, n_fb);
+            atomicMax(&g.stats->max_depth, maxd);
+        }
+        __syncwarp();
+    }
+}

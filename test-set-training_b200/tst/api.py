@@ -1,0 +1,401 @@
+"""Host side of the TsT Random-Forest diagnostic: a sklearn-like surface over the libtst.so C ABI.
+
+    TsTForest(...).fit(X, y).predict_proba(X)      names/defaults: SK/ensemble/_forest.py:1515-1537
+    run_tst(X, y, k, n_trees, seed)  -> TsTResult   k-fold OOF bias score s(x)   (REF/README.md:35)
+    ibp(X, y, rounds, k, n_trees, tau, batch)       Iterative Bias Pruning       (REF/README.md:35)
+
+torch is used only to own device memory, streams and the one NCCL all-gather; all compute is in
+the hand-written CUDA kernels behind include/tst.h.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from . import binning
+from ._lib import FOLD_INACTIVE, FOLD_TRAIN_ONLY, Params, Stats, TstError, check
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def resolve_max_features(max_features, d: int) -> int:
+    """SK/tree/_classes.py:330-345."""
+    if max_features is None:
+        return d
+    if isinstance(max_features, str):
+        if max_features == "sqrt":
+            return max(1, int(np.sqrt(d)))
+        if max_features == "log2":
+            return max(1, int(np.log2(d)))
+        raise ValueError(f"max_features={max_features!r}")
+    if isinstance(max_features, float):
+        return max(1, min(d, int(max_features * d)))
+    return max(1, min(d, int(max_features)))
+
+
+def make_params(d, max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt",
+                trees_in_flight=0, keep_forest=False) -> Params:
+    if min_samples_split < 2 or min_samples_leaf < 1:
+        raise ValueError("min_samples_split >= 2 and min_samples_leaf >= 1 required")
+    return Params(0 if max_depth is None else int(max_depth), int(min_samples_split), int(min_samples_leaf),
+                  resolve_max_features(max_features, d), int(trees_in_flight), int(bool(keep_forest)))
+
+
+def encode_labels(y):
+    """Class order = np.unique(y) (SK/ensemble/_forest.py:810-827)."""
+    classes, idx = np.unique(np.asarray(y), return_inverse=True)
+    if classes.shape[0] > _lib.MAX_CLASSES:
+        raise ValueError(f"at most {_lib.MAX_CLASSES} classes are supported")
+    return classes, idx.astype(np.uint8)
+
+
+def dist_info():
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:  # pragma: no cover
+        pass
+    return 0, 1
+
+
+def shard_trees(n_parts: int, n_trees: int, rank: int, world: int, t0: int = 0, t1: int | None = None):
+    """The (part, t) pairs rank `rank` of `world` builds: local id part*n_trees + t == rank (mod world)."""
+    t1 = n_trees if t1 is None else t1
+    return [(p, t) for p in range(n_parts) for t in range(t0, t1) if (p * n_trees + t) % world == rank]
+
+
+class Engine:
+    """One tst_handle = one (process, device).  All tensors handed to it live on that device."""
+
+    def __init__(self, device: int | None = None, rank: int = 0, world: int = 1):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise TstError(-2, "no CUDA device: the TsT engine has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.dev = torch.device("cuda", self.device)
+        self.rank, self.world = rank, world
+        self._h = C.c_void_p()
+        check(_lib.lib().tst_create(C.byref(self._h), self.device, rank, world, None))
+        self.n = self.d = 0
+        self.edges = self.n_edges = None
+
+    def close(self):
+        if self._h:
+            _lib.lib().tst_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.dev).cuda_stream)
+
+    def to_dev(self, a, dtype):
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.dev, dtype=dtype).contiguous()
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device=self.dev, dtype=dtype, non_blocking=True).contiguous()
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    # ---- table
+    def bin(self, X, n_bins: int = 256, edges=None, n_edges=None):
+        """X: host array or device tensor [n, d].  Edges are picked on the host (binning.py), the map runs on the GPU."""
+        torch = _torch()
+        if edges is None:
+            Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
+            edges, n_edges = binning.table_edges(Xh, n_bins)
+        Xd = self.to_dev(X, torch.float32)
+        n, d = Xd.shape
+        edges = np.ascontiguousarray(edges, np.float64)
+        n_edges = np.ascontiguousarray(n_edges, np.int32)
+        check(_lib.lib().tst_bin(self._h, self._ptr(Xd), C.c_int64(n), C.c_int32(d), edges.ctypes.data_as(C.c_void_p),
+                                 n_edges.ctypes.data_as(C.c_void_p), self._stream()))
+        torch.cuda.current_stream(self.dev).synchronize()  # edges/X staging buffers may be released
+        self.n, self.d, self.edges, self.n_edges = n, d, edges, n_edges
+        return self
+
+    def set_bins(self, bins_cm):
+        torch = _torch()
+        b = self.to_dev(bins_cm, torch.uint8)
+        d, n = b.shape
+        check(_lib.lib().tst_set_bins(self._h, self._ptr(b), C.c_int64(n), C.c_int32(d), self._stream()))
+        torch.cuda.current_stream(self.dev).synchronize()
+        self.n, self.d, self.edges, self.n_edges = n, d, None, None
+        return self
+
+    def get_bins(self) -> np.ndarray:
+        torch = _torch()
+        out = torch.empty((self.d, self.n), dtype=torch.uint8, device=self.dev)
+        check(_lib.lib().tst_get_bins(self._h, self._ptr(out), self._stream()))
+        return out.cpu().numpy()
+
+    # ---- folds / fit / votes
+    def assign_folds(self, y_dev, active_dev, k, n_classes, group_dev=None, n_groups=1):
+        torch = _torch()
+        fold = torch.empty(self.n, dtype=torch.uint8, device=self.dev)
+        check(_lib.lib().tst_assign_folds(self._h, self._ptr(y_dev), self._ptr(active_dev), self._ptr(group_dev),
+                                          C.c_int32(n_groups), C.c_int32(k), C.c_int32(n_classes), self._ptr(fold),
+                                          self._stream()))
+        return fold
+
+    def new_votes(self, n_classes):
+        torch = _torch()
+        return torch.zeros((self.n, n_classes), dtype=torch.int32, device=self.dev)  # bit pattern of uint32
+
+    def fit_oof(self, y_dev, fold_dev, k, n_trees, n_classes, params: Params, seed=0, gid_base=0, t0=0, t1=None,
+                group_dev=None, n_groups=1, votes=None):
+        t1 = n_trees if t1 is None else t1
+        check(_lib.lib().tst_fit_oof(self._h, self._ptr(y_dev), self._ptr(fold_dev), self._ptr(group_dev),
+                                     C.c_int32(n_groups), C.c_int32(k), C.c_int32(n_trees), C.c_int32(n_classes),
+                                     C.byref(params), C.c_uint64(seed), C.c_uint32(gid_base), C.c_int32(t0), C.c_int32(t1),
+                                     self._ptr(votes), self._stream()))
+        return votes
+
+    def allreduce_votes(self, votes):
+        """The path's one exchange step: NCCL all-gather of the per-rank votes, then a rank-ordered integer sum."""
+        if self.world == 1:
+            return votes
+        torch = _torch()
+        import torch.distributed as dist
+
+        gathered = torch.empty((self.world,) + tuple(votes.shape), dtype=votes.dtype, device=self.dev)
+        dist.all_gather_into_tensor(gathered, votes)
+        out = torch.empty_like(votes)
+        check(_lib.lib().tst_reduce_votes(self._h, self._ptr(gathered), C.c_int32(self.world), C.c_int64(votes.numel()),
+                                          self._ptr(out), self._stream()))
+        return out
+
+    def finalize(self, votes, y_dev, fold_dev, k, n_trees, n_classes, group_dev=None, n_groups=1):
+        torch = _torch()
+        s = torch.empty(self.n, dtype=torch.float32, device=self.dev)
+        correct = torch.empty(n_groups * k, dtype=torch.int32, device=self.dev)
+        total = torch.empty(n_groups * k, dtype=torch.int32, device=self.dev)
+        check(_lib.lib().tst_finalize(self._h, self._ptr(votes), self._ptr(y_dev), self._ptr(fold_dev), self._ptr(group_dev),
+                                      C.c_int32(n_groups), C.c_int32(k), C.c_int32(n_trees), C.c_int32(n_classes),
+                                      self._ptr(s), self._ptr(correct), self._ptr(total), self._stream()))
+        return s, correct, total
+
+    def ibp_select(self, votes, y_dev, fold_dev, k, n_classes, vmin, batch, active_dev) -> int:
+        removed = C.c_int64(0)
+        check(_lib.lib().tst_ibp_select(self._h, self._ptr(votes), self._ptr(y_dev), self._ptr(fold_dev), C.c_int32(k),
+                                        C.c_int32(n_classes), C.c_uint64(vmin), C.c_int64(batch), self._ptr(active_dev),
+                                        C.byref(removed), self._stream()))
+        return int(removed.value)
+
+    def ibp(self, y_dev, active_dev, k, n_trees, n_classes, params, seed, rounds, tau, batch, group_dev=None, n_groups=1,
+            want_s=True):
+        torch = _torch()
+        removed = (C.c_int64 * rounds)()
+        s = torch.empty((rounds, self.n), dtype=torch.float32, device=self.dev) if want_s else None
+        check(_lib.lib().tst_ibp(self._h, self._ptr(y_dev), self._ptr(active_dev), self._ptr(group_dev), C.c_int32(n_groups),
+                                 C.c_int32(k), C.c_int32(n_trees), C.c_int32(n_classes), C.byref(params), C.c_uint64(seed),
+                                 C.c_int32(rounds), C.c_double(tau), C.c_int64(batch), removed, self._ptr(s), self._stream()))
+        return np.array(list(removed), dtype=np.int64), s
+
+    # ---- kept forest
+    def predict_votes(self, X, n_classes):
+        torch = _torch()
+        Xd = self.to_dev(X, torch.float32)
+        votes = torch.zeros((Xd.shape[0], n_classes), dtype=torch.int32, device=self.dev)
+        check(_lib.lib().tst_predict(self._h, self._ptr(Xd), C.c_int64(Xd.shape[0]), self._ptr(votes), self._stream()))
+        return votes
+
+    def export_tree(self, part, t, n_classes):
+        n_nodes = C.c_int64(0)
+        _lib.lib().tst_export_tree(self._h, C.c_int32(part), C.c_int32(t), None, None, C.c_int64(0), C.byref(n_nodes))
+        if n_nodes.value <= 0:
+            raise TstError(-4, _lib.lib().tst_last_error().decode())
+        nodes = np.zeros(n_nodes.value, dtype=NODE_DTYPE)
+        counts = np.zeros((n_nodes.value, n_classes), dtype=np.uint32)
+        check(_lib.lib().tst_export_tree(self._h, C.c_int32(part), C.c_int32(t), nodes.ctypes.data_as(C.c_void_p),
+                                         counts.ctypes.data_as(C.c_void_p), C.c_int64(n_nodes.value), C.byref(n_nodes)))
+        return nodes, counts
+
+    def stats(self, reset=False) -> dict:
+        st = Stats()
+        check(_lib.lib().tst_get_stats(self._h, C.byref(st)))
+        if reset:
+            check(_lib.lib().tst_reset_stats(self._h))
+        return st.as_dict()
+
+
+NODE_DTYPE = np.dtype([("left", "<i4"), ("right", "<i4"), ("feature", "<i4"), ("bin", "<i4"),
+                       ("begin", "<u4"), ("end", "<u4"), ("depth", "<u4"), ("n_weighted", "<u4")])
+
+_engines: dict = {}
+
+
+def get_engine(device=None) -> Engine:
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise TstError(-2, "no CUDA device: the TsT engine has no CPU fallback")
+    rank, world = dist_info()
+    device = torch.cuda.current_device() if device is None else device
+    key = (device, rank, world)
+    if key not in _engines:
+        _engines[key] = Engine(device, rank, world)
+    return _engines[key]
+
+
+# ------------------------------------------------------------------------------------------------- run_tst
+@dataclass
+class TsTResult:
+    s: np.ndarray               # [n] float32 out-of-fold probability of the true class (bias score); -1 if never held out
+    oof_votes: np.ndarray       # [n, C] uint32 Q0.16 vote sums over the fold's n_trees
+    fold_id: np.ndarray         # [n] uint8
+    fold_accuracy: np.ndarray   # [n_groups * k] blind accuracy per (group, fold)
+    classes: np.ndarray
+    stats: dict = field(default_factory=dict)
+
+
+def run_tst(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, max_depth=None, min_samples_split=2,
+            min_samples_leaf=1, max_features="sqrt", n_bins=256, group=None, fold=None, engine: Engine | None = None,
+            trees_in_flight=0, tree_range=None, prebinned=False) -> TsTResult:
+    """k-fold x n_trees RF diagnostic.  X, y are host arrays (or device tensors); every copy is inside this call."""
+    torch = _torch()
+    eng = engine or get_engine()
+    classes, yi = encode_labels(y)
+    n_classes = int(classes.shape[0])
+    if prebinned:
+        eng.set_bins(X)
+    else:
+        eng.bin(X, n_bins=n_bins)
+    y_dev = eng.to_dev(yi, torch.uint8)
+    g_dev, n_groups = None, 1
+    if group is not None:
+        gi = np.asarray(group, dtype=np.int32)
+        n_groups = int(gi.max()) + 1
+        g_dev = eng.to_dev(gi, torch.int32)
+    if fold is None:
+        active = torch.ones(eng.n, dtype=torch.uint8, device=eng.dev)
+        fold_dev = eng.assign_folds(y_dev, active, k, n_classes, g_dev, n_groups)
+    else:
+        fold_dev = eng.to_dev(np.asarray(fold, dtype=np.uint8), torch.uint8)
+    prm = make_params(eng.d, max_depth, min_samples_split, min_samples_leaf, max_features, trees_in_flight)
+    votes = eng.new_votes(n_classes)
+    t0, t1 = (0, n_trees) if tree_range is None else tree_range
+    eng.stats(reset=True)
+    eng.fit_oof(y_dev, fold_dev, k, n_trees, n_classes, prm, seed=seed, t0=t0, t1=t1, group_dev=g_dev, n_groups=n_groups,
+                votes=votes)
+    votes = eng.allreduce_votes(votes)
+    s, correct, total = eng.finalize(votes, y_dev, fold_dev, k, n_trees, n_classes, g_dev, n_groups)
+    s_h = s.cpu().numpy()
+    votes_h = votes.cpu().numpy().view(np.uint32)
+    tot = total.cpu().numpy().astype(np.float64)
+    acc = np.divide(correct.cpu().numpy().astype(np.float64), tot, out=np.full_like(tot, np.nan), where=tot > 0)
+    return TsTResult(s_h, votes_h, fold_dev.cpu().numpy(), acc, classes, eng.stats())
+
+
+# ------------------------------------------------------------------------------------------------- IBP
+@dataclass
+class IBPResult:
+    keep_mask: np.ndarray          # [n] bool, rows surviving all rounds
+    removed_per_round: np.ndarray  # [rounds] int64
+    s_per_round: np.ndarray | None  # [rounds, n] float32 (-1 where the row was not scored in that round)
+    stats: dict = field(default_factory=dict)
+
+
+def ibp_vmin(tau: float, n_trees: int) -> int:
+    """Integer form of s >= tau: votes[y] >= ceil(tau * n_trees * 65536)."""
+    return int(np.ceil(np.float64(tau) * np.float64(n_trees) * 65536.0))
+
+
+def ibp(X, y, rounds: int = 10, k: int = 5, n_trees: int = 200, tau: float = 0.5, batch: int | None = None, seed: int = 0, *,
+        max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt", n_bins=256, group=None,
+        engine: Engine | None = None, want_s=True, prebinned=False) -> IBPResult:
+    """Iterative Bias Pruning; the table, labels, active mask, votes and s(x) never leave the device between rounds."""
+    torch = _torch()
+    eng = engine or get_engine()
+    classes, yi = encode_labels(y)
+    n_classes = int(classes.shape[0])
+    if prebinned:
+        eng.set_bins(X)
+    else:
+        eng.bin(X, n_bins=n_bins)
+    n = eng.n
+    batch = n if batch is None else int(batch)
+    y_dev = eng.to_dev(yi, torch.uint8)
+    g_dev, n_groups = None, 1
+    if group is not None:
+        gi = np.asarray(group, dtype=np.int32)
+        n_groups = int(gi.max()) + 1
+        g_dev = eng.to_dev(gi, torch.int32)
+    active = torch.ones(n, dtype=torch.uint8, device=eng.dev)
+    prm = make_params(eng.d, max_depth, min_samples_split, min_samples_leaf, max_features)
+    eng.stats(reset=True)
+    if eng.world == 1:
+        removed, s = eng.ibp(y_dev, active, k, n_trees, n_classes, prm, seed, rounds, tau, batch, g_dev, n_groups, want_s)
+    else:  # the per-round vote all-gather is issued from the host; data stays on the device
+        removed = np.zeros(rounds, np.int64)
+        s = torch.full((rounds, n), -1.0, dtype=torch.float32, device=eng.dev) if want_s else None
+        vmin = ibp_vmin(tau, n_trees)
+        per_round = n_groups * k * n_trees
+        for r in range(rounds):
+            fold_dev = eng.assign_folds(y_dev, active, k, n_classes, g_dev, n_groups)
+            votes = eng.new_votes(n_classes)
+            eng.fit_oof(y_dev, fold_dev, k, n_trees, n_classes, prm, seed=seed, gid_base=r * per_round, group_dev=g_dev,
+                        n_groups=n_groups, votes=votes)
+            votes = eng.allreduce_votes(votes)
+            if want_s:
+                s[r] = eng.finalize(votes, y_dev, fold_dev, k, n_trees, n_classes, g_dev, n_groups)[0]
+            removed[r] = eng.ibp_select(votes, y_dev, fold_dev, k, n_classes, vmin, batch, active)
+            if removed[r] == 0:
+                break
+    return IBPResult(active.cpu().numpy().astype(bool), removed, None if s is None else s.cpu().numpy(), eng.stats())
+
+
+# ------------------------------------------------------------------------------------------------- TsTForest
+class TsTForest:
+    """sklearn-like classifier over the same kernels (argument names: SK/ensemble/_forest.py:1515-1537)."""
+
+    def __init__(self, n_estimators=100, max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt",
+                 n_bins=256, random_state=0, engine: Engine | None = None):
+        self.n_estimators, self.max_depth = n_estimators, max_depth
+        self.min_samples_split, self.min_samples_leaf = min_samples_split, min_samples_leaf
+        self.max_features, self.n_bins, self.random_state = max_features, n_bins, random_state
+        self._engine = engine
+
+    def fit(self, X, y):
+        torch = _torch()
+        # a kept forest lives in its engine: use a private one unless the caller shares one
+        self._eng = self._engine or Engine(torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.classes_, yi = encode_labels(y)
+        self.n_classes_ = int(self.classes_.shape[0])
+        self._eng.bin(X, n_bins=self.n_bins)
+        self.n_features_in_ = self._eng.d
+        y_dev = self._eng.to_dev(yi, torch.uint8)
+        fold = torch.full((self._eng.n,), FOLD_TRAIN_ONLY, dtype=torch.uint8, device=self._eng.dev)
+        prm = make_params(self._eng.d, self.max_depth, self.min_samples_split, self.min_samples_leaf, self.max_features,
+                          keep_forest=True)
+        self._eng.fit_oof(y_dev, fold, 1, self.n_estimators, self.n_classes_, prm, seed=int(self.random_state or 0))
+        return self
+
+    def predict_votes(self, X) -> np.ndarray:
+        return self._eng.predict_votes(X, self.n_classes_).cpu().numpy().view(np.uint32)
+
+    def predict_proba(self, X) -> np.ndarray:
+        v = self.predict_votes(X).astype(np.float64)
+        return v / v.sum(axis=1, keepdims=True)
+
+    def predict(self, X):
+        return self.classes_[np.argmax(self.predict_votes(X), axis=1)]
+
+    def export_tree(self, t: int):
+        return self._eng.export_tree(0, t, self.n_classes_)

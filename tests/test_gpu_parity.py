@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libtst.so), against the CPU
+oracle on the same seeded inputs.  Bar: bit-exact (bins, folds, every node of every tree, integer
+votes, s(x) as float32 bits, IBP masks, work counters)."""
+import numpy as np
+import pytest
+
+from oracle import hist_rf as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import tst
+
+    e = tst.Engine(0)
+    yield e
+    e.close()
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def oracle_table(X, n_bins=256):
+    edges, ne = H.find_edges(X, n_bins)
+    return edges, ne, H.bin_table(X, edges, ne)
+
+
+def compare_tree(gn, gc, on, oc, tag):
+    assert len(gn) == len(on), f"{tag}: node count {len(gn)} != oracle {len(on)}"
+    for name in on.dtype.names:
+        bad = np.flatnonzero(gn[name] != on[name])
+        assert bad.size == 0, f"{tag}: field {name} differs at node {bad[0]}: gpu {gn[bad[0]]} oracle {on[bad[0]]}"
+    bad = np.argwhere(gc != oc)
+    assert bad.size == 0, f"{tag}: counts differ at {bad[0]}: gpu {gc[bad[0][0]]} oracle {oc[bad[0][0]]}"
+
+
+def run_both(eng, bins, y, fold, k, T, C, seed=0, keep=False, group=None, n_groups=1, **pk):
+    """Fit on GPU and oracle with identical inputs; returns (gpu votes, oracle votes, gpu stats, oracle stats, forest)."""
+    import tst
+
+    torch = _torch()
+    d = bins.shape[0]
+    eng.set_bins(bins)
+    y_dev = eng.to_dev(y, torch.uint8)
+    fold_dev = eng.to_dev(fold, torch.uint8)
+    g_dev = None if group is None else eng.to_dev(group, torch.int32)
+    prm = tst.make_params(d, keep_forest=keep, **pk)
+    votes = eng.new_votes(C)
+    eng.stats(reset=True)
+    eng.fit_oof(y_dev, fold_dev, k, T, C, prm, seed=seed, group_dev=g_dev, n_groups=n_groups, votes=votes)
+    gst = eng.stats()
+    oprm = H.make_params(d, **pk)
+    ov, ost, forest = H.fit_oof(bins, y, fold, k, T, C, oprm, seed=seed, keep=keep, group=group, n_groups=n_groups)
+    return votes.cpu().numpy().view(np.uint32), ov, gst, ost, forest
+
+
+def check_stats(gst, ost):
+    assert gst["row_visits_big"] + gst["row_visits_small"] == ost["row_visits"]
+    for key in ("nodes", "leaves", "searched", "fallback", "inbag_rows", "trees", "oof_steps", "max_depth"):
+        assert gst[key] == ost[key], f"stat {key}: gpu {gst[key]} oracle {ost[key]}"
+
+
+# --------------------------------------------------------------------------------------------- binning / folds
+def test_bin_map_bit_exact(eng, vsi_small):
+    X = vsi_small["X"].copy()
+    X[3, 2] = np.nan
+    X[11, 0] = np.inf
+    X[12, 0] = -np.inf
+    edges, ne, ref = oracle_table(X)
+    eng.bin(X)
+    assert np.array_equal(eng.edges, edges) and np.array_equal(eng.n_edges, ne)
+    got = eng.get_bins()
+    assert got.dtype == np.uint8 and np.array_equal(got, ref)
+    assert got[2, 3] == 255
+
+
+def test_bin_map_ragged_shapes(eng):
+    rng = np.random.default_rng(5)
+    for n, d in ((1, 1), (127, 3), (129, 17), (1000, 33)):
+        X = rng.standard_normal((n, d)).astype(np.float32)
+        X[:, 0] = np.round(X[:, 0])  # low cardinality column
+        edges, ne, ref = oracle_table(X)
+        eng.bin(X)
+        assert np.array_equal(eng.get_bins(), ref), (n, d)
+
+
+def test_set_bins_roundtrip(eng, vsi_small):
+    eng.set_bins(vsi_small["bins"])
+    assert np.array_equal(eng.get_bins(), vsi_small["bins"])
+
+
+@pytest.mark.parametrize("k,n_groups", [(5, 1), (3, 4), (10, 1)])
+def test_fold_assignment(eng, vsi_small, k, n_groups):
+    torch = _torch()
+    y = vsi_small["y"]
+    n = len(y)
+    rng = np.random.default_rng(k)
+    active = (rng.random(n) < 0.85).astype(np.uint8)
+    group = rng.integers(0, n_groups, n).astype(np.int32) if n_groups > 1 else None
+    eng.set_bins(vsi_small["bins"])
+    got = eng.assign_folds(eng.to_dev(y, torch.uint8), eng.to_dev(active, torch.uint8), k, 4,
+                           None if group is None else eng.to_dev(group, torch.int32), n_groups).cpu().numpy()
+    ref = H.assign_folds(y, active, k, 4, group, n_groups)
+    assert np.array_equal(got, ref)
+
+
+# --------------------------------------------------------------------------------------------- trees
+def test_trees_bit_exact_vsi_small(eng, vsi_small):
+    v = vsi_small
+    T = 8
+    gv, ov, gst, ost, forest = run_both(eng, v["bins"], v["y"], v["fold"], v["k"], T, v["C"], seed=3, keep=True)
+    for part in range(v["k"]):
+        for t in range(T):
+            gn, gc = eng.export_tree(part, t, v["C"])
+            ot = forest.tree(part, t)
+            compare_tree(gn, gc, ot.nodes, ot.counts, f"tree({part},{t})")
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+
+
+def test_votes_and_s_bit_exact_vsi_config(eng):
+    """BASELINE.json configs[1]: 5k x 32, 5-fold x 100 trees."""
+    from tst import synth
+
+    torch = _torch()
+    X, y = synth.vsi_table()
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 5, 4)
+    gv, ov, gst, ost, _ = run_both(eng, bins, y, fold, 5, 100, 4, seed=0)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    s, cor, tot = eng.finalize(eng.to_dev(gv.view(np.int32), torch.int32), eng.to_dev(y, torch.uint8),
+                               eng.to_dev(fold, torch.uint8), 5, 100, 4)
+    os_, ocor, otot = H.finalize(ov, y, fold, 5, 100)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    assert np.array_equal(cor.cpu().numpy(), ocor.astype(np.int32)) and np.array_equal(tot.cpu().numpy(), otot.astype(np.int32))
+
+
+def _edge_case_tables():
+    rng = np.random.default_rng(11)
+    out = {}
+    # low-cardinality only: many nodes where all m sampled features are constant -> fallback draws
+    n = 600
+    out["lowcard"] = (rng.integers(0, 3, (6, n)).astype(np.uint8), rng.integers(0, 3, n).astype(np.uint8), 3)
+    # duplicate rows with conflicting labels -> mixed leaves
+    b = rng.integers(0, 4, (4, 40)).astype(np.uint8)
+    out["dups"] = (np.tile(b, (1, 10)), rng.integers(0, 2, 400).astype(np.uint8), 2)
+    # single class
+    out["oneclass"] = (rng.integers(0, 255, (5, 300)).astype(np.uint8), np.zeros(300, np.uint8), 1)
+    # constant columns + one informative column + NaN bin
+    b = np.zeros((8, 500), np.uint8)
+    b[3] = rng.integers(0, 256, 500)
+    out["const"] = (b, (b[3] > 100).astype(np.uint8) + (b[3] > 200).astype(np.uint8), 3)
+    # many classes, wide table
+    out["manyclass"] = (rng.integers(0, 64, (40, 900)).astype(np.uint8), rng.integers(0, 13, 900).astype(np.uint8), 13)
+    # tiny
+    out["tiny"] = (rng.integers(0, 5, (2, 7)).astype(np.uint8), rng.integers(0, 2, 7).astype(np.uint8), 2)
+    return out
+
+
+@pytest.mark.parametrize("name", ["lowcard", "dups", "oneclass", "const", "manyclass", "tiny"])
+@pytest.mark.parametrize("pk", [dict(), dict(max_depth=3), dict(min_samples_leaf=3, min_samples_split=8), dict(max_features=None)])
+def test_edge_cases_bit_exact(eng, name, pk):
+    bins, y, C = _edge_case_tables()[name]
+    n = bins.shape[1]
+    k = 3
+    fold = H.assign_folds(y, np.ones(n, np.uint8), k, C)
+    T = 5
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, T, C, seed=9, keep=True, **pk)
+    for part in range(k):
+        for t in range(T):
+            gn, gc = eng.export_tree(part, t, C)
+            ot = forest.tree(part, t)
+            compare_tree(gn, gc, ot.nodes, ot.counts, f"{name} tree({part},{t})")
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+
+
+def test_fewer_rows_than_folds(eng):
+    rng = np.random.default_rng(2)
+    bins = rng.integers(0, 9, (3, 4)).astype(np.uint8)
+    y = np.array([0, 1, 0, 1], np.uint8)
+    fold = H.assign_folds(y, np.ones(4, np.uint8), 5, 2)  # fold 4 is empty, folds hold one row each
+    gv, ov, gst, ost, _ = run_both(eng, bins, y, fold, 5, 3, 2, seed=1)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+
+
+def test_grouped_forests_one_launch(eng):
+    """BASELINE.json configs[2]: per-question-type forests (MMMU-shaped: 30 groups x 30 rows)."""
+    from tst import synth
+
+    X, y, group, n_groups = synth.grouped_table("mmmu")
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 5, 4, group, n_groups)
+    gv, ov, gst, ost, _ = run_both(eng, bins, y, fold, 5, 20, 4, seed=4, group=group, n_groups=n_groups)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+
+
+def test_batching_does_not_change_results(eng, vsi_small):
+    import tst
+
+    torch = _torch()
+    v = vsi_small
+    eng.set_bins(v["bins"])
+    y_dev, fold_dev = eng.to_dev(v["y"], torch.uint8), eng.to_dev(v["fold"], torch.uint8)
+    outs = []
+    for tif in (0, 7, 1):
+        prm = tst.make_params(v["bins"].shape[0], trees_in_flight=tif)
+        votes = eng.new_votes(v["C"])
+        eng.fit_oof(y_dev, fold_dev, v["k"], 6, v["C"], prm, seed=5, votes=votes)
+        outs.append(votes.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_rank_sharding_sums_to_single_rank(vsi_small):
+    """world in {1, 2, 4}: ranks emulated sequentially on one GPU; integer votes make the sum exact."""
+    import tst
+
+    torch = _torch()
+    v = vsi_small
+    T = 6
+    ref = None
+    for world in (1, 2, 4):
+        parts = []
+        for rank in range(world):
+            e = tst.Engine(0, rank, world)
+            e.set_bins(v["bins"])
+            votes = e.new_votes(v["C"])
+            prm = tst.make_params(v["bins"].shape[0])
+            e.fit_oof(e.to_dev(v["y"], torch.uint8), e.to_dev(v["fold"], torch.uint8), v["k"], T, v["C"], prm, seed=2, votes=votes)
+            parts.append(votes)
+            if rank == world - 1:
+                gathered = torch.stack(parts).contiguous()
+                out = torch.empty_like(votes)
+                tst._lib.check(tst._lib.lib().tst_reduce_votes(e._h, e._ptr(gathered), world, votes.numel(), e._ptr(out), e._stream()))
+                total = out.cpu().numpy()
+            e.close()
+        if ref is None:
+            ref = total
+        assert np.array_equal(total, ref), world
+    ov, _, _ = H.fit_oof(v["bins"], v["y"], v["fold"], v["k"], T, v["C"], H.make_params(v["bins"].shape[0]), seed=2)
+    assert np.array_equal(ref.view(np.uint32), ov)
+
+
+def test_mid_size_table_bit_exact(eng):
+    """60k x 64 scale-up-shaped table: exercises deep level-wise growth and many warp subtrees."""
+    from tst import synth
+
+    X, y = synth.scaleup_table(60_000, 64, 4, seed=1)
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 10, 4)
+    gv, ov, gst, ost, _ = run_both(eng, bins, y, fold, 10, 2, 4, seed=0)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+
+
+# --------------------------------------------------------------------------------------------- IBP / API
+def test_ibp_bit_exact(eng, vsi_small):
+    import tst
+
+    torch = _torch()
+    v = vsi_small
+    n = len(v["y"])
+    T, rounds, tau, batch = 10, 4, 0.45, 60
+    eng.set_bins(v["bins"])
+    active = torch.ones(n, dtype=torch.uint8, device=eng.dev)
+    prm = tst.make_params(v["bins"].shape[0])
+    removed, s = eng.ibp(eng.to_dev(v["y"], torch.uint8), active, v["k"], T, v["C"], prm, 7, rounds, tau, batch)
+    oact, orem, os_ = H.ibp(v["bins"], v["y"], v["k"], T, v["C"], H.make_params(v["bins"].shape[0]), seed=7, rounds=rounds,
+                            tau=tau, batch=batch)
+    assert removed.tolist() == orem.tolist()
+    assert np.array_equal(active.cpu().numpy(), oact)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+
+
+def test_ibp_select_ties_and_threshold(eng):
+    import tst
+
+    torch = _torch()
+    rng = np.random.default_rng(0)
+    n, C, k = 3000, 3, 5
+    eng.set_bins(rng.integers(0, 4, (2, n)).astype(np.uint8))
+    y = rng.integers(0, C, n).astype(np.uint8)
+    fold = rng.integers(0, k, n).astype(np.uint8)
+    votes = (rng.integers(0, 40, (n, C)) * 65536).astype(np.uint32)  # heavy ties
+    for vmin, batch in ((0, 100), (20 * 65536, 57), (39 * 65536, 5000), (41 * 65536, 10), (0, 1)):
+        act0 = (rng.random(n) < 0.9).astype(np.uint8)
+        a_dev = eng.to_dev(act0, torch.uint8)
+        took = eng.ibp_select(eng.to_dev(votes.view(np.int32), torch.int32), eng.to_dev(y, torch.uint8),
+                              eng.to_dev(fold, torch.uint8), k, C, vmin, batch, a_dev)
+        ref = act0.copy()
+        otook = H.ibp_select(votes, y, fold, k, vmin, batch, ref)
+        assert took == otook and np.array_equal(a_dev.cpu().numpy(), ref), (vmin, batch)
+
+
+def test_public_api_run_tst_and_forest(vsi_small):
+    import tst
+
+    v = vsi_small
+    res = tst.run_tst(v["X"], v["y"], k=5, n_trees=12, seed=1)
+    ov, _, _ = H.fit_oof(v["bins"], v["y"], v["fold"], 5, 12, 4, H.make_params(16), seed=1)
+    assert np.array_equal(res.fold_id, v["fold"]) and np.array_equal(res.oof_votes, ov)
+    os_, cor, tot = H.finalize(ov, v["y"], v["fold"], 5, 12)
+    assert np.array_equal(res.s.view(np.uint32), os_.view(np.uint32))
+    assert np.allclose(res.fold_accuracy, cor / tot)
+    # sklearn-like classifier
+    clf = tst.TsTForest(n_estimators=10, random_state=3).fit(v["X"], v["y"])
+    proba = clf.predict_proba(v["X"][:200])
+    assert proba.shape == (200, 4) and np.allclose(proba.sum(1), 1.0)
+    fold = np.full(len(v["y"]), H.FOLD_TRAIN_ONLY, np.uint8)
+    _, _, forest = H.fit_oof(v["bins"], v["y"], fold, 1, 10, 4, H.make_params(16), seed=3, keep=True)
+    assert np.array_equal(clf.predict_votes(v["X"][:200]), forest.predict_votes(v["bins"][:, :200].copy()))
+    gn, gc = clf.export_tree(4)
+    ot = forest.tree(0, 4)
+    compare_tree(gn, gc, ot.nodes, ot.counts, "forest tree 4")
+    assert (clf.predict(v["X"]) == v["y"]).mean() > 0.9  # fully grown trees memorise the training set
