@@ -353,6 +353,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint32_t small_per_warp = (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
     uint32_t* counters = h->counters.as<uint32_t>();  // [0],[1] big queue counts, [2] small count
+    g.qsmall_count = counters + 2;
 
     for (size_t b0 = 0; b0 < total_trees; b0 += B) {
         const uint32_t nb = (uint32_t)std::min(B, total_trees - b0);
