@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- RF trees fit/sec on the 1M x 64 scale-up table (BASELINE.json metric / configs[4]).
+
+    python bench.py --gpus N --steps K --warmup W          own arm (CUDA path, libtst.so)
+    python bench.py --impl reference --gpus N --steps K ... CPU arm: sklearn RandomForestClassifier (the
+                                                           paper's RF in its canonical implementation;
+                                                           the reference repo ships no code) on the host cores
+
+A "step" = one pass of the hot path: this rank's 10 folds x TREES_PER_FOLD trees (Philox bootstrap ->
+histogram / Gini split / partition growth -> OOF inference), the vote all-gather, and s(x).  Step s
+builds trees [s*T, (s+1)*T) of the 10-fold x 1000-tree job, so K steps are K disjoint slices of that
+job.  Weak scaling: every rank builds TREES_PER_FOLD trees per fold per step.
+
+value  : trees/s with the binned table resident in HBM (CUDA events, barrier both sides, max over ranks)
+e2e    : trees/s through tst.run_tst on HOST arrays -- pinned X/y H2D, bin-edge selection, binning, folds,
+         fit, s(x), and D2H of s / votes / folds inside the timed region.
+roofline: dominant kernel k_grow_big; algorithmic bytes = (15 + m) per row-level visit,
+         row visits counted on the device, duration = CUDA events around its launches inside libtst.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "test-set-training_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+N_ROWS, N_FEAT, N_CLASSES, K_FOLDS, N_TREES = 1_000_000, 64, 4, 10, 1000
+METRIC, UNIT = "rf_trees_fit_per_sec_1Mx64", "trees/s"
+
+
+def workload(trees_per_fold):
+    return dict(workload=f"scale-up table {N_ROWS}x{N_FEAT} f32, {N_CLASSES} classes, {K_FOLDS}-fold x {N_TREES} trees "
+                         f"(BASELINE.json configs[4]); step = {K_FOLDS} folds x {trees_per_fold} trees per GPU, full depth, "
+                         f"max_features=sqrt(64)=8, 256 bins",
+                rows=N_ROWS, features=N_FEAT, classes=N_CLASSES, folds=K_FOLDS, trees_per_fold_per_step=trees_per_fold,
+                l2="working set per step (binned tables 128 MB + ~30 MB per tree in flight) is far larger than the 126 MB L2; no explicit flush")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def dram_traffic_per_launch():
+    """dram bytes per k_grow_big launch from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "grow_big_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import sklearn_tst
+    from tst import synth
+
+    cores = sklearn_tst.usable_cores()
+    X, y = synth.scaleup_table(N_ROWS, N_FEAT, N_CLASSES, seed=0)
+    fold = (np.arange(N_ROWS) % K_FOLDS).astype(np.uint8)
+    train = fold != 0
+    Xt = X[fold == 0]
+    trees = max(1, cores)  # one tree per core per step: the smallest sample that keeps every core busy
+    times = []
+    for s in range(args.warmup + args.steps):
+        r = sklearn_tst.time_fit_sample(X, y, train, trees, seed=s, n_jobs=cores, X_test=Xt)
+        if s >= args.warmup:
+            times.append(r["seconds"])
+    total = float(sum(times))
+    value = trees * len(times) / total
+    import sklearn
+
+    sample = (f"{trees} trees per step on fold 0's {int(train.sum())} training rows + predict_proba of the {len(Xt)} held-out rows, "
+              f"sklearn {sklearn.__version__} RandomForestClassifier(n_jobs={cores}) defaults")
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=workload(trees),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
+                                  note="the reference repository ships no code; this is the committed sklearn restatement of the paper's RF diagnostic"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- own arm
+def cpu_baseline_port(X, y, bins_cm, fold):
+    """CPU histogram-RF oracle (same algorithm, same Philox streams) on the host cores: bounded sample."""
+    from oracle import hist_rf as H
+
+    cores = len(os.sched_getaffinity(0))
+    prm = H.make_params(N_FEAT)
+    per_fold = max(1, (2 * cores + K_FOLDS - 1) // K_FOLDS)
+    t = time.perf_counter()
+    _, st, _ = H.fit_oof(bins_cm, y, fold, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=0, t1=per_fold, nthreads=cores)
+    dt = time.perf_counter() - t
+    trees = K_FOLDS * per_fold
+    return dict(value=trees / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{trees} trees ({per_fold} per fold) of the same job with oracle/hist_rf.c (OpenMP, {cores} threads), {dt:.1f} s"), st
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--trees-per-fold", type=int, default=int(os.environ.get("TST_BENCH_TREES_PER_FOLD", "32")))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3  # timing rules: W >= 3
+
+    import torch
+    import torch.distributed as dist
+
+    import tst
+    from tst import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- setup (untimed): synthetic table, resident binned copy, folds
+    T = args.trees_per_fold
+    X, y = synth.scaleup_table(N_ROWS, N_FEAT, N_CLASSES, seed=0)
+    eng = tst.Engine(local_rank, rank, world)
+    edges, n_edges = tst.binning.table_edges(X)
+    eng.bin(X, edges=edges, n_edges=n_edges)
+    classes, yi = tst.api.encode_labels(y)
+    y_dev = eng.to_dev(yi, torch.uint8)
+    active = torch.ones(N_ROWS, dtype=torch.uint8, device=eng.dev)
+    fold_dev = eng.assign_folds(y_dev, active, K_FOLDS, N_CLASSES)
+    prm = tst.make_params(N_FEAT)
+    votes = eng.new_votes(N_CLASSES)
+    m = prm.max_features
+
+    def step(i):
+        # trees [i*T*world, (i+1)*T*world) of every fold; this rank builds its T per fold (lid % world == rank)
+        lo = (i * T * world) % N_TREES
+        hi = min(N_TREES, lo + T * world)
+        eng.fit_oof(y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=lo, t1=hi, votes=votes)
+        total = eng.allreduce_votes(votes)
+        return eng.finalize(total, y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    eng.stats(reset=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            s_dev, _, _ = step(args.warmup + i)
+        ev1.record()
+        barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    st = eng.stats()
+    trees_per_rank = int(st["trees"])
+    trees_total = trees_per_rank * world  # weak scaling: every rank builds the same count
+    value = trees_total / (ms / 1e3)
+    clocks = clk.summary()
+
+    # ---- roofline of the dominant kernel (k_grow_big), algorithmic bytes per SURVEY 8(d)
+    peak, peak_src = measured_hbm_peak()
+    alg_bytes = (15 + m) * st["row_visits_big"]
+    achieved = alg_bytes / (st["ms_grow_big"] / 1e3) / 1e9 if st["ms_grow_big"] > 0 else 0.0
+    roofline = dict(bound="hbm", kernel="k_grow_big", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                    traffic=dram_traffic_per_launch(), peak_source=peak_src,
+                    algorithmic_bytes_per_launch=alg_bytes / max(1, st["launches_grow_big"]),
+                    avg_launch_ms=st["ms_grow_big"] / max(1, st["launches_grow_big"]), launches=int(st["launches_grow_big"]),
+                    kernel_share_of_step=st["ms_grow_big"] / ms,
+                    whole_tree=dict(algorithmic_bytes_per_tree=((15 + m) * (st["row_visits_big"] + st["row_visits_small"]) + st["inbag_rows"]
+                                                                + 9 * st["oof_steps"]) / max(1, trees_per_rank),
+                                    ms_small=st["ms_grow_small"], ms_infer=st["ms_infer"], ms_prep=st["ms_prep"]))
+    gpu_launches = int(st["kernel_launches"])
+
+    # ---- e2e through the public API on host buffers
+    e2e = None
+    if not args.no_e2e:
+        Xp = torch.from_numpy(X).pin_memory()
+        yp = y
+        h2d = X.nbytes + yi.nbytes
+        d2h = N_ROWS * 4 + N_ROWS * N_CLASSES * 4 + N_ROWS
+        e2e_steps = max(1, min(args.steps, 3))
+        tst.run_tst(Xp, yp, k=K_FOLDS, n_trees=N_TREES, seed=0, tree_range=(0, T * world), engine=eng)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            lo = ((i + 1) * T * world) % N_TREES
+            res = tst.run_tst(Xp, yp, k=K_FOLDS, n_trees=N_TREES, seed=0, tree_range=(lo, min(N_TREES, lo + T * world)), engine=eng)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = dict(value=K_FOLDS * T * world * e2e_steps / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   steps=e2e_steps, ms_per_step=1e3 * dt / e2e_steps,
+                   note="tst.run_tst on host arrays: pinned H2D of X/y, host bin-edge selection, GPU binning, folds, fit, s(x), D2H of s/votes/folds")
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic", config=workload(T),
+                roofline=roofline, e2e=e2e, gpu_launches=gpu_launches, clocks=clocks,
+                trees_per_step=trees_total // max(1, args.steps), nodes_per_tree=st["nodes"] / max(1, trees_per_rank),
+                max_depth=int(st["max_depth"]))
+
+    if rank == 0 and world == 1:
+        if not args.no_cpu:
+            bins_cm = eng.get_bins()
+            fold_h = fold_dev.cpu().numpy()
+            line["cpu_baseline"], _ = cpu_baseline_port(X, yi, bins_cm, fold_h)
+        if not args.no_secondary:
+            line["secondary"] = secondary_wallclock(tst, synth)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def secondary_wallclock(tst, synth):
+    """BASELINE.json's second metric: end-to-end TsT + IBP wall-clock on the VSI-shaped table (latency-bound)."""
+    import torch
+
+    X, y = synth.vsi_table()
+    out = {}
+    tst.run_tst(X, y, k=5, n_trees=100, seed=0)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    r = tst.run_tst(X, y, k=5, n_trees=100, seed=1)
+    out["tst_vsi_5k_x32_5fold_x100_ms"] = 1e3 * (time.perf_counter() - t)
+    out["tst_vsi_kernel_launches"] = int(r.stats["kernel_launches"])
+    t = time.perf_counter()
+    rb = tst.ibp(X, y, rounds=10, k=5, n_trees=200, tau=0.5, batch=250, seed=0, want_s=False)
+    out["ibp_10rounds_5fold_x200_ms"] = 1e3 * (time.perf_counter() - t)
+    out["ibp_removed_per_round"] = rb.removed_per_round.tolist()
+    out["note"] = "host arrays in, host arrays out; latency-bound (5k rows): reported as wall-clock, not bandwidth"
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -106,7 +106,7 @@ class Engine:
     def to_dev(self, a, dtype):
         torch = _torch()
         if isinstance(a, torch.Tensor):
-            return a.to(device=self.dev, dtype=dtype).contiguous()
+            return a.to(device=self.dev, dtype=dtype, non_blocking=True).contiguous()
         t = torch.from_numpy(np.ascontiguousarray(a))
         return t.to(device=self.dev, dtype=dtype, non_blocking=True).contiguous()
 
