@@ -9,6 +9,7 @@
 
 #include "tst_common.cuh"
 #include "tst_grow.cuh"
+#include "tst_grow_small.cuh"
 #include "tst_prep.cuh"
 
 // --------------------------------------------------------------------------------------------- errors
@@ -124,6 +125,7 @@ static int set_kernel_attrs(tst_handle* h) {
     if (h->attrs_set) return 0;
     CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET));
     CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_bin_map, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(k_cm_to_rm, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     h->attrs_set = true;
@@ -350,7 +352,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.MB = (int)std::min<size_t>(std::min<size_t>(32, (size_t)g.m), std::max<size_t>(1, BIG_SMEM_BUDGET / ((size_t)g.FS * 4)));
     const size_t big_smem = (size_t)g.MB * g.FS * 4;
     if (big_smem > BIG_SMEM_BUDGET) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
-    const uint32_t small_per_warp = (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
+    const bool small_packed = C <= 4;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
+    const uint32_t small_per_warp = small_packed ? 32u + 96u + (uint32_t)((d + 1) / 2)
+                                                 : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
     uint32_t* counters = h->counters.as<uint32_t>();  // [0],[1] big queue counts, [2] small count
     g.qsmall_count = counters + 2;
@@ -417,7 +421,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             uint32_t blocks = (nsmall + SMALL_WARPS - 1) / SMALL_WARPS;
             blocks = std::min<uint32_t>(blocks, (uint32_t)h->sm_count * 64u);
             CK(cudaEventRecord(h->ev0, st));
-            k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
             CKL();
             CK(cudaEventRecord(h->ev1, st));
             h->stats.kernel_launches++; h->stats.launches_grow_small++;

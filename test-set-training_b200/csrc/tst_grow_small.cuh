@@ -1,0 +1,203 @@
+// tst_grow_small.cuh -- warp-per-subtree kernel for nodes with <= 32 distinct rows, <= 4 classes.
+//
+// Same arithmetic as k_grow_small (tst_grow.cuh) but register-only:
+//   * class counts are packed 4 x 13 bits in one 64-bit word (a node of <= 32 rows x multiplicity
+//     <= 255 weighs <= 8160 < 2^13), the row's bin rides in bits 52..59, so "weights left of my
+//     threshold" is one compare + one 64-bit add per broadcast row;
+//   * the warp is cut into groups of G = 4 / 8 / 16 / 32 lanes (G >= rows in the node) and every
+//     group evaluates a different sampled feature, so a 4-row node evaluates 8 features at once.
+// Bit-exact with oracle/hist_rf.c: candidates are the occupied bins, gain in fp64, ties -> lowest
+// (feature, bin); fallback draws take the first feature in draw order that separates the rows.
+#pragma once
+#include "tst_grow.cuh"
+
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__device__ __forceinline__ void warp_argmax(double& gn, uint32_t& key) {
+    // (gain desc, key asc); every lane ends with the winner
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        double og = __shfl_xor_sync(0xffffffffu, gn, off);
+        uint32_t ok = __shfl_xor_sync(0xffffffffu, key, off);
+        if (og > gn || (og == gn && ok < key)) { gn = og; key = ok; }
+    }
+}
+
+#define F13(x, c) ((uint32_t)((x) >> (13 * (c))) & 0x1FFFu)
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_grow_small4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+    extern __shared__ uint32_t s_mem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int C = g.C, d = g.d, m = g.m;
+    // per-warp shared layout (words): src[32] | stack[32][3] | perm[(d+1)/2]
+    const uint32_t per_warp = 32u + 96u + (uint32_t)((d + 1) / 2);
+    uint32_t* s_src = s_mem + warp * per_warp;
+    uint32_t* s_stack = s_src + 32;
+    uint16_t* s_perm = (uint16_t*)(s_stack + 96);
+    const uint8_t* __restrict__ bins = g.bins_rm;
+    const uint32_t dstride = g.dstride;
+
+    for (uint32_t ti = blockIdx.x * WARPS + warp; ti < ntasks; ti += gridDim.x * WARPS) {
+        const Task t = tasks[ti];
+        const TreeDesc td = g.trees[t.tree];
+        const uint32_t* __restrict__ ent = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+        uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
+        uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
+        const uint32_t r = t.end - t.begin;
+        uint32_t e = lane < r ? ent[t.begin + lane] : 0u;
+        uint32_t cls = lane < r ? (uint32_t)g.y[e & ROW_MASK] : 0u;
+        uint32_t lo = 0, hi = r, depth = t.depth, slot = t.slot, sp = 0;
+        unsigned long long visits = 0, n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0;
+        uint32_t maxd = 0;
+        while (true) {
+            const bool active = lane >= lo && lane < hi;
+            const uint32_t rr = hi - lo;
+            const uint32_t abs_begin = t.begin + lo;
+            const unsigned long long cw = active ? ((unsigned long long)(e >> 24) << (13u * cls)) : 0ull;
+            const unsigned long long tot = warp_sum64(cw);
+            const uint32_t t0 = F13(tot, 0), t1 = F13(tot, 1), t2 = F13(tot, 2), t3 = F13(tot, 3);
+            const uint32_t N = t0 + t1 + t2 + t3;
+            const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
+            n_nodes++;
+            maxd = max(maxd, depth);
+            bool found = false;
+            double best_gain = -1.0;
+            uint32_t best_key = 0xFFFFFFFFu;
+            if (!stop_rule(g, N, depth, pure)) {
+                visits += rr;
+                n_search++;
+                // group layout: G lanes per feature
+                const uint32_t gshift = rr <= 4 ? 2u : (rr <= 8 ? 3u : (rr <= 16 ? 4u : 5u));
+                const uint32_t G = 1u << gshift, nf = 32u >> gshift;
+                const uint32_t gi = lane >> gshift, sub = lane & (G - 1u), gbase = lane & ~(G - 1u);
+                const bool gvalid = sub < rr;
+                const uint32_t srcl = lo + (gvalid ? sub : 0u);
+                const uint32_t e_g = __shfl_sync(0xffffffffu, e, srcl);
+                const uint32_t cls_g = __shfl_sync(0xffffffffu, cls, srcl);
+                const unsigned long long cw_g = gvalid ? ((unsigned long long)(e_g >> 24) << (13u * cls_g)) : 0ull;
+                const uint8_t* __restrict__ rowp = bins + (uint64_t)(e_g & ROW_MASK) * dstride;
+                for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
+                __syncwarp();
+                for (int pos0 = 0; pos0 < d;) {
+                    if (pos0 >= m && found) break;
+                    const int limit = pos0 < m ? m : d;
+                    const int nfc = min((int)nf, limit - pos0);
+                    if (lane == 0) {  // extend the node's Fisher-Yates draw to positions [pos0, pos0 + nfc)
+                        uint4 rnd = make_uint4(0, 0, 0, 0);
+                        for (int i = pos0; i < pos0 + nfc; ++i) {
+                            if (i == pos0 || (i & 3) == 0)
+                                rnd = philox4x32_10(abs_begin, depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);
+                            int j = i + (int)mulhi32(pick4(rnd, i & 3), (uint32_t)(d - i));
+                            uint16_t fj = s_perm[j];
+                            s_perm[j] = s_perm[i];
+                            s_perm[i] = fj;
+                        }
+                        if (pos0 == m) n_fb++;
+                    }
+                    __syncwarp();
+                    const bool pvalid = (int)gi < nfc;
+                    const uint32_t pos = (uint32_t)pos0 + (pvalid ? gi : 0u);
+                    const uint32_t f = s_perm[pos];
+                    const bool lv = gvalid && pvalid;
+                    const uint32_t b = lv ? (uint32_t)rowp[f] : 0u;
+                    const unsigned long long P = cw_g | ((unsigned long long)b << 52);
+                    unsigned long long acc = 0;
+                    for (uint32_t kk = 0; kk < rr; ++kk) {
+                        unsigned long long Pk = __shfl_sync(0xffffffffu, P, gbase + kk);
+                        if ((uint32_t)(Pk >> 52) <= b) acc += Pk;
+                    }
+                    const uint32_t L0 = F13(acc, 0), L1 = F13(acc, 1), L2 = F13(acc, 2), L3 = F13(acc, 3);
+                    const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+                    const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
+                    const bool ok = lv && NL >= g.msl && NR >= g.msl;
+                    double gn = -1.0;
+                    uint32_t key = 0xFFFFFFFFu;
+                    if (ok) {
+                        unsigned long long SL = (unsigned long long)L0 * L0 + (unsigned long long)L1 * L1 + (unsigned long long)L2 * L2 + (unsigned long long)L3 * L3;
+                        unsigned long long SR = (unsigned long long)R0 * R0 + (unsigned long long)R1 * R1 + (unsigned long long)R2 * R2 + (unsigned long long)R3 * R3;
+                        gn = gini_gain(SL, NL, SR, NR);
+                        key = (f << 8) | b;
+                    }
+                    if (pos0 < m) {
+                        warp_argmax(gn, key);
+                        if (key != 0xFFFFFFFFu && (gn > best_gain || (gn == best_gain && key < best_key))) {
+                            best_gain = gn; best_key = key; found = true;
+                        }
+                    } else {
+                        // fallback: the first position in draw order that has any valid split
+                        uint32_t mp = ok ? pos : 0xFFFFFFFFu;
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) mp = min(mp, __shfl_xor_sync(0xffffffffu, mp, off));
+                        if (mp != 0xFFFFFFFFu) {
+                            if (!(ok && pos == mp)) { gn = -1.0; key = 0xFFFFFFFFu; }
+                            warp_argmax(gn, key);
+                            best_gain = gn; best_key = key; found = true;
+                        }
+                    }
+                    pos0 += nfc;
+                }
+            }
+            if (!found) {
+                n_leaves++;
+                if (pure) {
+                    const uint32_t pc = t0 == N ? 0u : (t1 == N ? 1u : (t2 == N ? 2u : 3u));
+                    if (lane == 0) write_pure_leaf(nodes, slot, N, pc);
+                } else {
+                    if ((int)lane < C) leafc[(uint64_t)(abs_begin >> 1) * C + lane] = F13(tot, lane);
+                    if (lane == 0) write_mixed_leaf(nodes, slot, abs_begin);
+                }
+                if (sp == 0) break;
+                --sp;
+                uint32_t lh = s_stack[sp * 3];
+                lo = lh & 0xFFu; hi = lh >> 8; depth = s_stack[sp * 3 + 1]; slot = s_stack[sp * 3 + 2];
+                __syncwarp();
+                continue;
+            }
+            // partition inside the warp (stable)
+            const uint32_t bf = best_key >> 8, bb = best_key & 0xFFu;
+            const bool goL = active && bins[(uint64_t)(e & ROW_MASK) * dstride + bf] <= bb;
+            const uint32_t balL = __ballot_sync(0xffffffffu, goL);
+            const uint32_t balR = __ballot_sync(0xffffffffu, active && !goL);
+            const uint32_t nLd = __popc(balL);
+            if (nLd == 0 || nLd == rr) {  // cannot happen for a valid split; never loop on it
+                if (lane == 0) g.stats->error = 4;
+                break;
+            }
+            uint32_t dest = lane;
+            if (goL) dest = lo + __popc(balL & lanemask_lt());
+            else if (active) dest = lo + nLd + __popc(balR & lanemask_lt());
+            s_src[dest] = lane;
+            __syncwarp();
+            const uint32_t src = s_src[lane];
+            __syncwarp();
+            e = __shfl_sync(0xffffffffu, e, src);
+            cls = __shfl_sync(0xffffffffu, cls, src);
+            const uint32_t right_slot = slot + 2u * nLd;
+            if (lane == 0) {
+                write_internal(nodes, slot, right_slot, bf, bb);
+                s_stack[sp * 3] = (lo + nLd) | (hi << 8);
+                s_stack[sp * 3 + 1] = depth + 1u;
+                s_stack[sp * 3 + 2] = right_slot;
+            }
+            __syncwarp();
+            sp++;
+            hi = lo + nLd;
+            depth += 1u;
+            slot += 1u;
+        }
+        if (lane == 0) {
+            atomicAdd(&g.stats->row_visits_small, visits);
+            atomicAdd(&g.stats->nodes, n_nodes);
+            atomicAdd(&g.stats->leaves, n_leaves);
+            atomicAdd(&g.stats->searched, n_search);
+            if (n_fb) atomicAdd(&g.stats->fallback, n_fb);
+            atomicMax(&g.stats->max_depth, maxd);
+        }
+        __syncwarp();
+    }
+}
