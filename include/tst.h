@@ -75,6 +75,8 @@ typedef struct {
     double ms_infer;
     uint64_t launches_grow_big;
     uint64_t launches_grow_small;
+    double ms_grow_mid;         /* warp-per-node kernel (k_grow_mid) */
+    uint64_t launches_grow_mid;
 } tst_stats;
 
 /* Canonical tree export: nodes in breadth-first order, i.e. sorted by (depth, begin). */

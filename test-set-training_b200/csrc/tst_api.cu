@@ -10,6 +10,7 @@
 #include "tst_common.cuh"
 #include "tst_grow.cuh"
 #include "tst_grow_small.cuh"
+#include "tst_grow_mid.cuh"
 #include "tst_prep.cuh"
 
 // --------------------------------------------------------------------------------------------- errors
@@ -61,7 +62,7 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qsmall, counters, dstats, infer_parts;
+        qmid0, qmid1, qsmall, counters, dstats, infer_parts;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
@@ -70,13 +71,15 @@ struct tst_handle {
     // ibp / predict scratch
     DevBuf ibp_fold, ibp_votes, ibp_removed, pred_cm, pred_rm;
     uint32_t* h_pinned = nullptr;  // 16 words
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     tst_stats stats;
     bool attrs_set = false;
 };
 
 static const int BIG_THREADS = 256;
 static const int SMALL_WARPS = 4;
+static const int MID_WARPS = 8;
+static const int MID_R = 8;  // warp-per-node tier holds up to 32 * MID_R rows in registers
 static const size_t BIG_SMEM_BUDGET = 64 * 1024;
 
 extern "C" int tst_abi_version(void) { return TST_ABI_VERSION; }
@@ -102,6 +105,7 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     CK(cudaMallocHost((void**)&h->h_pinned, 64));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreate(&h->ev2));
     *out = h;
     return TST_OK;
 }
@@ -111,12 +115,13 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qsmall, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qsmall, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm};
     for (DevBuf* b : bufs) b->release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
     delete h;
     return TST_OK;
 }
@@ -126,6 +131,8 @@ static int set_kernel_attrs(tst_handle* h) {
     CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET));
     CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_bin_map, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(k_cm_to_rm, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     h->attrs_set = true;
@@ -299,12 +306,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint64_t leafc_stride = (n_cap / 2 + 1) * (uint64_t)C;
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / 8 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
-    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 2 * n_cap * 4 + (2 * qbig_per + qsmall_per) * sizeof(Task) + sizeof(TreeDesc);
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 2 * n_cap * 4 + (4 * qbig_per + qsmall_per) * sizeof(Task) + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
-                     h->qbig0.cap + h->qbig1.cap + h->qsmall.cap + h->keep_nodes.cap + h->keep_leafc.cap;
+                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qsmall.cap + h->keep_nodes.cap + h->keep_leafc.cap;
     size_t budget = (size_t)((free_b + reclaim) * 0.6);
     if (keep) {
         size_t need = total_trees * arena_bytes;
@@ -324,6 +331,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->entB, B * n_cap * 4);
     ENSURE(h->qbig0, B * qbig_per * sizeof(Task));
     ENSURE(h->qbig1, B * qbig_per * sizeof(Task));
+    ENSURE(h->qmid0, B * qbig_per * sizeof(Task));
+    ENSURE(h->qmid1, B * qbig_per * sizeof(Task));
     ENSURE(h->qsmall, B * qsmall_per * sizeof(Task));
     ENSURE(h->infer_parts, (size_t)n_groups * k * sizeof(InferPart));
     uint2* nodes_p; uint32_t* leafc_p;
@@ -356,8 +365,14 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint32_t small_per_warp = small_packed ? 32u + 96u + (uint32_t)((d + 1) / 2)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
-    uint32_t* counters = h->counters.as<uint32_t>();  // [0],[1] big queue counts, [2] small count
+    uint32_t* counters = h->counters.as<uint32_t>();  // [0],[1] big queue counts, [2] small count, [3],[4] mid queue counts
     g.qsmall_count = counters + 2;
+    const bool mid_packed = C <= 4;  // packed 16-bit class counts (k_grow_mid4)
+    const uint32_t mid_per_warp = mid_packed ? MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2)
+                                             : (uint32_t)g.FS + 2u * (uint32_t)C + (uint32_t)((d + 1) / 2);
+    const size_t mid_smem = (size_t)MID_WARPS * mid_per_warp * 4;
+    g.mid_max = mid_smem <= 200 * 1024 ? 32u * MID_R : SMALL_MAX;
+    if (const char* ev = getenv("TST_MID_MAX")) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)atoi(ev)));
 
     for (size_t b0 = 0; b0 < total_trees; b0 += B) {
         const uint32_t nb = (uint32_t)std::min(B, total_trees - b0);
@@ -382,37 +397,54 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             CKL();
             k_boot_scatter<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), g.entA, n_cap);
             CKL();
-            g.qnext = nullptr; g.qnext_count = nullptr;
-            k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb, h->qbig0.as<Task>(), counters + 0);
+            g.qnext = h->qbig0.as<Task>(); g.qnext_count = counters + 0;
+            g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 3;
+            k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb);
             CKL();
             h->stats.kernel_launches += 5;
         }
         CK(cudaEventRecord(h->ev1, st));
-        CK(cudaMemcpyAsync(h->h_pinned, counters, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->h_pinned, counters, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_prep += ms; }
 
-        // ---- level-synchronous growth of the nodes with > 32 rows
+        // ---- level-synchronous growth: CTA per node (> mid_max rows) and warp per node (33 .. mid_max rows)
         int cur = 0;
         uint64_t level_guard = 0;
-        uint32_t nbig = h->h_pinned[0];
-        while (nbig > 0) {
+        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[3];
+        while (nbig > 0 || nmid > 0) {
             Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
+            Task* qmcur = cur ? h->qmid1.as<Task>() : h->qmid0.as<Task>();
             g.qnext = cur ? h->qbig0.as<Task>() : h->qbig1.as<Task>();
             g.qnext_count = counters + (cur ^ 1);
+            g.qmid_next = cur ? h->qmid0.as<Task>() : h->qmid1.as<Task>();
+            g.qmid_next_count = counters + 3 + (cur ^ 1);
             CK(cudaMemsetAsync(g.qnext_count, 0, 4, st));
+            CK(cudaMemsetAsync(g.qmid_next_count, 0, 4, st));
             CK(cudaEventRecord(h->ev0, st));
-            k_grow_big<BIG_THREADS><<<nbig, BIG_THREADS, big_smem, st>>>(g, qcur, nbig);
-            CKL();
+            if (nbig) {
+                k_grow_big<BIG_THREADS><<<nbig, BIG_THREADS, big_smem, st>>>(g, qcur, nbig);
+                CKL();
+                h->stats.kernel_launches++; h->stats.launches_grow_big++;
+            }
             CK(cudaEventRecord(h->ev1, st));
-            CK(cudaMemcpyAsync(h->h_pinned, counters, 16, cudaMemcpyDeviceToHost, st));
+            if (nmid) {
+                if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(nmid + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, nmid);
+                else k_grow_mid<MID_WARPS, MID_R><<<(nmid + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, nmid);
+                CKL();
+                h->stats.kernel_launches++; h->stats.launches_grow_mid++;
+            }
+            CK(cudaEventRecord(h->ev2, st));
+            CK(cudaMemcpyAsync(h->h_pinned, counters, 32, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_big += ms; }
-            h->stats.kernel_launches++; h->stats.launches_grow_big++; h->stats.levels++;
+            { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_big += ms;
+              cudaEventElapsedTime(&ms, h->ev1, h->ev2); h->stats.ms_grow_mid += ms; }
+            h->stats.levels++;
             cur ^= 1;
             nbig = h->h_pinned[cur];
+            nmid = h->h_pinned[3 + cur];
             if (++level_guard > n_cap + 2) return fail(TST_ERR_STATE, "tree growth did not terminate");
-            if (nbig > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "big-node queue overflowed");
+            if (nbig > g.qbig_cap || nmid > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
         // ---- subtrees with <= 32 rows: one warp each
         const uint32_t nsmall = h->h_pinned[2];

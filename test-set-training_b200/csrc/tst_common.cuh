@@ -89,6 +89,9 @@ struct GrowCtx {
     Task* qnext;      // big-node queue for the next level
     uint32_t* qnext_count;
     uint32_t qbig_cap;
+    Task* qmid_next;  // warp-per-node queue for the next level (SMALL_MAX < rows <= mid_max)
+    uint32_t* qmid_next_count;
+    uint32_t mid_max; // == SMALL_MAX disables the mid tier
     Task* qsmall;
     uint32_t* qsmall_count;
     uint32_t qsmall_cap;

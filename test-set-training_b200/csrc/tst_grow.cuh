@@ -30,6 +30,50 @@ __device__ __forceinline__ bool stop_rule(const GrowCtx& g, uint32_t N, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// One thread finishes a split: internal node record, leaf children written in place, other children
+// routed by size to the CTA-per-node queue, the warp-per-node queue or the warp-per-subtree queue.
+__device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint2* nodes, uint32_t* leafc,
+                                           const uint32_t* tot, const uint32_t* bestL, uint32_t N, uint32_t nLd,
+                                           uint32_t bf, uint32_t bb) {
+    const int C = g.C;
+    uint32_t NL = 0;
+    for (int c = 0; c < C; ++c) NL += bestL[c];
+    const uint32_t NR = N - NL;
+    const uint32_t right_slot = t.slot + 2u * nLd;
+    write_internal(nodes, t.slot, right_slot, bf, bb);
+    unsigned long long new_leaves = 0;
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t cb = side ? t.begin + nLd : t.begin, ce = side ? t.end : t.begin + nLd;
+        const uint32_t cslot = side ? right_slot : t.slot + 1u;
+        const uint32_t Nc = side ? NR : NL;
+        int pc = -1;
+        for (int c = 0; c < C; ++c) {
+            uint32_t v = side ? tot[c] - bestL[c] : bestL[c];
+            if (v == Nc) pc = c;
+        }
+        if (stop_rule(g, Nc, t.depth + 1u, pc >= 0)) {
+            if (pc >= 0) write_pure_leaf(nodes, cslot, Nc, (uint32_t)pc);
+            else {
+                for (int c = 0; c < C; ++c) leafc[(uint64_t)(cb >> 1) * C + c] = side ? tot[c] - bestL[c] : bestL[c];
+                write_mixed_leaf(nodes, cslot, cb);
+            }
+            new_leaves++;
+        } else {
+            Task ct;
+            ct.tree = t.tree; ct.begin = cb; ct.end = ce; ct.depth = t.depth + 1u; ct.slot = cslot;
+            ct.pad0 = ct.pad1 = ct.pad2 = 0;
+            const uint32_t cr = ce - cb;
+            if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
+            else if (cr > SMALL_MAX) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
+            else queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
+        }
+    }
+    atomicAdd(&g.stats->nodes, 1ull + new_leaves);
+    if (new_leaves) { atomicAdd(&g.stats->leaves, new_leaves); atomicMax(&g.stats->max_depth, t.depth + 1u); }
+    atomicAdd(&g.stats->searched, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Split scan of one feature histogram by one warp.  Lane l owns bins [8l, 8l+8).  Per class: local
 // inclusive prefix, warp-shuffle exclusive scan of the lane totals, then L/R sums of squares are
 // accumulated exactly in uint64.  Returns the warp-wide best (gain, bin) with ties -> lowest bin.
@@ -276,40 +320,7 @@ __global__ void __launch_bounds__(THREADS) k_grow_big(GrowCtx g, const Task* __r
 
     // ---- node record + children (leaf children are finished here, the rest are queued)
     if (tid == 0) {
-        uint32_t NL = 0;
-        for (int c = 0; c < C; ++c) NL += s_bestL[c];
-        const uint32_t NR = s_N - NL;
-        const uint32_t right_slot = t.slot + 2u * nLd;
-        write_internal(nodes, t.slot, right_slot, bf, bb);
-        unsigned long long new_leaves = 0;
-        for (int side = 0; side < 2; ++side) {
-            const uint32_t cb = side ? t.begin + nLd : t.begin, ce = side ? t.end : t.begin + nLd;
-            const uint32_t cslot = side ? right_slot : t.slot + 1u;
-            const uint32_t Nc = side ? NR : NL;
-            int pc = -1;
-            for (int c = 0; c < C; ++c) {
-                uint32_t v = side ? s_tot[c] - s_bestL[c] : s_bestL[c];
-                if (v == Nc) pc = c;
-            }
-            if (stop_rule(g, Nc, t.depth + 1u, pc >= 0)) {
-                if (pc >= 0) write_pure_leaf(nodes, cslot, Nc, (uint32_t)pc);
-                else {
-                    for (int c = 0; c < C; ++c)
-                        leafc[(uint64_t)(cb >> 1) * C + c] = side ? s_tot[c] - s_bestL[c] : s_bestL[c];
-                    write_mixed_leaf(nodes, cslot, cb);
-                }
-                new_leaves++;
-            } else {
-                Task ct;
-                ct.tree = t.tree; ct.begin = cb; ct.end = ce; ct.depth = t.depth + 1u; ct.slot = cslot;
-                ct.pad0 = ct.pad1 = ct.pad2 = 0;
-                if (ce - cb > SMALL_MAX) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
-                else queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
-            }
-        }
-        atomicAdd(&g.stats->nodes, 1ull + new_leaves);
-        if (new_leaves) { atomicAdd(&g.stats->leaves, new_leaves); atomicMax(&g.stats->max_depth, t.depth + 1u); }
-        atomicAdd(&g.stats->searched, 1ull);
+        emit_split(g, t, nodes, leafc, s_tot, s_bestL, s_N, nLd, bf, bb);
         atomicAdd(&g.stats->row_visits_big, (unsigned long long)r);
     }
 }

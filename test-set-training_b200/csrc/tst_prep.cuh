@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(256) k_boot_scatter(const uint32_t* __restrict
         }
 }
 
-// Root tasks: empty tree -> empty leaf; <= 32 rows -> warp kernel; else first big level.
-__global__ void k_init_roots(GrowCtx g, uint32_t n_trees, Task* qbig, uint32_t* qbig_count) {
+// Root tasks: empty tree -> empty leaf; otherwise routed by size like any other node.
+__global__ void k_init_roots(GrowCtx g, uint32_t n_trees) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_trees) return;
     const TreeDesc td = g.trees[t];
@@ -316,7 +316,8 @@ __global__ void k_init_roots(GrowCtx g, uint32_t n_trees, Task* qbig, uint32_t* 
     }
     Task k;
     k.tree = t; k.begin = 0; k.end = td.n_inbag; k.depth = 0; k.slot = 0; k.pad0 = k.pad1 = k.pad2 = 0;
-    if (td.n_inbag > SMALL_MAX) queue_push(qbig, qbig_count, g.qbig_cap, g.stats, k);
+    if (td.n_inbag > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, k);
+    else if (td.n_inbag > SMALL_MAX) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, k);
     else queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, k);
 }
 
