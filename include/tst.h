@@ -77,6 +77,7 @@ typedef struct {
     uint64_t launches_grow_small;
     double ms_grow_mid;         /* warp-per-node kernel (k_grow_mid) */
     uint64_t launches_grow_mid;
+    uint64_t row_visits_mid;    /* ... by the warp-per-node kernel */
 } tst_stats;
 
 /* Canonical tree export: nodes in breadth-first order, i.e. sorted by (depth, begin). */

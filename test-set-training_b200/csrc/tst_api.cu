@@ -226,7 +226,7 @@ static int pull_stats(tst_handle* h, cudaStream_t st) {
     DevStats ds;
     CK(cudaMemcpyAsync(&ds, h->dstats.p, sizeof(ds), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    h->stats.row_visits_big += ds.row_visits_big; h->stats.row_visits_small += ds.row_visits_small;
+    h->stats.row_visits_big += ds.row_visits_big; h->stats.row_visits_mid += ds.row_visits_mid; h->stats.row_visits_small += ds.row_visits_small;
     h->stats.nodes += ds.nodes; h->stats.leaves += ds.leaves; h->stats.searched += ds.searched; h->stats.fallback += ds.fallback;
     h->stats.inbag_rows += ds.inbag_rows; h->stats.oof_steps += ds.oof_steps;
     h->stats.max_depth = std::max(h->stats.max_depth, ds.max_depth);

@@ -65,7 +65,7 @@ struct TreeDesc {  // one tree of the batch in flight
 };
 
 struct DevStats {
-    unsigned long long row_visits_big, row_visits_small, nodes, leaves, searched, fallback, oof_steps, inbag_rows;
+    unsigned long long row_visits_big, row_visits_mid, row_visits_small, nodes, leaves, searched, fallback, oof_steps, inbag_rows;
     uint32_t max_depth;
     uint32_t error;  // sticky: 1 = multiplicity overflow, 2 = queue overflow, 3 = bootstrap weight mismatch
 };

@@ -137,7 +137,7 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
 
 // ---------------------------------------------------------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(THREADS, 4) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     constexpr int NW = THREADS / 32;
     extern __shared__ uint32_t s_hist[];  // [MB][FS]
     __shared__ uint16_t s_perm[TST_MAX_FEATURES];
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(THREADS) k_grow_big(GrowCtx g, const Task* __r
     __shared__ double s_fgain[32];
     __shared__ uint32_t s_fbin[32];
     __shared__ uint32_t s_feat[32];
-    __shared__ uint32_t s_wl[2][NW], s_wr[2][NW];
+    __shared__ uint32_t s_wl[2][4][NW], s_wr[2][4][NW];
     __shared__ double s_bgain;
     __shared__ uint32_t s_bkey, s_found, s_newj, s_N, s_stop;
 
@@ -207,16 +207,43 @@ __global__ void __launch_bounds__(THREADS) k_grow_big(GrowCtx g, const Task* __r
                     rp[u] = bins + (uint64_t)row * dstride;
                     cls[u] = e[u] ? y[row] : 0u;
                 }
-                for (int jj = 0; jj < nb; ++jj) {
-                    int j = jj + (int)lane;  // rotate features across lanes: spreads the shared atomics
-                    j = j % nb;
-                    uint32_t f = s_feat[j];
-                    uint32_t b[U];
+                if (nb <= 8) {
+                    // all U x nb bin bytes are requested before the first atomic: 32 loads in flight per thread
+                    uint32_t lo[U], hi[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) b[u] = e[u] ? rp[u][f] : 0u;
+                    for (int u = 0; u < U; ++u) { lo[u] = 0; hi[u] = 0; }
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (e[u]) atomicAdd(&s_hist[j * g.FS + hist_index(b[u], cls[u], C)], e[u] >> 24);
+                    for (int jj = 0; jj < 8; ++jj) {
+                        if (jj < nb) {
+                            const uint32_t f = s_feat[jj];
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                uint32_t v = e[u] ? (uint32_t)rp[u][f] : 0u;
+                                if (jj < 4) lo[u] |= v << (8 * jj); else hi[u] |= v << (8 * (jj - 4));
+                            }
+                        }
+                    }
+                    for (int jj = 0; jj < nb; ++jj) {
+                        int j = jj + (int)lane;  // rotate features across lanes: spreads the shared atomics
+                        j = j % nb;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            uint32_t b = ((j < 4 ? lo[u] : hi[u]) >> (8 * (j & 3))) & 0xFFu;
+                            if (e[u]) atomicAdd(&s_hist[j * g.FS + hist_index(b, cls[u], C)], e[u] >> 24);
+                        }
+                    }
+                } else {
+                    for (int jj = 0; jj < nb; ++jj) {
+                        int j = jj + (int)lane;
+                        j = j % nb;
+                        uint32_t f = s_feat[j];
+                        uint32_t b[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) b[u] = e[u] ? rp[u][f] : 0u;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (e[u]) atomicAdd(&s_hist[j * g.FS + hist_index(b[u], cls[u], C)], e[u] >> 24);
+                    }
                 }
             }
         }
@@ -256,12 +283,15 @@ __global__ void __launch_bounds__(THREADS) k_grow_big(GrowCtx g, const Task* __r
         if (s_stop) break;
         if (s_newj != 0xFFFFFFFFu) {
             // left class counts of the new best split, kept because the histogram may be overwritten
-            uint32_t bb = s_bkey & 0xFFu;
-            for (int c = tid; c < C; c += THREADS) {
-                uint32_t L = 0;
-                const uint32_t* hf = s_hist + s_newj * g.FS;
-                for (uint32_t b = 0; b <= bb; ++b) L += hf[hist_index(b, c, C)];
-                s_bestL[c] = L;
+            const uint32_t bb = s_bkey & 0xFFu;
+            const uint32_t* hl = s_hist + s_newj * g.FS + lane * (8u * C + 1u);
+            for (int c = wid; c < C; c += NW) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v += (lane * 8u + q <= bb) ? hl[q * C + c] : 0u;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) s_bestL[c] = v;
             }
         }
         pos += nb;
@@ -292,25 +322,37 @@ __global__ void __launch_bounds__(THREADS) k_grow_big(GrowCtx g, const Task* __r
     const uint32_t bf = s_bkey >> 8, bb = s_bkey & 0xFFu;
     uint32_t lbase = 0, rbase = 0;
     int par = 0;
-    for (uint32_t c0 = t.begin; c0 < t.end; c0 += THREADS, par ^= 1) {
-        uint32_t idx = c0 + tid;
-        bool valid = idx < t.end;
-        uint32_t e = valid ? ent_in[idx] : 0u;
-        bool goL = valid && bins[(uint64_t)(e & ROW_MASK) * dstride + bf] <= bb;
-        uint32_t balL = __ballot_sync(0xffffffffu, goL);
-        uint32_t balR = __ballot_sync(0xffffffffu, valid && !goL);
-        if (lane == 0) { s_wl[par][wid] = __popc(balL); s_wr[par][wid] = __popc(balR); }
-        __syncthreads();
-        uint32_t pl = 0, pr = 0, tl = 0, tr = 0;
+    constexpr int PU = 4;  // chunks per barrier
+    for (uint32_t c0 = t.begin; c0 < t.end; c0 += THREADS * PU, par ^= 1) {
+        uint32_t e[PU], balL[PU], balR[PU];
+        bool goL[PU];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            uint32_t a = s_wl[par][w], b = s_wr[par][w];
-            if (w < (int)wid) { pl += a; pr += b; }
-            tl += a; tr += b;
+        for (int u = 0; u < PU; ++u) {
+            uint32_t idx = c0 + u * THREADS + tid;
+            e[u] = idx < t.end ? ent_in[idx] : 0u;
         }
-        if (goL) ent_out[t.begin + lbase + pl + __popc(balL & lanemask_lt())] = e;
-        else if (valid) ent_out[t.end - 1u - (rbase + pr + __popc(balR & lanemask_lt()))] = e;
-        lbase += tl; rbase += tr;
+#pragma unroll
+        for (int u = 0; u < PU; ++u) goL[u] = e[u] && bins[(uint64_t)(e[u] & ROW_MASK) * dstride + bf] <= bb;
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            balL[u] = __ballot_sync(0xffffffffu, goL[u]);
+            balR[u] = __ballot_sync(0xffffffffu, e[u] && !goL[u]);
+            if (lane == 0) { s_wl[par][u][wid] = __popc(balL[u]); s_wr[par][u][wid] = __popc(balR[u]); }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            uint32_t pl = 0, pr = 0, tl = 0, tr = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                uint32_t a = s_wl[par][u][w], b = s_wr[par][u][w];
+                if (w < (int)wid) { pl += a; pr += b; }
+                tl += a; tr += b;
+            }
+            if (goL[u]) ent_out[t.begin + lbase + pl + __popc(balL[u] & lanemask_lt())] = e[u];
+            else if (e[u]) ent_out[t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt()))] = e[u];
+            lbase += tl; rbase += tr;
+        }
     }
     const uint32_t nLd = lbase;
     if (nLd == 0 || nLd == r) {  // cannot happen for a valid split; never loop on it

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
             }
             atomicAdd(&g.stats->nodes, 1ull);
             atomicAdd(&g.stats->leaves, 1ull);
-            if (!stop) { atomicAdd(&g.stats->searched, 1ull); atomicAdd(&g.stats->row_visits_big, (unsigned long long)r); }
+            if (!stop) { atomicAdd(&g.stats->searched, 1ull); atomicAdd(&g.stats->row_visits_mid, (unsigned long long)r); }
             atomicMax(&g.stats->max_depth, t.depth);
         }
         return;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
     }
     if (lane == 0) {
         emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nLd, bf, bbin);
-        atomicAdd(&g.stats->row_visits_big, (unsigned long long)r);
+        atomicAdd(&g.stats->row_visits_mid, (unsigned long long)r);
     }
 }
 
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid4(GrowCtx g, const Task*
             }
             atomicAdd(&g.stats->nodes, 1ull);
             atomicAdd(&g.stats->leaves, 1ull);
-            if (!stop) { atomicAdd(&g.stats->searched, 1ull); atomicAdd(&g.stats->row_visits_big, (unsigned long long)r); }
+            if (!stop) { atomicAdd(&g.stats->searched, 1ull); atomicAdd(&g.stats->row_visits_mid, (unsigned long long)r); }
             atomicMax(&g.stats->max_depth, t.depth);
         }
         return;
@@ -388,6 +388,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid4(GrowCtx g, const Task*
     }
     if (lane == 0) {
         emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nLd, bf, bbin);
-        atomicAdd(&g.stats->row_visits_big, (unsigned long long)r);
+        atomicAdd(&g.stats->row_visits_mid, (unsigned long long)r);
     }
 }

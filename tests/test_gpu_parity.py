@@ -59,7 +59,7 @@ def run_both(eng, bins, y, fold, k, T, C, seed=0, keep=False, group=None, n_grou
 
 
 def check_stats(gst, ost):
-    assert gst["row_visits_big"] + gst["row_visits_small"] == ost["row_visits"]
+    assert gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"] == ost["row_visits"]
     for key in ("nodes", "leaves", "searched", "fallback", "inbag_rows", "trees", "oof_steps", "max_depth"):
         assert gst[key] == ost[key], f"stat {key}: gpu {gst[key]} oracle {ost[key]}"
 
