@@ -32,7 +32,7 @@ extern "C" {
 #define TST_MAX_EDGES 255        /* per feature; bins 0..254 + bin 255 for NaN */
 #define TST_MAX_CLASSES 32
 #define TST_MAX_FEATURES 1024
-#define TST_MAX_ROWS (1 << 24)   /* row id is packed in 24 bits next to the 8-bit multiplicity */
+#define TST_MAX_ROWS 0x7FFFFFF0  /* row ids are 32-bit; the tree-entry is (row, multiplicity | class << 8) */
 #define TST_FOLD_TRAIN_ONLY 254  /* row trains every tree, is never held out (plain fit) */
 #define TST_FOLD_INACTIVE 255    /* row pruned by IBP / not in the table */
 

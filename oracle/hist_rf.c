@@ -354,7 +354,7 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
                 const orc_params* prm, uint64_t seed, uint32_t gid_base, int32_t t0, int32_t t1,
                 int32_t rank, int32_t world, uint32_t* votes, orc_stats* stats, orc_forest** keep,
                 int32_t nthreads) {
-    if (n < 0 || n >= (1 << 24) || d < 1 || C < 1 || C > 256 || k < 1 || k > 250 || n_trees < 1 ||
+    if (n < 0 || n >= 0x7FFFFFF0LL || d < 1 || C < 1 || C > 256 || k < 1 || k > 250 || n_trees < 1 ||
         n_trees > 65535 || t0 < 0 || t1 > n_trees || t0 > t1 || world < 1 || rank < 0 || rank >= world ||
         prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2)
         return -1;

@@ -128,7 +128,7 @@ extern "C" int tst_destroy(tst_handle* h) {
 
 static int set_kernel_attrs(tst_handle* h) {
     if (h->attrs_set) return 0;
-    CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET));
+    CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -141,7 +141,7 @@ static int set_kernel_attrs(tst_handle* h) {
 
 // --------------------------------------------------------------------------------------------- binning
 static int alloc_table(tst_handle* h, int64_t n, int32_t d) {
-    if (n < 1 || n >= TST_MAX_ROWS) return fail(TST_ERR_INVALID, "table: need 1 <= n < 2^24 rows");
+    if (n < 1 || n >= TST_MAX_ROWS) return fail(TST_ERR_INVALID, "table: need 1 <= n < 2^31 - 16 rows");
     if (d < 1 || d > TST_MAX_FEATURES) return fail(TST_ERR_INVALID, "table: need 1 <= d <= 1024 features");
     h->n = n; h->d = d;
     h->ld = (n + 15) / 16 * 16;
@@ -306,7 +306,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint64_t leafc_stride = (n_cap / 2 + 1) * (uint64_t)C;
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / 8 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
-    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 2 * n_cap * 4 + (4 * qbig_per + qsmall_per) * sizeof(Task) + sizeof(TreeDesc);
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 2 * n_cap * sizeof(Entry) + (4 * qbig_per + qsmall_per) * sizeof(Task) + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
@@ -327,8 +327,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->counts8, B * n_pad);
     ENSURE(h->chunk_cnt, B * (size_t)n_chunks * 4);
     ENSURE(h->chunk_sum, B * (size_t)n_chunks * 4);
-    ENSURE(h->entA, B * n_cap * 4);
-    ENSURE(h->entB, B * n_cap * 4);
+    ENSURE(h->entA, B * n_cap * sizeof(Entry));
+    ENSURE(h->entB, B * n_cap * sizeof(Entry));
     ENSURE(h->qbig0, B * qbig_per * sizeof(Task));
     ENSURE(h->qbig1, B * qbig_per * sizeof(Task));
     ENSURE(h->qmid0, B * qbig_per * sizeof(Task));
@@ -349,18 +349,20 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
 
     GrowCtx g;
     memset(&g, 0, sizeof(g));
-    g.bins_rm = h->bins_rm.as<uint8_t>(); g.y = y_dev; g.dstride = h->dstride; g.d = d; g.C = C; g.m = prm->max_features;
+    g.bins_rm = h->bins_rm.as<uint8_t>(); g.dstride = h->dstride; g.d = d; g.C = C; g.m = prm->max_features;
     g.max_depth = prm->max_depth; g.mss = (uint32_t)prm->min_samples_split; g.msl = (uint32_t)prm->min_samples_leaf;
     g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
-    g.entA = h->entA.as<uint32_t>(); g.entB = h->entB.as<uint32_t>(); g.n_cap = n_cap;
+    g.entA = h->entA.as<Entry>(); g.entB = h->entB.as<Entry>(); g.n_cap = n_cap;
     g.nodes = nodes_p; g.node_stride = node_stride; g.leafc = leafc_p; g.leafc_stride = leafc_stride;
     g.trees = h->trees.as<TreeDesc>();
     g.qsmall = h->qsmall.as<Task>();
     g.stats = h->dstats.as<DevStats>();
     g.FS = 32 * (8 * C + 1);
     g.MB = (int)std::min<size_t>(std::min<size_t>(32, (size_t)g.m), std::max<size_t>(1, BIG_SMEM_BUDGET / ((size_t)g.FS * 4)));
-    const size_t big_smem = (size_t)g.MB * g.FS * 4;
-    if (big_smem > BIG_SMEM_BUDGET) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
+    g.big_tile = h->dstride <= 128 ? 1 : 0;  // cooperative whole-row fetch into a shared tile (rows of <= 128 bytes)
+    const size_t big_tile_bytes = g.big_tile ? (size_t)BIG_THREADS * ((h->dstride >> 2) + 1) * 4 : 0;
+    const size_t big_smem = (size_t)g.MB * g.FS * 4 + big_tile_bytes;
+    if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
     const bool small_packed = C <= 4;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
     const uint32_t small_per_warp = small_packed ? 32u + 96u + (uint32_t)((d + 1) / 2)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
@@ -395,7 +397,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             CKL();
             k_boot_scan<<<nb, 256, 0, st>>>(g.trees, n_chunks, h->chunk_cnt.as<uint32_t>(), h->chunk_sum.as<uint32_t>(), g.stats);
             CKL();
-            k_boot_scatter<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), g.entA, n_cap);
+            k_boot_scatter<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), y_dev, g.entA, n_cap);
             CKL();
             g.qnext = h->qbig0.as<Task>(); g.qnext_count = counters + 0;
             g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 3;

@@ -11,7 +11,6 @@
 #define KIND_INTERNAL 1u
 #define KIND_PURE 2u
 #define KIND_MIXED 3u
-#define ROW_MASK 0x00FFFFFFu
 #define SMALL_MAX 32u  // nodes with <= 32 distinct rows are finished by one warp (k_grow_small)
 
 // ---------------------------------------------------------------------------------------------
@@ -42,6 +41,13 @@ __host__ __device__ __forceinline__ uint32_t pick4(const uint4& v, uint32_t i) {
 __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 
 // ---------------------------------------------------------------------------------------------
+// One in-bag row of one tree: x = row id, y = bootstrap multiplicity | class << 8.  Real entries have
+// multiplicity >= 1, so y == 0 marks padding.  64-bit entries keep the class next to the row id
+// (no label gather in the hot loops) and leave the full 32 bits to the row id.
+typedef uint2 Entry;
+__device__ __forceinline__ uint32_t ent_w(const Entry& e) { return e.y & 0xFFu; }
+__device__ __forceinline__ uint32_t ent_cls(const Entry& e) { return e.y >> 8; }
+
 struct Task {  // 32 B, one node waiting for a split search
     uint32_t tree;   // batch-local tree index
     uint32_t begin;  // segment [begin, end) of the tree's in-bag entry list
@@ -72,14 +78,13 @@ struct DevStats {
 
 struct GrowCtx {
     const uint8_t* bins_rm;  // [n][dstride]
-    const uint8_t* y;
     uint32_t dstride;
     int32_t d, C, m;
     int32_t max_depth;
     uint32_t mss, msl;
     uint32_t k0, k1;  // Philox key = seed
-    uint32_t* entA;   // [trees][n_cap] ping
-    uint32_t* entB;   // pong
+    Entry* entA;      // [trees][n_cap] ping
+    Entry* entB;      // pong
     uint64_t n_cap;
     uint2* nodes;     // [arena slots][node_stride]
     uint64_t node_stride;
@@ -96,6 +101,7 @@ struct GrowCtx {
     uint32_t* qsmall_count;
     uint32_t qsmall_cap;
     DevStats* stats;
+    int32_t big_tile; // k_grow_big stages whole rows in shared memory (dstride <= 128)
     int32_t MB;       // features per shared-histogram batch
     int32_t FS;       // histogram words per feature = 32 * (8 * C + 1)
 };

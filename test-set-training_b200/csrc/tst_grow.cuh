@@ -136,10 +136,40 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-cooperative fetch of 32 binned rows (row-major table, `dstride` bytes each) into a shared tile.
+// Lane l owns row l of the tile; 16-byte pieces of a row are loaded by neighbouring lanes in ONE
+// instruction, so a 64-byte row costs one L1 wavefront and two L2 sectors instead of one sector per
+// sampled feature.  tile pitch = dstride/4 + 1 words: the per-row byte reads that follow are conflict-free.
+__device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, uint32_t dstride, uint32_t row, bool has,
+                                             uint32_t* tile /* this warp's 32 x pitch words */, uint32_t lane) {
+    const uint32_t P = dstride >> 4, pitch = (dstride >> 2) + 1u;
+    for (uint32_t i0 = 0; i0 < 32u * P; i0 += 128u) {
+        uint4 v[4];
+        uint32_t rs[4], pt[4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t idx = i0 + q * 32u + lane;
+            rs[q] = idx / P; pt[q] = idx - rs[q] * P;
+            uint32_t rid = __shfl_sync(0xffffffffu, row, rs[q] & 31u);
+            ok[q] = __shfl_sync(0xffffffffu, has ? 1u : 0u, rs[q] & 31u) && idx < 32u * P;
+            if (ok[q]) v[q] = __ldg((const uint4*)(bins + (uint64_t)rid * dstride) + pt[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (ok[q]) {
+                uint32_t* dst = tile + rs[q] * pitch + pt[q] * 4u;
+                dst[0] = v[q].x; dst[1] = v[q].y; dst[2] = v[q].z; dst[3] = v[q].w;
+            }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 4) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     constexpr int NW = THREADS / 32;
-    extern __shared__ uint32_t s_hist[];  // [MB][FS]
+    extern __shared__ uint32_t s_hist[];  // [MB][FS] histogram, then (row tile) [THREADS][dstride/4 + 1]
     __shared__ uint16_t s_perm[TST_MAX_FEATURES];
     __shared__ uint32_t s_tot[TST_MAX_CLASSES];
     __shared__ uint32_t s_bestL[TST_MAX_CLASSES];
@@ -155,13 +185,15 @@ __global__ void __launch_bounds__(THREADS, 4) k_grow_big(GrowCtx g, const Task* 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const int C = g.C, d = g.d, m = g.m;
     const TreeDesc td = g.trees[t.tree];
-    const uint32_t* __restrict__ ent_in = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
-    uint32_t* __restrict__ ent_out = ((t.depth & 1u) ? g.entA : g.entB) + (uint64_t)t.tree * g.n_cap;
+    const Entry* __restrict__ ent_in = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+    Entry* __restrict__ ent_out = ((t.depth & 1u) ? g.entA : g.entB) + (uint64_t)t.tree * g.n_cap;
     uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
     uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
     const uint8_t* __restrict__ bins = g.bins_rm;
-    const uint8_t* __restrict__ y = g.y;
     const uint32_t dstride = g.dstride;
+    const bool use_tile = g.big_tile != 0;
+    const uint32_t pitch = (dstride >> 2) + 1u;
+    uint32_t* s_tile = s_hist + g.MB * g.FS + wid * 32u * pitch;  // this warp's rows
 
     for (int f = tid; f < d; f += THREADS) s_perm[f] = (uint16_t)f;
     if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; }
@@ -191,59 +223,41 @@ __global__ void __launch_bounds__(THREADS, 4) k_grow_big(GrowCtx g, const Task* 
         __syncthreads();
 
         // ---- class histogram: hist[j][bin][class] += multiplicity (SK/.../histogram.pyx:336-425 pattern)
-        {
-            constexpr int U = 4;
-            for (uint32_t base = t.begin + tid; base < t.end; base += THREADS * U) {
-                uint32_t e[U], cls[U];
-                const uint8_t* rp[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    uint32_t idx = base + u * THREADS;
-                    e[u] = idx < t.end ? ent_in[idx] : 0u;  // multiplicity 0 = padding
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    uint32_t row = e[u] & ROW_MASK;
-                    rp[u] = bins + (uint64_t)row * dstride;
-                    cls[u] = e[u] ? y[row] : 0u;
-                }
-                if (nb <= 8) {
-                    // all U x nb bin bytes are requested before the first atomic: 32 loads in flight per thread
-                    uint32_t lo[U], hi[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) { lo[u] = 0; hi[u] = 0; }
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        if (jj < nb) {
-                            const uint32_t f = s_feat[jj];
-#pragma unroll
-                            for (int u = 0; u < U; ++u) {
-                                uint32_t v = e[u] ? (uint32_t)rp[u][f] : 0u;
-                                if (jj < 4) lo[u] |= v << (8 * jj); else hi[u] |= v << (8 * (jj - 4));
-                            }
-                        }
-                    }
+        if (use_tile) {
+            for (uint32_t base = t.begin; base < t.end; base += THREADS) {
+                const uint32_t idx = base + tid;
+                const Entry e = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
+                fetch_rows32(bins, dstride, e.x, e.y != 0u, s_tile, lane);
+                if (e.y) {
+                    const uint8_t* trow = (const uint8_t*)(s_tile + lane * pitch);
+                    const uint32_t cls = ent_cls(e), w = ent_w(e);
                     for (int jj = 0; jj < nb; ++jj) {
                         int j = jj + (int)lane;  // rotate features across lanes: spreads the shared atomics
                         j = j % nb;
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            uint32_t b = ((j < 4 ? lo[u] : hi[u]) >> (8 * (j & 3))) & 0xFFu;
-                            if (e[u]) atomicAdd(&s_hist[j * g.FS + hist_index(b, cls[u], C)], e[u] >> 24);
-                        }
+                        atomicAdd(&s_hist[j * g.FS + hist_index(trow[s_feat[j]], cls, C)], w);
                     }
-                } else {
-                    for (int jj = 0; jj < nb; ++jj) {
-                        int j = jj + (int)lane;
-                        j = j % nb;
-                        uint32_t f = s_feat[j];
-                        uint32_t b[U];
+                }
+                __syncwarp();
+            }
+        } else {
+            constexpr int U = 4;
+            for (uint32_t base = t.begin + tid; base < t.end; base += THREADS * U) {
+                Entry e[U];
 #pragma unroll
-                        for (int u = 0; u < U; ++u) b[u] = e[u] ? rp[u][f] : 0u;
+                for (int u = 0; u < U; ++u) {
+                    uint32_t idx = base + u * THREADS;
+                    e[u] = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
+                }
+                for (int jj = 0; jj < nb; ++jj) {
+                    int j = jj + (int)lane;
+                    j = j % nb;
+                    uint32_t f = s_feat[j];
+                    uint32_t b[U];
 #pragma unroll
-                        for (int u = 0; u < U; ++u)
-                            if (e[u]) atomicAdd(&s_hist[j * g.FS + hist_index(b[u], cls[u], C)], e[u] >> 24);
-                    }
+                    for (int u = 0; u < U; ++u) b[u] = e[u].y ? (uint32_t)bins[(uint64_t)e[u].x * dstride + f] : 0u;
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (e[u].y) atomicAdd(&s_hist[j * g.FS + hist_index(b[u], ent_cls(e[u]), C)], ent_w(e[u]));
                 }
             }
         }
@@ -324,19 +338,20 @@ __global__ void __launch_bounds__(THREADS, 4) k_grow_big(GrowCtx g, const Task* 
     int par = 0;
     constexpr int PU = 4;  // chunks per barrier
     for (uint32_t c0 = t.begin; c0 < t.end; c0 += THREADS * PU, par ^= 1) {
-        uint32_t e[PU], balL[PU], balR[PU];
+        Entry e[PU];
+        uint32_t balL[PU], balR[PU];
         bool goL[PU];
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
             uint32_t idx = c0 + u * THREADS + tid;
-            e[u] = idx < t.end ? ent_in[idx] : 0u;
+            e[u] = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
         }
 #pragma unroll
-        for (int u = 0; u < PU; ++u) goL[u] = e[u] && bins[(uint64_t)(e[u] & ROW_MASK) * dstride + bf] <= bb;
+        for (int u = 0; u < PU; ++u) goL[u] = e[u].y && bins[(uint64_t)e[u].x * dstride + bf] <= bb;
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
             balL[u] = __ballot_sync(0xffffffffu, goL[u]);
-            balR[u] = __ballot_sync(0xffffffffu, e[u] && !goL[u]);
+            balR[u] = __ballot_sync(0xffffffffu, e[u].y && !goL[u]);
             if (lane == 0) { s_wl[par][u][wid] = __popc(balL[u]); s_wr[par][u][wid] = __popc(balR[u]); }
         }
         __syncthreads();
@@ -350,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 4) k_grow_big(GrowCtx g, const Task* 
                 tl += a; tr += b;
             }
             if (goL[u]) ent_out[t.begin + lbase + pl + __popc(balL[u] & lanemask_lt())] = e[u];
-            else if (e[u]) ent_out[t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt()))] = e[u];
+            else if (e[u].y) ent_out[t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt()))] = e[u];
             lbase += tl; rbase += tr;
         }
     }
@@ -389,18 +404,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task
     for (uint32_t ti = blockIdx.x * WARPS + warp; ti < ntasks; ti += gridDim.x * WARPS) {
         const Task t = tasks[ti];
         const TreeDesc td = g.trees[t.tree];
-        const uint32_t* __restrict__ ent = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+        const Entry* __restrict__ ent = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
         uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
         uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
         const uint32_t r = t.end - t.begin;
-        uint32_t e = lane < r ? ent[t.begin + lane] : 0u;
-        uint32_t cls = lane < r ? (uint32_t)g.y[e & ROW_MASK] : 0u;
+        Entry e = lane < r ? ent[t.begin + lane] : make_uint2(0u, 0u);
+        uint32_t cls = ent_cls(e);
         uint32_t lo = 0, hi = r, depth = t.depth, slot = t.slot, sp = 0;
         unsigned long long visits = 0, n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0;
         uint32_t maxd = 0;
         while (true) {
             const bool active = lane >= lo && lane < hi;
-            const uint32_t w = active ? (e >> 24) : 0u;
+            const uint32_t w = active ? ent_w(e) : 0u;
             const uint32_t abs_begin = t.begin + lo;
             // node totals (SK/tree/_criterion.pyx:302-370)
             for (int c = lane; c < C; c += 32) s_tot[c] = 0;
@@ -437,7 +452,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task
                         if (i == m) n_fb++;
                     }
                     f = __shfl_sync(0xffffffffu, f, 0);
-                    const uint32_t b = active ? bins[(uint64_t)(e & ROW_MASK) * dstride + f] : 0u;
+                    const uint32_t b = active ? bins[(uint64_t)e.x * dstride + f] : 0u;
                     const uint32_t packed = b | (cls << 8) | (w << 16);
                     for (int c = 0; c < C; ++c) s_L[c * 32 + lane] = 0;
                     for (uint32_t kk = lo; kk < hi; ++kk) {
@@ -490,7 +505,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task
             }
             // partition inside the warp (stable)
             const uint32_t bf = best_key >> 8, bb = best_key & 0xFFu;
-            const bool goL = active && bins[(uint64_t)(e & ROW_MASK) * dstride + bf] <= bb;
+            const bool goL = active && bins[(uint64_t)e.x * dstride + bf] <= bb;
             const uint32_t balL = __ballot_sync(0xffffffffu, goL);
             const uint32_t balR = __ballot_sync(0xffffffffu, active && !goL);
             const uint32_t nLd = __popc(balL);
@@ -505,8 +520,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task
             __syncwarp();
             const uint32_t src = s_src[lane];
             __syncwarp();
-            e = __shfl_sync(0xffffffffu, e, src);
-            cls = __shfl_sync(0xffffffffu, cls, src);
+            e.x = __shfl_sync(0xffffffffu, e.x, src);
+            e.y = __shfl_sync(0xffffffffu, e.y, src);
+            cls = ent_cls(e);
             const uint32_t right_slot = slot + 2u * nLd;
             if (lane == 0) {
                 write_internal(nodes, slot, right_slot, bf, bb);

@@ -37,20 +37,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 
     const Task t = tasks[ti];
     const TreeDesc td = g.trees[t.tree];
-    const uint32_t* __restrict__ ent_in = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
-    uint32_t* __restrict__ ent_out = ((t.depth & 1u) ? g.entA : g.entB) + (uint64_t)t.tree * g.n_cap;
+    const Entry* __restrict__ ent_in = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+    Entry* __restrict__ ent_out = ((t.depth & 1u) ? g.entA : g.entB) + (uint64_t)t.tree * g.n_cap;
     uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
     uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
     const uint32_t r = t.end - t.begin;
 
-    uint32_t e[R], cls[R];
+    Entry e[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         uint32_t i = lane + 32u * k;
-        e[k] = i < r ? ent_in[t.begin + i] : 0u;  // multiplicity 0 = padding
+        e[k] = i < r ? ent_in[t.begin + i] : make_uint2(0u, 0u);  // multiplicity 0 = padding
     }
-#pragma unroll
-    for (int k = 0; k < R; ++k) cls[k] = e[k] ? (uint32_t)g.y[e[k] & ROW_MASK] : 0u;
     for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
     __syncwarp();
 
@@ -77,11 +75,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
         for (int w = lane; w < g.FS; w += 32) s_hist[w] = 0;
         uint32_t b[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) b[k] = e[k] ? (uint32_t)bins[(uint64_t)(e[k] & ROW_MASK) * dstride + f] : 0u;
+        for (int k = 0; k < R; ++k) b[k] = e[k].y ? (uint32_t)bins[(uint64_t)e[k].x * dstride + f] : 0u;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < R; ++k)
-            if (e[k]) atomicAdd(&s_hist[hist_index(b[k], cls[k], C)], e[k] >> 24);
+            if (e[k].y) atomicAdd(&s_hist[hist_index(b[k], ent_cls(e[k]), C)], ent_w(e[k]));
         __syncwarp();
         double bg;
         uint32_t bb;
@@ -140,7 +138,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
     uint32_t goL = 0;  // bit k: element k goes left
 #pragma unroll
     for (int k = 0; k < R; ++k)
-        if (e[k] && bins[(uint64_t)(e[k] & ROW_MASK) * dstride + bf] <= bbin) goL |= 1u << k;
+        if (e[k].y && bins[(uint64_t)e[k].x * dstride + bf] <= bbin) goL |= 1u << k;
     uint32_t nLd = 0;
 #pragma unroll
     for (int k = 0; k < R; ++k) nLd += __popc(__ballot_sync(0xffffffffu, (goL >> k) & 1u));
@@ -151,7 +149,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
     uint32_t lbase = 0, rbase = 0;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        const bool l = (goL >> k) & 1u, v = e[k] != 0u;
+        const bool l = (goL >> k) & 1u, v = e[k].y != 0u;
         const uint32_t balL = __ballot_sync(0xffffffffu, l), balR = __ballot_sync(0xffffffffu, v && !l);
         if (l) ent_out[t.begin + lbase + __popc(balL & lanemask_lt())] = e[k];
         else if (v) ent_out[t.begin + nLd + rbase + __popc(balR & lanemask_lt())] = e[k];
@@ -193,20 +191,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid4(GrowCtx g, const Task*
 
     const Task t = tasks[ti];
     const TreeDesc td = g.trees[t.tree];
-    const uint32_t* __restrict__ ent_in = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
-    uint32_t* __restrict__ ent_out = ((t.depth & 1u) ? g.entA : g.entB) + (uint64_t)t.tree * g.n_cap;
+    const Entry* __restrict__ ent_in = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+    Entry* __restrict__ ent_out = ((t.depth & 1u) ? g.entA : g.entB) + (uint64_t)t.tree * g.n_cap;
     uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
     uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
     const uint32_t r = t.end - t.begin;
 
-    uint32_t e[R], cls[R];
+    Entry e[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         uint32_t i = lane + 32u * k;
-        e[k] = i < r ? ent_in[t.begin + i] : 0u;
+        e[k] = i < r ? ent_in[t.begin + i] : make_uint2(0u, 0u);
     }
-#pragma unroll
-    for (int k = 0; k < R; ++k) cls[k] = e[k] ? (uint32_t)g.y[e[k] & ROW_MASK] : 0u;
     for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
     __syncwarp();
     uint4 rnd = make_uint4(0, 0, 0, 0);
@@ -230,7 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid4(GrowCtx g, const Task*
     {
         const uint32_t f0 = s_perm[0];
 #pragma unroll
-        for (int k = 0; k < R; ++k) bnext[k] = e[k] ? (uint32_t)bins[(uint64_t)(e[k] & ROW_MASK) * dstride + f0] : 0u;
+        for (int k = 0; k < R; ++k) bnext[k] = e[k].y ? (uint32_t)bins[(uint64_t)e[k].x * dstride + f0] : 0u;
     }
     for (int i = 0; i < d; ++i) {
         if (i >= m && found) break;
@@ -254,18 +250,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid4(GrowCtx g, const Task*
             if (i + 1 < m) {
                 const uint32_t fn = s_perm[i + 1];
 #pragma unroll
-                for (int k = 0; k < R; ++k) bnext[k] = e[k] ? (uint32_t)bins[(uint64_t)(e[k] & ROW_MASK) * dstride + fn] : 0u;
+                for (int k = 0; k < R; ++k) bnext[k] = e[k].y ? (uint32_t)bins[(uint64_t)e[k].x * dstride + fn] : 0u;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < R; ++k) b[k] = e[k] ? (uint32_t)bins[(uint64_t)(e[k] & ROW_MASK) * dstride + f] : 0u;
+            for (int k = 0; k < R; ++k) b[k] = e[k].y ? (uint32_t)bins[(uint64_t)e[k].x * dstride + f] : 0u;
         }
         // packed class histogram of this feature
         for (uint32_t w = lane; w < MID4_HIST; w += 32) s_hist[w] = 0;
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < R; ++k)
-            if (e[k]) atomicAdd(&s_hist[(b[k] >> 3) * 17u + (b[k] & 7u) * 2u + (cls[k] >> 1)], (e[k] >> 24) << (16u * (cls[k] & 1u)));
+            if (e[k].y) atomicAdd(&s_hist[(b[k] >> 3) * 17u + (b[k] & 7u) * 2u + (ent_cls(e[k]) >> 1)], ent_w(e[k]) << (16u * (ent_cls(e[k]) & 1u)));
         __syncwarp();
         // packed prefix scan over bins
         const uint32_t* hl = s_hist + lane * 17u;
@@ -368,7 +364,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid4(GrowCtx g, const Task*
     uint32_t goL = 0;
 #pragma unroll
     for (int k = 0; k < R; ++k)
-        if (e[k] && bins[(uint64_t)(e[k] & ROW_MASK) * dstride + bf] <= bbin) goL |= 1u << k;
+        if (e[k].y && bins[(uint64_t)e[k].x * dstride + bf] <= bbin) goL |= 1u << k;
     uint32_t nLd = 0;
 #pragma unroll
     for (int k = 0; k < R; ++k) nLd += __popc(__ballot_sync(0xffffffffu, (goL >> k) & 1u));
@@ -379,7 +375,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid4(GrowCtx g, const Task*
     uint32_t lbase = 0, rbase = 0;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-        const bool l = (goL >> k) & 1u, v = e[k] != 0u;
+        const bool l = (goL >> k) & 1u, v = e[k].y != 0u;
         const uint32_t balL = __ballot_sync(0xffffffffu, l), balR = __ballot_sync(0xffffffffu, v && !l);
         if (l) ent_out[t.begin + lbase + __popc(balL & lanemask_lt())] = e[k];
         else if (v) ent_out[t.begin + nLd + rbase + __popc(balR & lanemask_lt())] = e[k];

@@ -45,12 +45,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small4(GrowCtx g, const Tas
     for (uint32_t ti = blockIdx.x * WARPS + warp; ti < ntasks; ti += gridDim.x * WARPS) {
         const Task t = tasks[ti];
         const TreeDesc td = g.trees[t.tree];
-        const uint32_t* __restrict__ ent = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+        const Entry* __restrict__ ent = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
         uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
         uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
         const uint32_t r = t.end - t.begin;
-        uint32_t e = lane < r ? ent[t.begin + lane] : 0u;
-        uint32_t cls = lane < r ? (uint32_t)g.y[e & ROW_MASK] : 0u;
+        Entry e = lane < r ? ent[t.begin + lane] : make_uint2(0u, 0u);
         uint32_t lo = 0, hi = r, depth = t.depth, slot = t.slot, sp = 0;
         unsigned long long visits = 0, n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0;
         uint32_t maxd = 0;
@@ -58,7 +57,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small4(GrowCtx g, const Tas
             const bool active = lane >= lo && lane < hi;
             const uint32_t rr = hi - lo;
             const uint32_t abs_begin = t.begin + lo;
-            const unsigned long long cw = active ? ((unsigned long long)(e >> 24) << (13u * cls)) : 0ull;
+            const unsigned long long cw = active ? ((unsigned long long)ent_w(e) << (13u * ent_cls(e))) : 0ull;
             const unsigned long long tot = warp_sum64(cw);
             const uint32_t t0 = F13(tot, 0), t1 = F13(tot, 1), t2 = F13(tot, 2), t3 = F13(tot, 3);
             const uint32_t N = t0 + t1 + t2 + t3;
@@ -77,10 +76,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small4(GrowCtx g, const Tas
                 const uint32_t gi = lane >> gshift, sub = lane & (G - 1u), gbase = lane & ~(G - 1u);
                 const bool gvalid = sub < rr;
                 const uint32_t srcl = lo + (gvalid ? sub : 0u);
-                const uint32_t e_g = __shfl_sync(0xffffffffu, e, srcl);
-                const uint32_t cls_g = __shfl_sync(0xffffffffu, cls, srcl);
-                const unsigned long long cw_g = gvalid ? ((unsigned long long)(e_g >> 24) << (13u * cls_g)) : 0ull;
-                const uint8_t* __restrict__ rowp = bins + (uint64_t)(e_g & ROW_MASK) * dstride;
+                Entry e_g;
+                e_g.x = __shfl_sync(0xffffffffu, e.x, srcl);
+                e_g.y = __shfl_sync(0xffffffffu, e.y, srcl);
+                const unsigned long long cw_g = gvalid ? ((unsigned long long)ent_w(e_g) << (13u * ent_cls(e_g))) : 0ull;
+                const uint8_t* __restrict__ rowp = bins + (uint64_t)e_g.x * dstride;
                 for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
                 __syncwarp();
                 for (int pos0 = 0; pos0 < d;) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small4(GrowCtx g, const Tas
             }
             // partition inside the warp (stable)
             const uint32_t bf = best_key >> 8, bb = best_key & 0xFFu;
-            const bool goL = active && bins[(uint64_t)(e & ROW_MASK) * dstride + bf] <= bb;
+            const bool goL = active && bins[(uint64_t)e.x * dstride + bf] <= bb;
             const uint32_t balL = __ballot_sync(0xffffffffu, goL);
             const uint32_t balR = __ballot_sync(0xffffffffu, active && !goL);
             const uint32_t nLd = __popc(balL);
@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small4(GrowCtx g, const Tas
             __syncwarp();
             const uint32_t src = s_src[lane];
             __syncwarp();
-            e = __shfl_sync(0xffffffffu, e, src);
-            cls = __shfl_sync(0xffffffffu, cls, src);
+            e.x = __shfl_sync(0xffffffffu, e.x, src);
+            e.y = __shfl_sync(0xffffffffu, e.y, src);
             const uint32_t right_slot = slot + 2u * nLd;
             if (lane == 0) {
                 write_internal(nodes, slot, right_slot, bf, bb);

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) k_boot_draw(const TreeDesc* __restrict__ 
     }
 }
 
-// Entry compaction: in-bag rows ascending, entry = row | multiplicity << 24 (zero-weight rows are
+// Entry compaction: in-bag rows ascending, entry = (row, multiplicity | class << 8) (zero-weight rows are
 // dropped as SK/tree/_splitter.pyx:167-171).  Chunk = 4096 rows: count -> per-tree scan -> scatter.
 #define BOOT_CHUNK 4096
 __global__ void __launch_bounds__(256) k_boot_count(const uint32_t* __restrict__ counts8, uint64_t n_pad, uint32_t n_chunks,
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(256) k_boot_scan(TreeDesc* __restrict__ trees,
 }
 
 __global__ void __launch_bounds__(256) k_boot_scatter(const uint32_t* __restrict__ counts8, uint64_t n_pad, uint32_t n_chunks,
-                                                      const uint32_t* __restrict__ chunk_off, uint32_t* __restrict__ entA,
-                                                      uint64_t n_cap) {
+                                                      const uint32_t* __restrict__ chunk_off, const uint8_t* __restrict__ y,
+                                                      Entry* __restrict__ entA, uint64_t n_cap) {
     __shared__ uint32_t s_w[8];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint4* src = (const uint4*)(counts8 + (uint64_t)blockIdx.y * (n_pad / 4));
@@ -292,14 +292,14 @@ __global__ void __launch_bounds__(256) k_boot_scatter(const uint32_t* __restrict
     __syncthreads();
     uint32_t pos = chunk_off[(uint64_t)blockIdx.y * n_chunks + blockIdx.x] + incl - c;
     for (uint32_t w = 0; w < wid; ++w) pos += s_w[w];
-    uint32_t* out = entA + (uint64_t)blockIdx.y * n_cap;
+    Entry* out = entA + (uint64_t)blockIdx.y * n_cap;
     uint32_t row = (uint32_t)(v * 16);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             uint32_t m = (ws[i] >> (8 * b)) & 0xFFu;
-            if (m) out[pos++] = (row + i * 4 + b) | (m << 24);
+            if (m) { uint32_t rw = row + i * 4 + b; out[pos++] = make_uint2(rw, m | ((uint32_t)y[rw] << 8)); }
         }
 }
 

@@ -16,7 +16,7 @@ FOLD_INACTIVE = 255
 MAX_EDGES = 255
 MAX_CLASSES = 32
 MAX_FEATURES = 1024
-MAX_ROWS = 1 << 24
+MAX_ROWS = 0x7FFFFFF0
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
