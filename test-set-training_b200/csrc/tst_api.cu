@@ -145,7 +145,9 @@ static int alloc_table(tst_handle* h, int64_t n, int32_t d) {
     if (d < 1 || d > TST_MAX_FEATURES) return fail(TST_ERR_INVALID, "table: need 1 <= d <= 1024 features");
     h->n = n; h->d = d;
     h->ld = (n + 15) / 16 * 16;
+    // rows of <= 128 bytes are padded to a power of two so the cooperative row fetch can shift instead of divide
     h->dstride = (uint32_t)((d + 15) / 16 * 16);
+    if (d <= 128) { uint32_t p2 = 16; while (p2 < (uint32_t)d) p2 <<= 1; h->dstride = p2; }
     ENSURE(h->bins_cm, (size_t)h->ld * d);
     ENSURE(h->bins_rm, (size_t)n * h->dstride);
     return 0;

@@ -107,8 +107,9 @@ struct GrowCtx {
 };
 
 __device__ __forceinline__ uint32_t hist_index(uint32_t bin, uint32_t cls, uint32_t C) {
-    // 8 bins per lane, lane stride 8C+1 words: the split scan reads without bank conflicts
-    return (bin >> 3) * (8u * C + 1u) + (bin & 7u) * C + cls;
+    // 8 bins per lane, lane stride 8C+1 words (one pad word per 8 bins): the split scan reads without
+    // bank conflicts.  (bin >> 3) * (8C + 1) + (bin & 7) * C + cls  ==  bin * C + (bin >> 3) + cls.
+    return bin * C + (bin >> 3) + cls;
 }
 
 __device__ __forceinline__ uint32_t lanemask_lt() {

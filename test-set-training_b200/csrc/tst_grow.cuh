@@ -142,7 +142,8 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
 // sampled feature.  tile pitch = dstride/4 + 1 words: the per-row byte reads that follow are conflict-free.
 __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, uint32_t dstride, uint32_t row, bool has,
                                              uint32_t* tile /* this warp's 32 x pitch words */, uint32_t lane) {
-    const uint32_t P = dstride >> 4, pitch = (dstride >> 2) + 1u;
+    // dstride is a power of two here (16 / 32 / 64 / 128): P pieces of 16 bytes per row
+    const uint32_t P = dstride >> 4, lp = 31u - __clz(P), pitch = (dstride >> 2) + 1u;
     for (uint32_t i0 = 0; i0 < 32u * P; i0 += 128u) {
         uint4 v[4];
         uint32_t rs[4], pt[4];
@@ -150,7 +151,7 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t idx = i0 + q * 32u + lane;
-            rs[q] = idx / P; pt[q] = idx - rs[q] * P;
+            rs[q] = idx >> lp; pt[q] = idx & (P - 1u);
             uint32_t rid = __shfl_sync(0xffffffffu, row, rs[q] & 31u);
             ok[q] = __shfl_sync(0xffffffffu, has ? 1u : 0u, rs[q] & 31u) && idx < 32u * P;
             if (ok[q]) v[q] = __ldg((const uint4*)(bins + (uint64_t)rid * dstride) + pt[q]);
@@ -223,19 +224,20 @@ __global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* 
         __syncthreads();
 
         // ---- class histogram: hist[j][bin][class] += multiplicity (SK/.../histogram.pyx:336-425 pattern)
-        if (use_tile) {
+        if (use_tile && nb <= 8) {
+            uint32_t featr[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) featr[jj] = jj < nb ? s_feat[jj] : 0u;
+            const uint8_t* trow = (const uint8_t*)(s_tile + lane * pitch);
             for (uint32_t base = t.begin; base < t.end; base += THREADS) {
                 const uint32_t idx = base + tid;
                 const Entry e = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
                 fetch_rows32(bins, dstride, e.x, e.y != 0u, s_tile, lane);
                 if (e.y) {
-                    const uint8_t* trow = (const uint8_t*)(s_tile + lane * pitch);
                     const uint32_t cls = ent_cls(e), w = ent_w(e);
-                    for (int jj = 0; jj < nb; ++jj) {
-                        int j = jj + (int)lane;  // rotate features across lanes: spreads the shared atomics
-                        j = j % nb;
-                        atomicAdd(&s_hist[j * g.FS + hist_index(trow[s_feat[j]], cls, C)], w);
-                    }
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj)
+                        if (jj < nb) atomicAdd(&s_hist[jj * g.FS + hist_index(trow[featr[jj]], cls, C)], w);
                 }
                 __syncwarp();
             }
@@ -248,9 +250,10 @@ __global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* 
                     uint32_t idx = base + u * THREADS;
                     e[u] = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
                 }
+                const int jr = (int)lane % nb;  // rotate features across lanes: spreads same-address atomics
                 for (int jj = 0; jj < nb; ++jj) {
-                    int j = jj + (int)lane;
-                    j = j % nb;
+                    int j = jj + jr;
+                    if (j >= nb) j -= nb;
                     uint32_t f = s_feat[j];
                     uint32_t b[U];
 #pragma unroll
