@@ -71,7 +71,9 @@ struct tst_handle {
     // ibp / predict scratch
     DevBuf ibp_fold, ibp_votes, ibp_removed, pred_cm, pred_rm;
     uint32_t* h_pinned = nullptr;  // 16 words
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
+    cudaStream_t s_mid = nullptr, s_small = nullptr;  // side streams: warp-per-node and warp-per-subtree kernels overlap the CTA kernel
+    bool overlap = false;  // TST_OVERLAP=1: measured on B200, the tiers each fill the SMs, co-scheduling gains nothing
     tst_stats stats;
     bool attrs_set = false;
 };
@@ -106,6 +108,10 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->ev2));
+    CK(cudaEventCreate(&h->evm0)); CK(cudaEventCreate(&h->evm1)); CK(cudaEventCreate(&h->evs0)); CK(cudaEventCreate(&h->evs1));
+    CK(cudaStreamCreateWithFlags(&h->s_mid, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_small, cudaStreamNonBlocking));
+    if (const char* ev = getenv("TST_OVERLAP")) h->overlap = atoi(ev) != 0;
     *out = h;
     return TST_OK;
 }
@@ -122,6 +128,9 @@ extern "C" int tst_destroy(tst_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
+    for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1}) if (e) cudaEventDestroy(e);
+    if (h->s_mid) cudaStreamDestroy(h->s_mid);
+    if (h->s_small) cudaStreamDestroy(h->s_small);
     delete h;
     return TST_OK;
 }
@@ -415,6 +424,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         // ---- level-synchronous growth: CTA per node (> mid_max rows) and warp per node (33 .. mid_max rows)
         int cur = 0;
         uint64_t level_guard = 0;
+        uint32_t small_done = 0;
+        bool small_started = false;
         uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[3];
         while (nbig > 0 || nmid > 0) {
             Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
@@ -426,6 +437,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             CK(cudaMemsetAsync(g.qnext_count, 0, 4, st));
             CK(cudaMemsetAsync(g.qmid_next_count, 0, 4, st));
             CK(cudaEventRecord(h->ev0, st));
+            const bool side = h->overlap && nmid > 0;
+            cudaStream_t sm = side ? h->s_mid : st;
+            if (side) {  // the two kernels of a level are independent: run them side by side
+                CK(cudaStreamWaitEvent(h->s_mid, h->ev0, 0));
+                CK(cudaEventRecord(h->evm0, h->s_mid));
+            }
             if (nbig) {
                 k_grow_big<BIG_THREADS><<<nbig, BIG_THREADS, big_smem, st>>>(g, qcur, nbig);
                 CKL();
@@ -433,35 +450,59 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             }
             CK(cudaEventRecord(h->ev1, st));
             if (nmid) {
-                if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(nmid + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, nmid);
-                else k_grow_mid<MID_WARPS, MID_R><<<(nmid + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, nmid);
+                if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(nmid + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, sm>>>(g, qmcur, nmid);
+                else k_grow_mid<MID_WARPS, MID_R><<<(nmid + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, sm>>>(g, qmcur, nmid);
                 CKL();
                 h->stats.kernel_launches++; h->stats.launches_grow_mid++;
+            }
+            if (side) {
+                CK(cudaEventRecord(h->evm1, h->s_mid));
+                CK(cudaStreamWaitEvent(st, h->evm1, 0));
             }
             CK(cudaEventRecord(h->ev2, st));
             CK(cudaMemcpyAsync(h->h_pinned, counters, 32, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_big += ms;
-              cudaEventElapsedTime(&ms, h->ev1, h->ev2); h->stats.ms_grow_mid += ms; }
+              if (side) cudaEventElapsedTime(&ms, h->evm0, h->evm1); else cudaEventElapsedTime(&ms, h->ev1, h->ev2);
+              h->stats.ms_grow_mid += ms; }
             h->stats.levels++;
             cur ^= 1;
             nbig = h->h_pinned[cur];
             nmid = h->h_pinned[3 + cur];
             if (++level_guard > n_cap + 2) return fail(TST_ERR_STATE, "tree growth did not terminate");
             if (nbig > g.qbig_cap || nmid > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
+            // subtrees with <= 32 rows that this level produced start right away on their own stream
+            if (h->overlap && (nbig > 0 || nmid > 0)) {
+                const uint32_t now = std::min<uint32_t>(h->h_pinned[2], g.qsmall_cap);
+                if (now > small_done + 4096u) {
+                    const uint32_t cnt = now - small_done;
+                    uint32_t blocks = std::min<uint32_t>((cnt + SMALL_WARPS - 1) / SMALL_WARPS, (uint32_t)h->sm_count * 64u);
+                    if (!small_started) { CK(cudaEventRecord(h->evs0, h->s_small)); small_started = true; }
+                    if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, h->s_small>>>(g, g.qsmall + small_done, cnt);
+                    else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, h->s_small>>>(g, g.qsmall + small_done, cnt);
+                    CKL();
+                    h->stats.kernel_launches++; h->stats.launches_grow_small++;
+                    small_done = now;
+                }
+            }
         }
-        // ---- subtrees with <= 32 rows: one warp each
+        // ---- remaining subtrees with <= 32 rows: one warp each
         const uint32_t nsmall = h->h_pinned[2];
         if (nsmall > g.qsmall_cap) return fail(TST_ERR_OVERFLOW, "small-node queue overflowed");
-        if (nsmall) {
-            uint32_t blocks = (nsmall + SMALL_WARPS - 1) / SMALL_WARPS;
-            blocks = std::min<uint32_t>(blocks, (uint32_t)h->sm_count * 64u);
-            CK(cudaEventRecord(h->ev0, st));
-            if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
-            else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+        if (nsmall > small_done) {
+            const uint32_t cnt = nsmall - small_done;
+            uint32_t blocks = std::min<uint32_t>((cnt + SMALL_WARPS - 1) / SMALL_WARPS, (uint32_t)h->sm_count * 64u);
+            cudaStream_t ss = h->overlap ? h->s_small : st;
+            if (!small_started) { CK(cudaEventRecord(h->evs0, ss)); small_started = true; }
+            if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, ss>>>(g, g.qsmall + small_done, cnt);
+            else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, ss>>>(g, g.qsmall + small_done, cnt);
             CKL();
-            CK(cudaEventRecord(h->ev1, st));
             h->stats.kernel_launches++; h->stats.launches_grow_small++;
+        }
+        if (small_started) {
+            cudaStream_t ss = h->overlap ? h->s_small : st;
+            CK(cudaEventRecord(h->evs1, ss));
+            if (h->overlap) CK(cudaStreamWaitEvent(st, h->evs1, 0));
         }
         // ---- OOF inference of this batch's trees on their held-out rows
         std::vector<InferPart> ips;
@@ -487,7 +528,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             h->stats.kernel_launches++;
         }
         CK(cudaStreamSynchronize(st));
-        if (nsmall) { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_small += ms; }
+        if (small_started) { float ms = 0; cudaEventElapsedTime(&ms, h->evs0, h->evs1); h->stats.ms_grow_small += ms; }  // span when overlapped
         if (evi0) {
             float ms = 0; cudaEventElapsedTime(&ms, evi0, evi1); h->stats.ms_infer += ms;
             cudaEventDestroy(evi0); cudaEventDestroy(evi1);

@@ -172,8 +172,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 #define MID4_HIST 544u   // 32 lanes x (8 bins x 2 words + 1 pad)
 #define MID4_CAND 768u   // 256 candidates x (P0, P1, bin)
 
+#ifndef MID_MINB
+#define MID_MINB 3
+#endif
 template <int WARPS, int R>
-__global__ void __launch_bounds__(WARPS * 32) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     static_assert(32 * R * 255 < 65536, "packed 16-bit class counts need <= 256 rows per node");
     extern __shared__ uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;

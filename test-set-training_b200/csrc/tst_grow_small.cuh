@@ -29,8 +29,11 @@ __device__ __forceinline__ void warp_argmax(double& gn, uint32_t& key) {
 
 #define F13(x, c) ((uint32_t)((x) >> (13 * (c))) & 0x1FFFu)
 
+#ifndef SMALL_MINB
+#define SMALL_MINB 8
+#endif
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_grow_small4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     extern __shared__ uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int C = g.C, d = g.d, m = g.m;

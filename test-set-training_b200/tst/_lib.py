@@ -8,7 +8,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_ROOT, "libtst.so")
+LIB_PATH = os.environ.get("TST_LIB") or os.path.join(_ROOT, "libtst.so")  # TST_LIB: A/B builds while tuning
 CSRC = os.path.join(_ROOT, "csrc")
 
 FOLD_TRAIN_ONLY = 254
