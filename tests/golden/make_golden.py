@@ -1,0 +1,64 @@
+"""Generates tests/golden/*.npz.  Run from the repo root:  python tests/golden/make_golden.py
+
+Two kinds of vectors (the reference repo ships none -- "parity unpinned"):
+  sklearn_*   outputs of the third-party reference the oracle restates (scikit-learn, imported here):
+              bin thresholds of _find_binning_thresholds and _BinMapper bins on fixed seeded inputs.
+  spec_*      outputs of the CPU oracle (oracle/hist_rf.c) on small seeded tables: they freeze the
+              normative spec so that neither side can drift between rounds.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "test-set-training_b200"))
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sklearn_vectors():
+    import sklearn
+    from sklearn.ensemble._hist_gradient_boosting.binning import _BinMapper, _find_binning_thresholds
+
+    rng = np.random.default_rng(2024)
+    cols = {
+        "normal": rng.standard_normal(3000).astype(np.float32),
+        "poisson": rng.poisson(6.0, 2000).astype(np.float32),
+        "lowcard": rng.integers(0, 7, 500).astype(np.float32),
+        "heavy_ties": np.round(rng.standard_normal(4000) * 40).astype(np.float32),
+    }
+    out = {"sklearn_version": np.array(sklearn.__version__)}
+    for k, v in cols.items():
+        out[f"col_{k}"] = v
+        out[f"thr_{k}"] = _find_binning_thresholds(v.astype(np.float64), 255)
+    X = np.stack([cols["normal"][:500], cols["poisson"][:500], cols["lowcard"]], axis=1).astype(np.float64)
+    bm = _BinMapper(n_bins=256, subsample=None, random_state=0).fit(X)
+    out["binmapper_X"] = X.astype(np.float32)
+    out["binmapper_bins"] = bm.transform(X)
+    np.savez_compressed(os.path.join(HERE, "sklearn_binning.npz"), **out)
+
+
+def spec_vectors():
+    from oracle import hist_rf as H
+    from tst import synth
+
+    X, y = synth.vsi_table(400, 12, 3, seed=5)
+    edges, ne = H.find_edges(X)
+    bins = H.bin_table(X, edges, ne)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 4, 3)
+    prm = H.make_params(12)
+    votes, st, forest = H.fit_oof(bins, y, fold, 4, 6, 3, prm, seed=11, keep=True, nthreads=1)
+    s, cor, tot = H.finalize(votes, y, fold, 4, 6)
+    t = forest.tree(2, 3)
+    act, removed, s_rounds = H.ibp(bins, y, 4, 6, 3, prm, seed=11, rounds=3, tau=0.4, batch=25)
+    np.savez_compressed(os.path.join(HERE, "spec_small.npz"), X=X, y=y, edges=edges, n_edges=ne, bins=bins, fold=fold,
+                        votes=votes, s=s, correct=cor, total=tot, tree_nodes=t.nodes, tree_counts=t.counts,
+                        stats=np.array([st[k] for k in ("row_visits", "nodes", "leaves", "searched", "fallback", "inbag_rows", "max_depth")]),
+                        ibp_active=act, ibp_removed=removed, ibp_s=s_rounds)
+
+
+if __name__ == "__main__":
+    sklearn_vectors()
+    spec_vectors()
+    print("wrote", sorted(os.listdir(HERE)))
