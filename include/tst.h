@@ -104,6 +104,11 @@ int tst_destroy(tst_handle* h);
  * Builds both the column-major [d][ld] and row-major [n][stride] uint8 tables in HBM. */
 int tst_bin(tst_handle* h, const float* X_dev, int64_t n, int32_t d, const double* edges_host,
             const int32_t* n_edges_host, void* stream);
+/* Same, with the bin edges selected on the device (per-column radix sort + integer-rank quantiles, the
+ * rule of DESIGN.md 2.1 / SK/.../binning.py:31-111): nothing but X crosses PCIe.  n_bins in [3, 256].
+ * edges_out_host [d][TST_MAX_EDGES] / n_edges_out_host [d] receive the chosen edges (may be NULL). */
+int tst_bin_auto(tst_handle* h, const float* X_dev, int64_t n, int32_t d, int32_t n_bins, double* edges_out_host,
+                 int32_t* n_edges_out_host, void* stream);
 /* Same, from an already binned column-major table [d][n] on the device (tests, pre-binned data). */
 int tst_set_bins(tst_handle* h, const uint8_t* bins_cm_dev, int64_t n, int32_t d, void* stream);
 /* Copy the column-major table out: out_dev [d][n]. */

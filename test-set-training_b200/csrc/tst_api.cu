@@ -12,6 +12,7 @@
 #include "tst_grow_small.cuh"
 #include "tst_grow_mid.cuh"
 #include "tst_prep.cuh"
+#include "tst_quantile.cuh"
 
 // --------------------------------------------------------------------------------------------- errors
 static thread_local std::string g_err;
@@ -69,7 +70,7 @@ struct tst_handle {
     int32_t kept_C = 0, kept_n_trees = 0;
     uint64_t kept_node_stride = 0, kept_leafc_stride = 0;
     // ibp / predict scratch
-    DevBuf ibp_fold, ibp_votes, ibp_removed, pred_cm, pred_rm;
+    DevBuf ibp_fold, ibp_votes, ibp_removed, pred_cm, pred_rm, sort_a, sort_b, sort_dk;
     uint32_t* h_pinned = nullptr;  // 16 words
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
     cudaStream_t s_mid = nullptr, s_small = nullptr;  // side streams: warp-per-node and warp-per-subtree kernels overlap the CTA kernel
@@ -122,7 +123,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
                       &h->qmid0, &h->qmid1, &h->qsmall, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
-                      &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm};
+                      &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk};
     for (DevBuf* b : bufs) b->release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -184,6 +185,44 @@ extern "C" int tst_bin(tst_handle* h, const float* X_dev, int64_t n, int32_t d, 
     CKL();
     h->stats.kernel_launches++;
     h->have_edges = true;
+    return TST_OK;
+}
+
+extern "C" int tst_bin_auto(tst_handle* h, const float* X_dev, int64_t n, int32_t d, int32_t n_bins, double* edges_out_host,
+                            int32_t* n_edges_out_host, void* stream) {
+    if (!h || !X_dev) return fail(TST_ERR_INVALID, "tst_bin_auto: null argument");
+    if (n_bins < 3 || n_bins > 256) return fail(TST_ERR_INVALID, "tst_bin_auto: n_bins must be in [3, 256]");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = alloc_table(h, n, d);
+    if (rc) return rc;
+    if ((rc = set_kernel_attrs(h))) return rc;
+    const int64_t ldk = (n + 3) / 4 * 4;
+    ENSURE(h->sort_a, (size_t)ldk * d * 4);
+    ENSURE(h->sort_b, (size_t)ldk * d * 4);
+    ENSURE(h->sort_dk, (size_t)d * 256 * 4);
+    ENSURE(h->edges, (size_t)d * TST_MAX_EDGES * sizeof(double));
+    ENSURE(h->n_edges, (size_t)d * sizeof(int32_t));
+    CK(cudaMemsetAsync(h->edges.p, 0, (size_t)d * TST_MAX_EDGES * sizeof(double), st));
+    dim3 gt((unsigned)((n + 31) / 32), (unsigned)((d + 31) / 32));
+    k_keys_transpose<<<gt, 256, 0, st>>>(X_dev, n, d, h->sort_a.as<uint32_t>(), ldk);
+    CKL();
+    k_sort_columns<<<d, SORT_THREADS, 0, st>>>(h->sort_a.as<uint32_t>(), h->sort_b.as<uint32_t>(), n, ldk);
+    CKL();
+    k_edges_from_sorted<<<d, 256, 0, st>>>(h->sort_a.as<uint32_t>(), n, ldk, n_bins, h->edges.as<double>(), h->n_edges.as<int>(),
+                                          h->sort_dk.as<uint32_t>());
+    CKL();
+    CK(cudaMemsetAsync(h->bins_rm.p, 0, (size_t)n * h->dstride, st));
+    unsigned grid = (unsigned)((n + BIN_TILE - 1) / BIN_TILE);
+    size_t smem = (size_t)d * (BIN_TILE + 4);
+    k_bin_map<<<grid, 256, smem, st>>>(X_dev, n, d, h->edges.as<double>(), h->n_edges.as<int>(), h->bins_cm.as<uint8_t>(), h->ld,
+                                       h->bins_rm.as<uint8_t>(), h->dstride);
+    CKL();
+    h->stats.kernel_launches += 4;
+    h->have_edges = true;
+    if (edges_out_host) CK(cudaMemcpyAsync(edges_out_host, h->edges.p, (size_t)d * TST_MAX_EDGES * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (n_edges_out_host) CK(cudaMemcpyAsync(n_edges_out_host, h->n_edges.p, (size_t)d * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (edges_out_host || n_edges_out_host) CK(cudaStreamSynchronize(st));
     return TST_OK;
 }
 
@@ -338,8 +377,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->counts8, B * n_pad);
     ENSURE(h->chunk_cnt, B * (size_t)n_chunks * 4);
     ENSURE(h->chunk_sum, B * (size_t)n_chunks * 4);
-    ENSURE(h->entA, B * n_cap * sizeof(Entry));
-    ENSURE(h->entB, B * n_cap * sizeof(Entry));
+    ENSURE(h->entA, B * n_cap * sizeof(Entry) + 4096);  // slack: TMA tiles are whole 256-byte chunks
+    ENSURE(h->entB, B * n_cap * sizeof(Entry) + 4096);
     ENSURE(h->qbig0, B * qbig_per * sizeof(Task));
     ENSURE(h->qbig1, B * qbig_per * sizeof(Task));
     ENSURE(h->qmid0, B * qbig_per * sizeof(Task));
@@ -370,8 +409,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.stats = h->dstats.as<DevStats>();
     g.FS = 32 * (8 * C + 1);
     g.MB = (int)std::min<size_t>(std::min<size_t>(32, (size_t)g.m), std::max<size_t>(1, BIG_SMEM_BUDGET / ((size_t)g.FS * 4)));
-    g.big_tile = h->dstride <= 128 ? 1 : 0;  // cooperative whole-row fetch into a shared tile (rows of <= 128 bytes)
+    g.big_tile = h->dstride <= 64 ? 1 : 0;  // cooperative whole-row fetch into a shared tile (rows of <= 64 bytes)
     const size_t big_tile_bytes = g.big_tile ? (size_t)BIG_THREADS * ((h->dstride >> 2) + 1) * 4 : 0;
+    g.big_tma = 1;
+    if (const char* ev = getenv("TST_BIG_TMA")) g.big_tma = atoi(ev) != 0;
     const size_t big_smem = (size_t)g.MB * g.FS * 4 + big_tile_bytes;
     if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
     const bool small_packed = C <= 4;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise

@@ -102,6 +102,7 @@ struct GrowCtx {
     uint32_t qsmall_cap;
     DevStats* stats;
     int32_t big_tile; // k_grow_big stages whole rows in shared memory (dstride <= 128)
+    int32_t big_tma;  // ... and its row-index tiles arrive through TMA bulk copies
     int32_t MB;       // features per shared-histogram batch
     int32_t FS;       // histogram words per feature = 32 * (8 * C + 1)
 };
@@ -123,6 +124,37 @@ __device__ __forceinline__ double gini_gain(unsigned long long SL, uint32_t NL, 
     // two IEEE divisions and one add -- no multiply, so nothing can be contracted into an FMA.
     return __dadd_rn(__ddiv_rn(__ull2double_rn(SL), __uint2double_rn(NL)),
                      __ddiv_rn(__ull2double_rn(SR), __uint2double_rn(NR)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier helpers: 1-D global -> shared tiles of the in-bag entry lists are
+// staged by the async proxy (SASS: UBLKCP) so the row-id stream never occupies LSU issue slots or
+// registers and runs several tiles ahead of the gathers that depend on it.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 __device__ __forceinline__ void queue_push(Task* q, uint32_t* count, uint32_t cap, DevStats* st, const Task& t) {

@@ -166,9 +166,24 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
     __syncwarp();
 }
 
+#ifndef BIG_MINB
+#define BIG_MINB 3
+#endif
+#ifndef BIG_PART_SCAN
+#define BIG_PART_SCAN 1
+#endif
+// TMA ring for the row-index tiles of the histogram pass.  Measured on B200 (1M x 64, 320 trees in flight): the
+// ring adds mbarrier bookkeeping and registers to a kernel that sits at 80 registers / 3 CTAs per SM and is
+// issue-bound, k_grow_big 134 ms with it vs 112 ms without; it is therefore compiled out by default
+// (-DBIG_TMA_RING=1 builds it; TST_BIG_TMA=0 disables it at run time).  TMA is used where it pays: k_root_hist.
+#ifndef BIG_TMA_RING
+#define BIG_TMA_RING 0
+#endif
+#define ENT_STAGES 4  // 32-entry (256-byte) TMA tiles in flight per warp
+
 // ---------------------------------------------------------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     constexpr int NW = THREADS / 32;
     extern __shared__ uint32_t s_hist[];  // [MB][FS] histogram, then (row tile) [THREADS][dstride/4 + 1]
     __shared__ uint16_t s_perm[TST_MAX_FEATURES];
@@ -177,9 +192,17 @@ __global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* 
     __shared__ double s_fgain[32];
     __shared__ uint32_t s_fbin[32];
     __shared__ uint32_t s_feat[32];
+#if BIG_PART_SCAN
+    __shared__ uint32_t s_wl[2][4][NW];
+#else
     __shared__ uint32_t s_wl[2][4][NW], s_wr[2][4][NW];
+#endif
     __shared__ double s_bgain;
     __shared__ uint32_t s_bkey, s_found, s_newj, s_N, s_stop;
+#if BIG_TMA_RING
+    __shared__ __align__(16) Entry s_ent[NW][ENT_STAGES][32];  // TMA-staged row-index tiles, one ring per warp
+    __shared__ __align__(8) uint64_t s_bar[NW][ENT_STAGES];
+#endif
 
     if (blockIdx.x >= ntasks) return;
     const Task t = tasks[blockIdx.x];
@@ -198,6 +221,18 @@ __global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* 
 
     for (int f = tid; f < d; f += THREADS) s_perm[f] = (uint16_t)f;
     if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; }
+#if BIG_TMA_RING
+    const bool use_tma = use_tile && g.big_tma != 0 && dstride <= 64;
+    if (use_tma && lane == 0) {
+        for (int sidx = 0; sidx < ENT_STAGES; ++sidx) mbar_init(&s_bar[wid][sidx], 1);
+        mbar_fence_init();
+    }
+    // this warp's 32-entry chunks: c = wid, wid + NW, ...; chunk starts are 16-byte aligned (a0 even)
+    const uint32_t a0 = t.begin & ~1u;
+    const uint32_t n_chunks = (t.end - a0 + 31u) >> 5;
+    const uint32_t n_my = n_chunks > wid ? (n_chunks - wid + NW - 1) / NW : 0u;
+    uint32_t tma_ph = 0;  // bit s = parity the next wait on stage s must see (uniform across the warp)
+#endif
     __syncthreads();
 
     int pos = 0;
@@ -229,6 +264,36 @@ __global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* 
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) featr[jj] = jj < nb ? s_feat[jj] : 0u;
             const uint8_t* trow = (const uint8_t*)(s_tile + lane * pitch);
+#if BIG_TMA_RING
+            if (use_tma) {
+                // row-index tiles staged by TMA: a ring of ENT_STAGES 256-byte tiles per warp runs ahead of the gathers
+                if (lane == 0)
+                    for (uint32_t sidx = 0; sidx < ENT_STAGES && sidx < n_my; ++sidx) {
+                        mbar_expect_tx(&s_bar[wid][sidx], 256u);
+                        tma_load_1d(&s_ent[wid][sidx][0], ent_in + a0 + 32u * (wid + sidx * NW), 256u, &s_bar[wid][sidx]);
+                    }
+                for (uint32_t i = 0; i < n_my; ++i) {
+                    const uint32_t stage = i % ENT_STAGES;
+                    mbar_wait(&s_bar[wid][stage], (tma_ph >> stage) & 1u);
+                    tma_ph ^= 1u << stage;
+                    const uint32_t idx = a0 + 32u * (wid + i * NW) + lane;
+                    Entry e = s_ent[wid][stage][lane];
+                    if (idx < t.begin || idx >= t.end) e = make_uint2(0u, 0u);
+                    fetch_rows32(bins, dstride, e.x, e.y != 0u, s_tile, lane);
+                    if (lane == 0 && i + ENT_STAGES < n_my) {  // every lane consumed its entry (fetch ends with __syncwarp)
+                        mbar_expect_tx(&s_bar[wid][stage], 256u);
+                        tma_load_1d(&s_ent[wid][stage][0], ent_in + a0 + 32u * (wid + (i + ENT_STAGES) * NW), 256u, &s_bar[wid][stage]);
+                    }
+                    if (e.y) {
+                        const uint32_t cls = ent_cls(e), w = ent_w(e);
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj)
+                            if (jj < nb) atomicAdd(&s_hist[jj * g.FS + hist_index(trow[featr[jj]], cls, C)], w);
+                    }
+                    __syncwarp();
+                }
+            } else
+#endif
             for (uint32_t base = t.begin; base < t.end; base += THREADS) {
                 const uint32_t idx = base + tid;
                 const Entry e = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
@@ -351,6 +416,33 @@ __global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* 
         }
 #pragma unroll
         for (int u = 0; u < PU; ++u) goL[u] = e[u].y && bins[(uint64_t)e[u].x * dstride + bf] <= bb;
+#if BIG_PART_SCAN
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            balL[u] = __ballot_sync(0xffffffffu, goL[u]);
+            balR[u] = __ballot_sync(0xffffffffu, e[u].y && !goL[u]);
+            if (lane == 0) s_wl[par][u][wid] = __popc(balL[u]) | (__popc(balR[u]) << 16);  // (left, right) counts packed
+        }
+        __syncthreads();
+        {   // packed exclusive scan over the PU x NW (chunk, warp) counts, in element order: lane = u * NW + w
+            static_assert(PU * NW <= 32, "one warp scans all chunk counts");
+            uint32_t cnt = lane < PU * NW ? s_wl[par][lane / NW][lane % NW] : 0u, incl = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t a = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= (uint32_t)off) incl += a;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int u = 0; u < PU; ++u) {
+                const uint32_t pre = __shfl_sync(0xffffffffu, incl - cnt, u * NW + wid);
+                const uint32_t pl = pre & 0xFFFFu, pr = pre >> 16;
+                if (goL[u]) ent_out[t.begin + lbase + pl + __popc(balL[u] & lanemask_lt())] = e[u];
+                else if (e[u].y) ent_out[t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt()))] = e[u];
+            }
+            lbase += tot & 0xFFFFu; rbase += tot >> 16;
+        }
+#else
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
             balL[u] = __ballot_sync(0xffffffffu, goL[u]);
@@ -371,6 +463,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_grow_big(GrowCtx g, const Task* 
             else if (e[u].y) ent_out[t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt()))] = e[u];
             lbase += tl; rbase += tr;
         }
+#endif
     }
     const uint32_t nLd = lbase;
     if (nLd == 0 || nLd == r) {  // cannot happen for a valid split; never loop on it

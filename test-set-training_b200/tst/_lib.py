@@ -77,7 +77,7 @@ def lib():
                                "(libtst has no CPU fallback)")
         L = C.CDLL(LIB_PATH)
         L.tst_last_error.restype = C.c_char_p
-        for name in ("tst_create", "tst_destroy", "tst_bin", "tst_set_bins", "tst_get_bins", "tst_assign_folds",
+        for name in ("tst_create", "tst_destroy", "tst_bin", "tst_bin_auto", "tst_set_bins", "tst_get_bins", "tst_assign_folds",
                      "tst_fit_oof", "tst_reduce_votes", "tst_finalize", "tst_ibp_select", "tst_ibp", "tst_predict",
                      "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_abi_version"):
             getattr(L, name).restype = C.c_int
@@ -85,7 +85,7 @@ def lib():
     return _lib
 
 
-EXPORTS = ["tst_abi_version", "tst_last_error", "tst_create", "tst_destroy", "tst_bin", "tst_set_bins", "tst_get_bins",
+EXPORTS = ["tst_abi_version", "tst_last_error", "tst_create", "tst_destroy", "tst_bin", "tst_bin_auto", "tst_set_bins", "tst_get_bins",
            "tst_assign_folds", "tst_fit_oof", "tst_reduce_votes", "tst_finalize", "tst_ibp_select", "tst_ibp",
            "tst_predict", "tst_export_tree", "tst_get_stats", "tst_reset_stats"]
 

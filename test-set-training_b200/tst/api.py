@@ -115,14 +115,23 @@ class Engine:
         return C.c_void_p(0 if t is None else t.data_ptr())
 
     # ---- table
-    def bin(self, X, n_bins: int = 256, edges=None, n_edges=None):
-        """X: host array or device tensor [n, d].  Edges are picked on the host (binning.py), the map runs on the GPU."""
+    def bin(self, X, n_bins: int = 256, edges=None, n_edges=None, host_edges: bool = False):
+        """X: host array or device tensor [n, d].  By default the bin edges are selected on the GPU
+        (tst_bin_auto: per-column radix sort + integer-rank quantiles); `edges=` / `host_edges=True` use the
+        host rule of binning.py (bit-identical, kept as the cross-check)."""
         torch = _torch()
+        Xd = self.to_dev(X, torch.float32)
+        n, d = Xd.shape
+        if edges is None and not host_edges:
+            edges = np.zeros((d, binning.MAX_EDGES), np.float64)
+            n_edges = np.zeros(d, np.int32)
+            check(_lib.lib().tst_bin_auto(self._h, self._ptr(Xd), C.c_int64(n), C.c_int32(d), C.c_int32(n_bins),
+                                          edges.ctypes.data_as(C.c_void_p), n_edges.ctypes.data_as(C.c_void_p), self._stream()))
+            self.n, self.d, self.edges, self.n_edges = n, d, edges, n_edges
+            return self
         if edges is None:
             Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
             edges, n_edges = binning.table_edges(Xh, n_bins)
-        Xd = self.to_dev(X, torch.float32)
-        n, d = Xd.shape
         edges = np.ascontiguousarray(edges, np.float64)
         n_edges = np.ascontiguousarray(n_edges, np.int32)
         check(_lib.lib().tst_bin(self._h, self._ptr(Xd), C.c_int64(n), C.c_int32(d), edges.ctypes.data_as(C.c_void_p),

@@ -88,6 +88,32 @@ def test_bin_map_ragged_shapes(eng):
         assert np.array_equal(eng.get_bins(), ref), (n, d)
 
 
+@pytest.mark.parametrize("n_bins", [256, 16, 3])
+def test_device_edge_selection_bit_exact(eng, n_bins):
+    """tst_bin_auto (radix sort + integer-rank quantiles on the GPU) against the oracle's edge rule."""
+    rng = np.random.default_rng(n_bins)
+    n = 5003
+    cols = [rng.standard_normal(n), np.round(rng.standard_normal(n) * 3), rng.poisson(3.0, n).astype(float),
+            np.full(n, 2.5), rng.integers(0, 300, n).astype(float), -np.abs(rng.standard_normal(n)) * 1e-30,
+            np.where(rng.random(n) < 0.3, np.nan, rng.standard_normal(n)), np.full(n, np.nan),
+            np.where(rng.random(n) < 0.5, -0.0, 0.0), rng.standard_normal(n) * 1e30]
+    X = np.stack(cols, axis=1).astype(np.float32)
+    X[7, 0] = np.inf
+    X[8, 0] = -np.inf
+    edges, ne = H.find_edges(X, n_bins)
+    eng.bin(X, n_bins=n_bins)
+    assert np.array_equal(eng.n_edges, ne)
+    assert np.array_equal(eng.edges, edges)
+    assert np.array_equal(eng.get_bins(), H.bin_table(X, edges, ne))
+    eng.bin(X, n_bins=n_bins, host_edges=True)  # the host rule gives the same table
+    assert np.array_equal(eng.edges, edges) and np.array_equal(eng.get_bins(), H.bin_table(X, edges, ne))
+    for nn in (1, 2, 31, 257):
+        Xs = X[:nn].copy()
+        e2, n2 = H.find_edges(Xs, n_bins)
+        eng.bin(Xs, n_bins=n_bins)
+        assert np.array_equal(eng.n_edges, n2) and np.array_equal(eng.edges, e2), nn
+
+
 def test_set_bins_roundtrip(eng, vsi_small):
     eng.set_bins(vsi_small["bins"])
     assert np.array_equal(eng.get_bins(), vsi_small["bins"])
