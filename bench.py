@@ -275,7 +275,7 @@ def main():
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = dict(value=K_FOLDS * T * world * e2e_steps / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                    steps=e2e_steps, ms_per_step=1e3 * dt / e2e_steps,
-                   note="tst.run_tst on host arrays: pinned H2D of X/y, host bin-edge selection, GPU binning, folds, fit, s(x), D2H of s/votes/folds")
+                   note="tst.run_tst on host arrays: pinned H2D of X/y, bin-edge selection + binning on the GPU, folds, fit, s(x), D2H of s/votes/folds")
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic", config=workload(T),
@@ -289,7 +289,7 @@ def main():
             fold_h = fold_dev.cpu().numpy()
             line["cpu_baseline"], _ = cpu_baseline_port(X, yi, bins_cm, fold_h)
         if not args.no_secondary:
-            line["secondary"] = secondary_wallclock(tst, synth)
+            line["secondary"] = secondary_wallclock(tst, synth, eng)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -297,21 +297,30 @@ def main():
     return 0
 
 
-def secondary_wallclock(tst, synth):
-    """BASELINE.json's second metric: end-to-end TsT + IBP wall-clock on the VSI-shaped table (latency-bound)."""
+def secondary_wallclock(tst, synth, eng):
+    """BASELINE.json's second metric: end-to-end TsT + IBP wall-clock on the VSI-shaped table (latency-bound).
+    Best of 3 after one warm-up call each (the first call pays allocations and lazy kernel loading)."""
     import torch
 
     X, y = synth.vsi_table()
     out = {}
-    tst.run_tst(X, y, k=5, n_trees=100, seed=0)
-    torch.cuda.synchronize()
-    t = time.perf_counter()
-    r = tst.run_tst(X, y, k=5, n_trees=100, seed=1)
-    out["tst_vsi_5k_x32_5fold_x100_ms"] = 1e3 * (time.perf_counter() - t)
+    tst.run_tst(X, y, k=5, n_trees=100, seed=0, engine=eng)
+    best = 1e9
+    for i in range(3):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = tst.run_tst(X, y, k=5, n_trees=100, seed=1 + i, engine=eng)
+        best = min(best, time.perf_counter() - t)
+    out["tst_vsi_5k_x32_5fold_x100_ms"] = 1e3 * best
     out["tst_vsi_kernel_launches"] = int(r.stats["kernel_launches"])
-    t = time.perf_counter()
-    rb = tst.ibp(X, y, rounds=10, k=5, n_trees=200, tau=0.5, batch=250, seed=0, want_s=False)
-    out["ibp_10rounds_5fold_x200_ms"] = 1e3 * (time.perf_counter() - t)
+    tst.ibp(X, y, rounds=2, k=5, n_trees=200, tau=0.5, batch=250, seed=0, want_s=False, engine=eng)
+    best = 1e9
+    for i in range(3):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        rb = tst.ibp(X, y, rounds=10, k=5, n_trees=200, tau=0.5, batch=250, seed=0, want_s=False, engine=eng)
+        best = min(best, time.perf_counter() - t)
+    out["ibp_10rounds_5fold_x200_ms"] = 1e3 * best
     out["ibp_removed_per_round"] = rb.removed_per_round.tolist()
     out["note"] = "host arrays in, host arrays out; latency-bound (5k rows): reported as wall-clock, not bandwidth"
     return out
