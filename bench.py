@@ -134,7 +134,7 @@ def run_reference(args):
               f"sklearn {sklearn.__version__} RandomForestClassifier(n_jobs={cores}) defaults")
     line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=workload(trees),
+                data="synthetic", config=dict(workload(args.trees_per_fold), reference_sample=sample),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample,
                                   note="the reference repository ships no code; this is the committed sklearn restatement of the paper's RF diagnostic"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)

@@ -408,3 +408,24 @@ class TsTForest:
 
     def export_tree(self, t: int):
         return self._eng.export_tree(0, t, self.n_classes_)
+
+    @property
+    def feature_importances_(self) -> np.ndarray:
+        """Gini importances (mean over trees, normalised), computed on the host from the exported trees --
+        the "interpretable auditing" output of REF/README.md:35 (SK/ensemble/_forest.py feature_importances_)."""
+        from .features import gini_importances
+
+        imp = np.zeros(self.n_features_in_, dtype=np.float64)
+        for t in range(self.n_estimators):
+            nodes, counts = self.export_tree(t)
+            imp += gini_importances(nodes, counts, self.n_features_in_)
+        imp /= self.n_estimators
+        s = imp.sum()
+        return imp / s if s > 0 else imp
+
+    def sklearn_tree(self, t: int) -> dict:
+        """Tree `t` as sklearn-style node arrays with raw-space thresholds (SK/tree/_tree.pxd:15-25)."""
+        from .features import to_sklearn_arrays
+
+        nodes, counts = self.export_tree(t)
+        return to_sklearn_arrays(nodes, counts, self._eng.edges)

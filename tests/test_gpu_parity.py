@@ -346,3 +346,7 @@ def test_public_api_run_tst_and_forest(vsi_small):
     ot = forest.tree(0, 4)
     compare_tree(gn, gc, ot.nodes, ot.counts, "forest tree 4")
     assert (clf.predict(v["X"]) == v["y"]).mean() > 0.9  # fully grown trees memorise the training set
+    imp = clf.feature_importances_
+    assert imp.shape == (16,) and abs(imp.sum() - 1.0) < 1e-9 and (imp >= 0).all()
+    sk = clf.sklearn_tree(0)
+    assert sk["threshold"].shape == sk["feature"].shape and np.isfinite(sk["threshold"]).all()
