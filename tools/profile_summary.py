@@ -82,7 +82,13 @@ def kernel(src, dst, traffic_json=None):
     if traffic_json and traffic:
         u = units.get("dram__bytes_read.sum", "byte").lower()
         scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
-        json.dump({"dram_bytes_per_launch": sum(traffic) * scale / len(traffic), "launches": len(traffic), "source": dst}, open(traffic_json, "w"))
+        try:
+            allk = json.load(open(traffic_json))
+        except Exception:
+            allk = {}
+        kname = launches_[0]["name"].replace("void ", "").split("<")[0].split("(")[0].strip() if launches_ else "kernel"
+        allk[kname] = {"dram_bytes_per_launch": sum(traffic) * scale / len(traffic), "launches": len(traffic), "source": dst}
+        json.dump(allk, open(traffic_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
