@@ -45,6 +45,10 @@ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __u
 // multiplicity >= 1, so y == 0 marks padding.  64-bit entries keep the class next to the row id
 // (no label gather in the hot loops) and leave the full 32 bits to the row id.
 typedef uint2 Entry;
+// entry lists are read once per pass and written once per level: stream them (evict-first) so they do not
+// push the binned table out of L2
+__device__ __forceinline__ Entry ent_load(const Entry* p) { return __ldcs(p); }
+__device__ __forceinline__ void ent_store(Entry* p, const Entry& e) { __stcs(p, e); }
 __device__ __forceinline__ uint32_t ent_w(const Entry& e) { return e.y & 0xFFu; }
 __device__ __forceinline__ uint32_t ent_cls(const Entry& e) { return e.y >> 8; }
 

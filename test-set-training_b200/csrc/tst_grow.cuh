@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 #endif
             for (uint32_t base = t.begin; base < t.end; base += THREADS) {
                 const uint32_t idx = base + tid;
-                const Entry e = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
+                const Entry e = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
                 fetch_rows32(bins, dstride, e.x, e.y != 0u, s_tile, lane);
                 if (e.y) {
                     const uint32_t cls = ent_cls(e), w = ent_w(e);
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     uint32_t idx = base + u * THREADS;
-                    e[u] = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
+                    e[u] = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
                 }
                 const int jr = (int)lane % nb;  // rotate features across lanes: spreads same-address atomics
                 for (int jj = 0; jj < nb; ++jj) {
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
             uint32_t idx = c0 + u * THREADS + tid;
-            e[u] = idx < t.end ? ent_in[idx] : make_uint2(0u, 0u);
+            e[u] = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < PU; ++u) goL[u] = e[u].y && bins[(uint64_t)e[u].x * dstride + bf] <= bb;
@@ -437,8 +437,8 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
             for (int u = 0; u < PU; ++u) {
                 const uint32_t pre = __shfl_sync(0xffffffffu, incl - cnt, u * NW + wid);
                 const uint32_t pl = pre & 0xFFFFu, pr = pre >> 16;
-                if (goL[u]) ent_out[t.begin + lbase + pl + __popc(balL[u] & lanemask_lt())] = e[u];
-                else if (e[u].y) ent_out[t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt()))] = e[u];
+                if (goL[u]) ent_store(ent_out + t.begin + lbase + pl + __popc(balL[u] & lanemask_lt()), e[u]);
+                else if (e[u].y) ent_store(ent_out + t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt())), e[u]);
             }
             lbase += tot & 0xFFFFu; rbase += tot >> 16;
         }
@@ -459,8 +459,8 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                 if (w < (int)wid) { pl += a; pr += b; }
                 tl += a; tr += b;
             }
-            if (goL[u]) ent_out[t.begin + lbase + pl + __popc(balL[u] & lanemask_lt())] = e[u];
-            else if (e[u].y) ent_out[t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt()))] = e[u];
+            if (goL[u]) ent_store(ent_out + t.begin + lbase + pl + __popc(balL[u] & lanemask_lt()), e[u]);
+            else if (e[u].y) ent_store(ent_out + t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt())), e[u]);
             lbase += tl; rbase += tr;
         }
 #endif
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task
         uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
         uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
         const uint32_t r = t.end - t.begin;
-        Entry e = lane < r ? ent[t.begin + lane] : make_uint2(0u, 0u);
+        Entry e = lane < r ? ent_load(ent + t.begin + lane) : make_uint2(0u, 0u);
         uint32_t cls = ent_cls(e);
         uint32_t lo = 0, hi = r, depth = t.depth, slot = t.slot, sp = 0;
         unsigned long long visits = 0, n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         uint32_t i = lane + 32u * k;
-        e[k] = i < r ? ent_in[t.begin + i] : make_uint2(0u, 0u);  // multiplicity 0 = padding
+        e[k] = i < r ? ent_load(ent_in + t.begin + i) : make_uint2(0u, 0u);  // multiplicity 0 = padding
     }
     for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
     __syncwarp();
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
     for (int k = 0; k < R; ++k) {
         const bool l = (goL >> k) & 1u, v = e[k].y != 0u;
         const uint32_t balL = __ballot_sync(0xffffffffu, l), balR = __ballot_sync(0xffffffffu, v && !l);
-        if (l) ent_out[t.begin + lbase + __popc(balL & lanemask_lt())] = e[k];
-        else if (v) ent_out[t.begin + nLd + rbase + __popc(balR & lanemask_lt())] = e[k];
+        if (l) ent_store(ent_out + t.begin + lbase + __popc(balL & lanemask_lt()), e[k]);
+        else if (v) ent_store(ent_out + t.begin + nLd + rbase + __popc(balR & lanemask_lt()), e[k]);
         lbase += __popc(balL);
         rbase += __popc(balR);
     }
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         uint32_t i = lane + 32u * k;
-        e[k] = i < r ? ent_in[t.begin + i] : make_uint2(0u, 0u);
+        e[k] = i < r ? ent_load(ent_in + t.begin + i) : make_uint2(0u, 0u);
     }
     for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
     __syncwarp();
@@ -380,8 +380,8 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
     for (int k = 0; k < R; ++k) {
         const bool l = (goL >> k) & 1u, v = e[k].y != 0u;
         const uint32_t balL = __ballot_sync(0xffffffffu, l), balR = __ballot_sync(0xffffffffu, v && !l);
-        if (l) ent_out[t.begin + lbase + __popc(balL & lanemask_lt())] = e[k];
-        else if (v) ent_out[t.begin + nLd + rbase + __popc(balR & lanemask_lt())] = e[k];
+        if (l) ent_store(ent_out + t.begin + lbase + __popc(balL & lanemask_lt()), e[k]);
+        else if (v) ent_store(ent_out + t.begin + nLd + rbase + __popc(balR & lanemask_lt()), e[k]);
         lbase += __popc(balL);
         rbase += __popc(balR);
     }

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
         uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
         uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
         const uint32_t r = t.end - t.begin;
-        Entry e = lane < r ? ent[t.begin + lane] : make_uint2(0u, 0u);
+        Entry e = lane < r ? ent_load(ent + t.begin + lane) : make_uint2(0u, 0u);
         uint32_t lo = 0, hi = r, depth = t.depth, slot = t.slot, sp = 0;
         unsigned long long visits = 0, n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0;
         uint32_t maxd = 0;
