@@ -206,6 +206,43 @@ def test_edge_cases_bit_exact(eng, name, pk):
     check_stats(gst, ost)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configurations_bit_exact(eng, seed):
+    """Randomised shapes / cardinalities / parameters: every tier (CTA, warp-per-node, warp-per-subtree, packed and
+    generic) is hit with node sizes straddling the 32- and 256-row tier boundaries."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([37, 64, 65, 300, 513, 1400, 3000]))
+    d = int(rng.integers(1, 40))
+    C = int(rng.choice([1, 2, 3, 4, 5, 9, 17]))
+    card = int(rng.choice([2, 3, 7, 40, 256]))
+    k = int(rng.integers(1, 5))
+    bins = rng.integers(0, card, (d, n)).astype(np.uint8)
+    if rng.random() < 0.3:
+        bins[rng.integers(0, d)] = 255 * (rng.random(n) < 0.2)  # a NaN-bin column
+    y = rng.integers(0, C, n).astype(np.uint8)
+    if rng.random() < 0.5 and d > 1:  # make the labels learnable so trees are not all noise
+        y = ((bins[0].astype(int) * C) // card).clip(0, C - 1).astype(np.uint8)
+        flip = rng.random(n) < 0.15
+        y[flip] = rng.integers(0, C, int(flip.sum()))
+    active = (rng.random(n) < 0.9).astype(np.uint8)
+    fold = H.assign_folds(y, active, k, C)
+    pk = {}
+    if rng.random() < 0.3:
+        pk["max_depth"] = int(rng.integers(1, 12))
+    if rng.random() < 0.3:
+        pk["min_samples_leaf"] = int(rng.integers(1, 6)); pk["min_samples_split"] = int(rng.integers(2, 12))
+    if rng.random() < 0.3:
+        pk["max_features"] = int(rng.integers(1, d + 1))
+    T = 3
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, T, C, seed=seed, keep=True, **pk)
+    assert np.array_equal(gv, ov), (n, d, C, card, k, pk)
+    check_stats(gst, ost)
+    part, t = int(rng.integers(0, k)), int(rng.integers(0, T))
+    gn, gc = eng.export_tree(part, t, C)
+    ot = forest.tree(part, t)
+    compare_tree(gn, gc, ot.nodes, ot.counts, f"seed {seed} tree({part},{t})")
+
+
 def test_fewer_rows_than_folds(eng):
     rng = np.random.default_rng(2)
     bins = rng.integers(0, 9, (3, 4)).astype(np.uint8)
