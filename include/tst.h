@@ -78,6 +78,8 @@ typedef struct {
     double ms_grow_mid;         /* warp-per-node kernel (k_grow_mid) */
     uint64_t launches_grow_mid;
     uint64_t row_visits_mid;    /* ... by the warp-per-node kernel */
+    double ms_grow_tiny;        /* thread-per-subtree kernel (k_grow_tiny4); its visits are counted in row_visits_small */
+    uint64_t launches_grow_tiny;
 } tst_stats;
 
 /* Canonical tree export: nodes in breadth-first order, i.e. sorted by (depth, begin). */

@@ -11,6 +11,7 @@
 #include "tst_grow.cuh"
 #include "tst_grow_small.cuh"
 #include "tst_grow_mid.cuh"
+#include "tst_grow_tiny.cuh"
 #include "tst_prep.cuh"
 #include "tst_quantile.cuh"
 
@@ -65,7 +66,7 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qmid0, qmid1, qsmall, counters, dstats, infer_parts;
+        qmid0, qmid1, qsmall, qtiny, qtiny2, counters, dstats, infer_parts;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
@@ -83,6 +84,10 @@ struct tst_handle {
 
 static const int BIG_THREADS = 256;
 static const int SMALL_WARPS = 4;
+#ifndef TINY_MAX_ROWS
+#define TINY_MAX_ROWS 6
+#endif
+static const int TINY_MAX = TINY_MAX_ROWS;   // thread-per-subtree tier: rows held in registers by one thread
 static const int MID_WARPS = 8;
 static const int MID_R = 8;  // warp-per-node tier holds up to 32 * MID_R rows in registers
 static const size_t BIG_SMEM_BUDGET = 64 * 1024;
@@ -109,7 +114,7 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize; h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     if (const char* ev = getenv("TST_L2_PERSIST")) h->l2_persist = atoi(ev) != 0;
     memset(&h->stats, 0, sizeof(h->stats));
-    CK(cudaMallocHost((void**)&h->h_pinned, 64));
+    CK(cudaMallocHost((void**)&h->h_pinned, 256));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->ev2));
@@ -126,7 +131,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qsmall, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qtiny, &h->qtiny2, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk};
     for (DevBuf* b : bufs) b->release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -345,7 +350,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->part_start, (size_t)(np + 1) * 4);
     ENSURE(h->sorted, (size_t)n * 4);
     ENSURE(h->dstats, sizeof(DevStats));
-    ENSURE(h->counters, 64);
+    ENSURE(h->counters, 256);
     CK(cudaMemsetAsync(h->dstats.p, 0, sizeof(DevStats), st));
     k_part_count<1024><<<np, 1024, 0, st>>>(fold_dev, group_dev, n, k, h->part_count.as<uint32_t>());
     CKL();
@@ -389,14 +394,14 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint32_t n_chunks = (uint32_t)((n_pad + BOOT_CHUNK - 1) / BOOT_CHUNK);
     const uint64_t node_stride = 2 * n_cap;
     const uint64_t leafc_stride = (n_cap / 2 + 1) * (uint64_t)C;
-    const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / 8 + 2;
+    const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / 8 + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
-    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 2 * n_cap * sizeof(Entry) + (4 * qbig_per + qsmall_per) * sizeof(Task) + sizeof(TreeDesc);
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 2 * n_cap * sizeof(Entry) + (4 * qbig_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
-                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qsmall.cap + h->keep_nodes.cap + h->keep_leafc.cap;
+                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qsmall.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap;
     size_t budget = (size_t)((free_b + reclaim) * 0.6);
     if (keep) {
         size_t need = total_trees * arena_bytes;
@@ -419,6 +424,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->qmid0, B * qbig_per * sizeof(Task));
     ENSURE(h->qmid1, B * qbig_per * sizeof(Task));
     ENSURE(h->qsmall, B * qsmall_per * sizeof(Task));
+    ENSURE(h->qtiny, B * qtiny_per * 16);
+    ENSURE(h->qtiny2, B * qtiny_per * 16);
     ENSURE(h->infer_parts, (size_t)n_groups * k * sizeof(InferPart));
     uint2* nodes_p; uint32_t* leafc_p;
     if (keep) {
@@ -456,6 +463,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
     uint32_t* counters = h->counters.as<uint32_t>();  // [0],[1] big queue counts, [2] small count, [3],[4] mid queue counts
     g.qsmall_count = counters + 2;
+    g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
+    g.tiny_max = (C <= 4 && d <= TINY_FY_MAX && B <= 65535) ? TINY_MAX : 0;  // packed 4-class thread-per-subtree tier
+    if (const char* ev = getenv("TST_TINY_MAX")) g.tiny_max = std::min<uint32_t>(g.tiny_max, (uint32_t)atoi(ev));
     const bool mid_packed = C <= 4;  // packed 16-bit class counts (k_grow_mid4)
     const uint32_t mid_per_warp = mid_packed ? MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2)
                                              : (uint32_t)g.FS + 2u * (uint32_t)C + (uint32_t)((d + 1) / 2);
@@ -469,11 +479,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         CK(cudaMemcpyAsync(h->trees.p, all.data() + b0, (size_t)nb * sizeof(TreeDesc), cudaMemcpyHostToDevice, st));
         g.qbig_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qbig_per);
         g.qsmall_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qsmall_per);
+        g.qtiny_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qtiny_per);
 
         // ---- bootstrap + compaction
         CK(cudaEventRecord(h->ev0, st));
         CK(cudaMemsetAsync(h->counts8.p, 0, (size_t)nb * n_pad, st));
-        CK(cudaMemsetAsync(counters, 0, 64, st));
+        CK(cudaMemsetAsync(counters, 0, 256, st));
         {
             uint32_t blocks4 = (max_train + 3) / 4;
             dim3 grid((blocks4 + 255) / 256, nb);
@@ -501,7 +512,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         int cur = 0;
         uint64_t level_guard = 0;
         uint32_t small_done = 0;
-        bool small_started = false;
+        bool small_started = false, tiny_timed = false;
         uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[3];
         while (nbig > 0 || nmid > 0) {
             Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
@@ -580,6 +591,28 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             CK(cudaEventRecord(h->evs1, ss));
             if (h->overlap) CK(cudaStreamWaitEvent(st, h->evs1, 0));
         }
+        // ---- subtrees with <= TINY_MAX rows: one thread each (tasks come from every other tier)
+        if (g.tiny_max) {
+            CK(cudaMemcpyAsync(h->h_pinned, counters, 128, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const uint32_t ntiny = h->h_pinned[5];
+            if (ntiny > g.qtiny_cap) return fail(TST_ERR_OVERFLOW, "tiny-node queue overflowed");
+            if (ntiny) {
+                // bucket offsets, largest subtrees first; counters[6 + r] holds the number of tasks with r rows
+                uint32_t cur[TINY_MAX + 1], acc = 0;
+                for (int rr = TINY_MAX; rr >= 0; --rr) { cur[rr] = acc; acc += h->h_pinned[6 + rr]; }
+                for (int rr = 0; rr <= TINY_MAX; ++rr) h->h_pinned[32 + rr] = cur[rr];
+                CK(cudaMemcpyAsync(counters + 32, h->h_pinned + 32, (TINY_MAX + 1) * 4, cudaMemcpyHostToDevice, st));
+                CK(cudaEventRecord(h->evm0, st));
+                k_tiny_sort<<<(ntiny + 255) / 256, 256, 0, st>>>((const uint4*)h->qtiny.p, ntiny, counters + 32, (uint4*)h->qtiny2.p);
+                CKL();
+                k_grow_tiny4<TINY_MAX><<<(ntiny + 127) / 128, 128, 0, st>>>(g, (const uint4*)h->qtiny2.p, ntiny);
+                CKL();
+                CK(cudaEventRecord(h->evm1, st));
+                tiny_timed = true;
+                h->stats.kernel_launches += 2; h->stats.launches_grow_tiny++;
+            }
+        }
         // ---- OOF inference of this batch's trees on their held-out rows
         std::vector<InferPart> ips;
         uint32_t max_fsz = 0;
@@ -605,6 +638,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         }
         CK(cudaStreamSynchronize(st));
         if (small_started) { float ms = 0; cudaEventElapsedTime(&ms, h->evs0, h->evs1); h->stats.ms_grow_small += ms; }  // span when overlapped
+        if (tiny_timed) { float ms = 0; cudaEventElapsedTime(&ms, h->evm0, h->evm1); h->stats.ms_grow_tiny += ms; }
         if (evi0) {
             float ms = 0; cudaEventElapsedTime(&ms, evi0, evi1); h->stats.ms_infer += ms;
             cudaEventDestroy(evi0); cudaEventDestroy(evi1);

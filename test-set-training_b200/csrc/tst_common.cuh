@@ -104,6 +104,10 @@ struct GrowCtx {
     Task* qsmall;
     uint32_t* qsmall_count;
     uint32_t qsmall_cap;
+    void* qtiny;      // thread-per-subtree queue (16-byte TinyTask), rows <= tiny_max
+    uint32_t* qtiny_count;
+    uint32_t qtiny_cap;
+    uint32_t tiny_max; // 0 disables the tier
     DevStats* stats;
     int32_t big_tile; // k_grow_big stages whole rows in shared memory (dstride <= 128)
     int32_t big_tma;  // ... and its row-index tiles arrive through TMA bulk copies
@@ -159,6 +163,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+
+__device__ __forceinline__ void tiny_push(const GrowCtx& g, uint32_t tree, uint32_t begin, uint32_t rows, uint32_t depth, uint32_t slot) {
+    // TinyTask = (begin, slot, depth, tree | rows << 16)
+    uint32_t i = atomicAdd(g.qtiny_count, 1u);
+    atomicAdd(g.qtiny_count + 1u + rows, 1u);  // histogram by row count: the tasks are sorted by size before they run
+    if (i < g.qtiny_cap) ((uint4*)g.qtiny)[i] = make_uint4(begin, slot, depth, tree | (rows << 16));
+    else g.stats->error = 2;
 }
 
 __device__ __forceinline__ void queue_push(Task* q, uint32_t* count, uint32_t cap, DevStats* st, const Task& t) {

@@ -63,7 +63,8 @@ __device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint
             ct.tree = t.tree; ct.begin = cb; ct.end = ce; ct.depth = t.depth + 1u; ct.slot = cslot;
             ct.pad0 = ct.pad1 = ct.pad2 = 0;
             const uint32_t cr = ce - cb;
-            if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
+            if (cr <= g.tiny_max) tiny_push(g, t.tree, cb, cr, t.depth + 1u, cslot);
+            else if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
             else if (cr > SMALL_MAX) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
             else queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
         }

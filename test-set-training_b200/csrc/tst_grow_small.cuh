@@ -65,12 +65,25 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
             const uint32_t t0 = F13(tot, 0), t1 = F13(tot, 1), t2 = F13(tot, 2), t3 = F13(tot, 3);
             const uint32_t N = t0 + t1 + t2 + t3;
             const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
+            const bool stop = stop_rule(g, N, depth, pure);
+            if (!stop && rr <= g.tiny_max) {
+                // hand the node to the thread-per-subtree tier: park its rows in the entry buffer of its depth
+                Entry* eb = ((depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+                if (active) ent_store(eb + t.begin + lane, e);
+                if (lane == 0) tiny_push(g, t.tree, abs_begin, rr, depth, slot);
+                if (sp == 0) break;
+                --sp;
+                uint32_t lh = s_stack[sp * 3];
+                lo = lh & 0xFFu; hi = lh >> 8; depth = s_stack[sp * 3 + 1]; slot = s_stack[sp * 3 + 2];
+                __syncwarp();
+                continue;
+            }
             n_nodes++;
             maxd = max(maxd, depth);
             bool found = false;
             double best_gain = -1.0;
             uint32_t best_key = 0xFFFFFFFFu;
-            if (!stop_rule(g, N, depth, pure)) {
+            if (!stop) {
                 visits += rr;
                 n_search++;
                 // group layout: G lanes per feature
