@@ -630,8 +630,17 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             CK(cudaMemcpyAsync(h->infer_parts.p, ips.data(), ips.size() * sizeof(InferPart), cudaMemcpyHostToDevice, st));
             CK(cudaEventCreate(&evi0)); CK(cudaEventCreate(&evi1));
             CK(cudaEventRecord(evi0, st));
-            dim3 grid((max_fsz + 255) / 256, (unsigned)ips.size());
-            k_oof_infer<<<grid, 256, 0, st>>>(g, h->infer_parts.as<InferPart>(), h->sorted.as<uint32_t>(), votes_dev);
+            // enough threads to fill the GPU: cut the trees of a partition into chunks when the held-out sets are small
+            uint32_t max_trees = 0, rows_total = 0;
+            for (auto& ip : ips) { max_trees = std::max(max_trees, ip.tree_hi - ip.tree_lo); rows_total += ip.fsz; }
+            uint32_t chunks = 1;
+            const uint32_t want_threads = (uint32_t)h->sm_count * 2048u * 2u;
+            if (rows_total < want_threads) chunks = std::min<uint32_t>(max_trees, std::max<uint32_t>(1u, want_threads / std::max(1u, rows_total)));
+            const uint32_t tpc = (max_trees + chunks - 1) / chunks;
+            chunks = (max_trees + tpc - 1) / tpc;
+            dim3 grid((max_fsz + 255) / 256, (unsigned)ips.size(), chunks);
+            if (chunks > 1) k_oof_infer<true><<<grid, 256, 0, st>>>(g, h->infer_parts.as<InferPart>(), h->sorted.as<uint32_t>(), votes_dev, tpc);
+            else k_oof_infer<false><<<grid, 256, 0, st>>>(g, h->infer_parts.as<InferPart>(), h->sorted.as<uint32_t>(), votes_dev, tpc);
             CKL();
             CK(cudaEventRecord(evi1, st));
             h->stats.kernel_launches++;

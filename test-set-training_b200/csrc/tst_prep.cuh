@@ -328,39 +328,49 @@ __global__ void k_init_roots(GrowCtx g, uint32_t n_trees) {
 // (count_c << 16) / N of the reached leaf (SK/tree/_criterion.pyx:483-486, _forest.py:961-962).
 struct InferPart { uint32_t fs, fsz, tree_lo, tree_hi; };
 
+template <bool ATOMIC>
 __device__ __forceinline__ void add_leaf_votes(uint2 rec, const uint32_t* __restrict__ leafc, int C, uint32_t* __restrict__ vrow) {
     uint32_t kind = rec.y >> 30;
     if (kind == KIND_PURE) {
-        if (rec.x) vrow[rec.y & 0xFFu] += 65536u;
+        if (rec.x) { if (ATOMIC) atomicAdd(&vrow[rec.y & 0xFFu], 65536u); else vrow[rec.y & 0xFFu] += 65536u; }
     } else {
         const uint32_t* lc = leafc + (uint64_t)rec.x * C;
         unsigned long long N = 0;
         for (int c = 0; c < C; ++c) N += lc[c];
-        if (N) for (int c = 0; c < C; ++c) { uint32_t v = (uint32_t)(((unsigned long long)lc[c] << 16) / N); if (v) vrow[c] += v; }
+        if (N) for (int c = 0; c < C; ++c) {
+            uint32_t v = (uint32_t)(((unsigned long long)lc[c] << 16) / N);
+            if (v) { if (ATOMIC) atomicAdd(&vrow[c], v); else vrow[c] += v; }
+        }
     }
 }
 
+// grid = (row blocks, partitions, tree chunks).  With one tree chunk a thread owns its row's votes; benchmark-sized
+// tables have too few held-out rows to fill the GPU, so the trees are cut into chunks as well and the (integer,
+// order-independent) votes are added atomically.
+template <bool ATOMIC>
 __global__ void __launch_bounds__(256) k_oof_infer(GrowCtx g, const InferPart* __restrict__ parts, const uint32_t* __restrict__ sorted,
-                                                   uint32_t* __restrict__ votes) {
+                                                   uint32_t* __restrict__ votes, uint32_t trees_per_chunk) {
     const InferPart ip = parts[blockIdx.y];
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= ip.fsz) return;
-    const uint32_t row = sorted[ip.fs + q];
-    const uint8_t* __restrict__ rp = g.bins_rm + (uint64_t)row * g.dstride;
-    uint32_t* vrow = votes + (uint64_t)row * g.C;
+    const uint32_t tlo = ip.tree_lo + blockIdx.z * trees_per_chunk, thi = min(ip.tree_hi, tlo + trees_per_chunk);
     unsigned long long steps = 0;
-    for (uint32_t t = ip.tree_lo; t < ip.tree_hi; ++t) {
-        const uint32_t arena = g.trees[t].arena;
-        const uint2* __restrict__ nodes = g.nodes + (uint64_t)arena * g.node_stride;
-        uint32_t slot = 0;
-        uint2 rec = nodes[0];
-        while ((rec.y >> 30) == KIND_INTERNAL) {
-            uint32_t f = (rec.y >> 8) & 0xFFFFu, b = rec.y & 0xFFu;
-            slot = rp[f] <= b ? slot + 1u : rec.x;
-            rec = nodes[slot];
-            steps++;
+    if (q < ip.fsz && tlo < thi) {
+        const uint32_t row = sorted[ip.fs + q];
+        const uint8_t* __restrict__ rp = g.bins_rm + (uint64_t)row * g.dstride;
+        uint32_t* vrow = votes + (uint64_t)row * g.C;
+        for (uint32_t t = tlo; t < thi; ++t) {
+            const uint32_t arena = g.trees[t].arena;
+            const uint2* __restrict__ nodes = g.nodes + (uint64_t)arena * g.node_stride;
+            uint32_t slot = 0;
+            uint2 rec = nodes[0];
+            while ((rec.y >> 30) == KIND_INTERNAL) {
+                uint32_t f = (rec.y >> 8) & 0xFFFFu, b = rec.y & 0xFFu;
+                slot = rp[f] <= b ? slot + 1u : rec.x;
+                rec = nodes[slot];
+                steps++;
+            }
+            add_leaf_votes<ATOMIC>(rec, g.leafc + (uint64_t)arena * g.leafc_stride, g.C, vrow);
         }
-        add_leaf_votes(rec, g.leafc + (uint64_t)arena * g.leafc_stride, g.C, vrow);
     }
     // warp-aggregate the step counter
 #pragma unroll
@@ -387,7 +397,7 @@ __global__ void __launch_bounds__(256) k_predict(const uint8_t* __restrict__ rm,
             slot = rp[f] <= b ? slot + 1u : rec.x;
             rec = nodes[slot];
         }
-        add_leaf_votes(rec, leafc_all + (uint64_t)arena * leafc_stride, C, vrow);
+        add_leaf_votes<false>(rec, leafc_all + (uint64_t)arena * leafc_stride, C, vrow);
     }
 }
 
