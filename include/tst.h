@@ -80,6 +80,7 @@ typedef struct {
     uint64_t row_visits_mid;    /* ... by the warp-per-node kernel */
     double ms_grow_tiny;        /* thread-per-subtree kernel (k_grow_tiny4); its visits are counted in row_visits_small */
     uint64_t launches_grow_tiny;
+    uint64_t launches_root;     /* dense root kernels (k_root_hist + k_root_split), timed inside ms_prep */
 } tst_stats;
 
 /* Canonical tree export: nodes in breadth-first order, i.e. sorted by (depth, begin). */

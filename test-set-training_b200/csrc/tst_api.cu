@@ -12,6 +12,7 @@
 #include "tst_grow_small.cuh"
 #include "tst_grow_mid.cuh"
 #include "tst_grow_tiny.cuh"
+#include "tst_root.cuh"
 #include "tst_prep.cuh"
 #include "tst_quantile.cuh"
 
@@ -66,7 +67,7 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qmid0, qmid1, qsmall, qtiny, qtiny2, counters, dstats, infer_parts;
+        qmid0, qmid1, qsmall, qtiny, qtiny2, counters, dstats, infer_parts, ghist, rsplit, y_pad;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
@@ -131,7 +132,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qtiny, &h->qtiny2, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk};
     for (DevBuf* b : bufs) b->release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -152,6 +153,8 @@ static int set_kernel_attrs(tst_handle* h) {
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_root_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_root_split, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_bin_map, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(k_cm_to_rm, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     h->attrs_set = true;
@@ -461,6 +464,20 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint32_t small_per_warp = small_packed ? 32u + 96u + (uint32_t)((d + 1) / 2)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
+    // dense root histograms (tst_root.cuh): big tables only; needs m <= 8 and the histogram + 2 TMA stages in shared memory
+    const size_t root_smem = (size_t)g.m * g.FS * 4 + 2 * (size_t)(g.m + 2) * ROOT_TILE;
+    bool root_dense = n >= 65536 && g.m <= 8 && root_smem <= 200 * 1024 && max_train > 32u * MID_R;
+    if (const char* ev = getenv("TST_ROOT_DENSE")) {  // 0 = off, 2 = on for any table size (tests)
+        if (atoi(ev) == 0) root_dense = false;
+        if (atoi(ev) == 2) root_dense = g.m <= 8 && root_smem <= 200 * 1024 && max_train > 32u * MID_R;
+    }
+    if (root_dense) {
+        ENSURE(h->ghist, B * (size_t)g.m * g.FS * 4);
+        ENSURE(h->rsplit, B * sizeof(RootSplit));
+        ENSURE(h->y_pad, (size_t)h->ld);
+        CK(cudaMemsetAsync(h->y_pad.p, 0, (size_t)h->ld, st));
+        CK(cudaMemcpyAsync(h->y_pad.p, y_dev, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    }
     uint32_t* counters = h->counters.as<uint32_t>();  // [0],[1] big queue counts, [2] small count, [3],[4] mid queue counts
     g.qsmall_count = counters + 2;
     g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
@@ -497,6 +514,18 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             CKL();
             k_boot_scatter<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), y_dev, g.entA, n_cap);
             CKL();
+            g.rsplit = nullptr;
+            if (root_dense) {
+                CK(cudaMemsetAsync(h->ghist.p, 0, (size_t)nb * g.m * g.FS * 4, st));
+                dim3 gr((unsigned)((n + ROOT_CHUNK - 1) / ROOT_CHUNK), nb);
+                k_root_hist<<<gr, 256, root_smem, st>>>(g, h->bins_cm.as<uint8_t>(), (uint64_t)h->ld, h->y_pad.as<uint8_t>(), h->counts8.as<uint8_t>(),
+                                                       (uint64_t)n, h->ghist.as<uint32_t>());
+                CKL();
+                k_root_split<<<nb, 256, (size_t)g.m * g.FS * 4, st>>>(g, h->ghist.as<uint32_t>(), h->rsplit.as<RootSplit>());
+                CKL();
+                g.rsplit = h->rsplit.as<RootSplit>();
+                h->stats.kernel_launches += 2; h->stats.launches_root += 2;
+            }
             g.qnext = h->qbig0.as<Task>(); g.qnext_count = counters + 0;
             g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 3;
             k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb);

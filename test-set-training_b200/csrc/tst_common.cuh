@@ -80,6 +80,15 @@ struct DevStats {
     uint32_t error;  // sticky: 1 = multiplicity overflow, 2 = queue overflow, 3 = bootstrap weight mismatch
 };
 
+struct RootSplit {
+    uint32_t state;  // 0 = none, 1 = split found, 2 = leaf (stop rule), 3 = no valid split among the first m: generic path
+    uint32_t key;    // feature << 8 | bin
+    uint32_t N;
+    uint32_t pad;
+    uint32_t tot[TST_MAX_CLASSES];
+    uint32_t bestL[TST_MAX_CLASSES];
+};
+
 struct GrowCtx {
     const uint8_t* bins_rm;  // [n][dstride]
     uint32_t dstride;
@@ -109,6 +118,7 @@ struct GrowCtx {
     uint32_t qtiny_cap;
     uint32_t tiny_max; // 0 disables the tier
     DevStats* stats;
+    const RootSplit* rsplit;  // non-null: big roots were split by the dense root kernels (Task.pad0 == 1)
     int32_t big_tile; // k_grow_big stages whole rows in shared memory (dstride <= 128)
     int32_t big_tma;  // ... and its row-index tiles arrive through TMA bulk copies
     int32_t MB;       // features per shared-histogram batch

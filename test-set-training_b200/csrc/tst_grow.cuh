@@ -236,7 +236,17 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 #endif
     __syncthreads();
 
-    int pos = 0;
+    // roots already split by the dense column-major kernels (tst_root.cuh) only need the partition below
+    const bool presplit = t.pad0 == 1u && g.rsplit != nullptr && (g.rsplit[t.tree].state == 1u || g.rsplit[t.tree].state == 2u);
+    if (presplit) {
+        if (tid == 0) {
+            const RootSplit& R = g.rsplit[t.tree];
+            s_N = R.N; s_bkey = R.key; s_found = R.state == 1u; s_stop = R.state == 2u;
+            for (int c = 0; c < C; ++c) { s_tot[c] = R.tot[c]; s_bestL[c] = R.bestL[c]; }
+        }
+        __syncthreads();
+    }
+    int pos = presplit ? d : 0;
     while (pos < d) {
         if (pos >= m && s_found) break;
         const bool primary = pos < m;

@@ -316,6 +316,7 @@ __global__ void k_init_roots(GrowCtx g, uint32_t n_trees) {
     }
     Task k;
     k.tree = t; k.begin = 0; k.end = td.n_inbag; k.depth = 0; k.slot = 0; k.pad0 = k.pad1 = k.pad2 = 0;
+    if (g.rsplit && td.n_inbag > g.mid_max) k.pad0 = 1;  // pre-split by k_root_hist / k_root_split
     if (td.n_inbag <= g.tiny_max) tiny_push(g, t, 0u, td.n_inbag, 0u, 0u);
     else if (td.n_inbag > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, k);
     else if (td.n_inbag > SMALL_MAX) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, k);

@@ -41,7 +41,7 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("levels", C.c_uint64), ("max_depth", C.c_uint32),
                 ("pad", C.c_uint32), ("ms_grow_big", C.c_double), ("ms_grow_small", C.c_double),
                 ("ms_prep", C.c_double), ("ms_infer", C.c_double), ("launches_grow_big", C.c_uint64),
-                ("launches_grow_small", C.c_uint64), ("ms_grow_mid", C.c_double), ("launches_grow_mid", C.c_uint64), ("row_visits_mid", C.c_uint64), ("ms_grow_tiny", C.c_double), ("launches_grow_tiny", C.c_uint64)]
+                ("launches_grow_small", C.c_uint64), ("ms_grow_mid", C.c_double), ("launches_grow_mid", C.c_uint64), ("row_visits_mid", C.c_uint64), ("ms_grow_tiny", C.c_double), ("launches_grow_tiny", C.c_uint64), ("launches_root", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}

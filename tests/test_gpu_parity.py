@@ -243,6 +243,30 @@ def test_random_configurations_bit_exact(eng, seed):
     compare_tree(gn, gc, ot.nodes, ot.counts, f"seed {seed} tree({part},{t})")
 
 
+@pytest.mark.parametrize("n,d,C,k", [(3000, 16, 4, 3), (5001, 9, 3, 2), (2100, 40, 7, 4)])
+def test_dense_root_kernels_bit_exact(eng, monkeypatch, n, d, C, k):
+    """k_root_hist / k_root_split (TMA-streamed column-major histogram of the root) forced on small tables."""
+    monkeypatch.setenv("TST_ROOT_DENSE", "2")
+    rng = np.random.default_rng(n)
+    bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
+    y = ((bins[1].astype(int) * C) // 256).astype(np.uint8)
+    flip = rng.random(n) < 0.2
+    y[flip] = rng.integers(0, C, int(flip.sum()))
+    fold = H.assign_folds(y, np.ones(n, np.uint8), k, C)
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, 4, C, seed=5, keep=True)
+    assert gst["launches_root"] > 0
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    gn, gc = eng.export_tree(k - 1, 2, C)
+    ot = forest.tree(k - 1, 2)
+    compare_tree(gn, gc, ot.nodes, ot.counts, "dense-root tree")
+    # a pure table: the dense root path must produce the one-leaf tree
+    y0 = np.zeros(n, np.uint8)
+    gv, ov, gst, ost, _ = run_both(eng, bins, y0, fold, k, 2, 1)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+
+
 def test_fewer_rows_than_folds(eng):
     rng = np.random.default_rng(2)
     bins = rng.integers(0, 9, (3, 4)).astype(np.uint8)
