@@ -86,8 +86,12 @@ def kernel(src, dst, traffic_json=None):
             allk = json.load(open(traffic_json))
         except Exception:
             allk = {}
-        kname = launches_[0]["name"].replace("void ", "").split("<")[0].split("(")[0].strip() if launches_ else "kernel"
-        allk[kname] = {"dram_bytes_per_launch": sum(traffic) * scale / len(traffic), "launches": len(traffic), "source": dst}
+        per = {}
+        for c, tr in zip(launches_, traffic):
+            kname = c["name"].replace("void ", "").split("<")[0].split("(")[0].strip()
+            per.setdefault(kname, []).append(tr)
+        for kname, v in per.items():
+            allk[kname] = {"dram_bytes_per_launch": sum(v) * scale / len(v), "launches": len(v), "source": dst}
         json.dump(allk, open(traffic_json, "w"), indent=1)
 
 
