@@ -411,3 +411,62 @@ def test_public_api_run_tst_and_forest(vsi_small):
     assert imp.shape == (16,) and abs(imp.sum() - 1.0) < 1e-9 and (imp >= 0).all()
     sk = clf.sklearn_tree(0)
     assert sk["threshold"].shape == sk["feature"].shape and np.isfinite(sk["threshold"]).all()
+
+
+# --------------------------------------------------------------------------------------------- full size (BASELINE.json configs[4])
+def test_full_size_properties():
+    """1M x 64, 10 folds: too big for the CPU oracle in a unit test, so the checks are the size-independent properties
+    of the domain -- determinism, independence from batching / tree ranges / rank count (integer votes), Q0.16 vote
+    mass per held-out row, binary-tree counters, fully grown trees reproducing their in-bag labels."""
+    import tst
+    from tst import synth
+
+    torch = _torch()
+    n, d, C, k, T = 1_000_000, 64, 4, 10, 1000
+    X, y = synth.scaleup_table(n, d, C, seed=0)
+    eng = tst.Engine(0)
+    eng.bin(X)
+    assert eng.n_edges.min() == 254  # continuous columns: all 255 bins used
+    y_dev = eng.to_dev(y, torch.uint8)
+    active = torch.ones(n, dtype=torch.uint8, device=eng.dev)
+    fold = eng.assign_folds(y_dev, active, k, C)
+    sizes = torch.bincount(fold.long(), minlength=k)
+    assert int(sizes.max() - sizes.min()) <= 1
+    prm = tst.make_params(d)
+
+    def fit(t0, t1, tif=0, rank=0, world=1, e=eng):
+        votes = e.new_votes(C)
+        p = tst.make_params(d, trees_in_flight=tif)
+        e.stats(reset=True)
+        e.fit_oof(y_dev, fold, k, T, C, p, seed=3, t0=t0, t1=t1, votes=votes)
+        return votes, e.stats()
+
+    v_all, st = fit(0, 2)
+    assert st["trees"] == 20 and st["nodes"] == 2 * st["leaves"] - st["trees"]
+    assert st["row_visits_big"] > st["row_visits_mid"] > st["row_visits_small"] > 0 and st["launches_root"] > 0
+    # every held-out row received 2 trees x 65536 of vote mass (floor rounding loses < C units per tree)
+    mass = v_all.sum(1)
+    assert int(mass.max()) <= 2 * 65536 and int(mass.min()) > 2 * 65536 - 2 * C
+    # determinism and batching independence
+    v_again, _ = fit(0, 2)
+    v_b3, _ = fit(0, 2, tif=3)
+    assert torch.equal(v_all, v_again) and torch.equal(v_all, v_b3)
+    # tree ranges compose
+    v0, _ = fit(0, 1)
+    v1, _ = fit(1, 2)
+    assert torch.equal(v_all, v0 + v1)
+    # two emulated ranks sum to the single-rank result
+    parts = []
+    for r in range(2):
+        e2 = tst.Engine(0, r, 2)
+        e2.set_bins(eng.get_bins())
+        vv = e2.new_votes(C)
+        e2.fit_oof(y_dev, fold, k, T, C, prm, seed=3, t0=0, t1=2, votes=vv)
+        parts.append(vv)
+        e2.close()
+    assert torch.equal(v_all, parts[0] + parts[1])
+    # blind accuracy is far above chance on this learnable table and s(x) is a probability
+    s, cor, tot = eng.finalize(v_all, y_dev, fold, k, 2, C)
+    acc = cor.double().sum() / tot.double().sum()
+    assert 0.4 < float(acc) < 0.9 and float(s.min()) >= 0 and float(s.max()) <= 1
+    eng.close()
