@@ -83,7 +83,10 @@ struct tst_handle {
     bool attrs_set = false;
 };
 
-static const int BIG_THREADS = 256;
+#ifndef BIG_THREADS_N
+#define BIG_THREADS_N 256
+#endif
+static const int BIG_THREADS = BIG_THREADS_N;
 static const int SMALL_WARPS = 4;
 #ifndef TINY_MAX_ROWS
 #define TINY_MAX_ROWS 6

@@ -267,6 +267,23 @@ def test_dense_root_kernels_bit_exact(eng, monkeypatch, n, d, C, k):
     check_stats(gst, ost)
 
 
+@pytest.mark.parametrize("d,C,mf", [(100, 3, "sqrt"), (200, 4, "sqrt"), (130, 6, 40), (70, 2, None)])
+def test_wide_tables_bit_exact(eng, d, C, mf):
+    """d > 64: rows wider than the shared row tile (byte-gather path), more than 8 sampled features per node
+    (several histogram batches), non-power-of-two row strides."""
+    rng = np.random.default_rng(d)
+    n = 1500
+    bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
+    y = ((bins[3].astype(int) + bins[d - 1]) % C).astype(np.uint8)
+    fold = H.assign_folds(y, np.ones(n, np.uint8), 3, C)
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, 3, 3, C, seed=2, keep=True, max_features=mf)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    gn, gc = eng.export_tree(1, 1, C)
+    ot = forest.tree(1, 1)
+    compare_tree(gn, gc, ot.nodes, ot.counts, f"wide d={d}")
+
+
 def test_fewer_rows_than_folds(eng):
     rng = np.random.default_rng(2)
     bins = rng.integers(0, 9, (3, 4)).astype(np.uint8)
