@@ -207,8 +207,7 @@ def main():
     T = args.trees_per_fold
     X, y = synth.scaleup_table(N_ROWS, N_FEAT, N_CLASSES, seed=0)
     eng = tst.Engine(local_rank, rank, world)
-    edges, n_edges = tst.binning.table_edges(X)
-    eng.bin(X, edges=edges, n_edges=n_edges)
+    eng.bin(X)  # bin edges selected on the device
     classes, yi = tst.api.encode_labels(y)
     y_dev = eng.to_dev(yi, torch.uint8)
     active = torch.ones(N_ROWS, dtype=torch.uint8, device=eng.dev)

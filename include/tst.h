@@ -96,9 +96,15 @@ typedef struct {
 int tst_abi_version(void);
 const char* tst_last_error(void);
 
-/* nccl_unique_id: reserved (NULL).  The vote exchange is done by the host with one NCCL
- * all-gather (torch.distributed) followed by tst_reduce_votes; see INTEGRATION.md. */
+/* Multi-GPU: one handle per (process, device).  nccl_unique_id (128 bytes from tst_nccl_unique_id on rank 0,
+ * distributed by the host) makes the handle join an NCCL communicator of `world` ranks (libnccl.so.2 is
+ * dlopen'ed: no link-time dependency); all ranks must call tst_create together.  With NULL the handle has no
+ * communicator and the host does the vote all-gather itself before tst_reduce_votes. */
+int tst_nccl_unique_id(void* out128);
 int tst_create(tst_handle** out, int device, int rank, int world, const void* nccl_unique_id);
+/* (C1 + K9) In place: ONE ncclAllGather of the [n_values] uint32 vote tensor over NVLink, then the rank-ordered
+ * integer sum.  Collective: every rank calls it.  No-op for world == 1. */
+int tst_allreduce_votes(tst_handle* h, uint32_t* votes_dev, int64_t n_values, void* stream);
 int tst_destroy(tst_handle* h);
 
 /* (1) Quantile binning -- "hand-crafted features" table ingest (REF/README.md:35); replaces
@@ -150,7 +156,8 @@ int tst_ibp_select(tst_handle* h, const uint32_t* votes_dev, const uint8_t* y_de
                    int32_t k, int32_t n_classes, uint64_t vmin, int64_t batch, uint8_t* active_dev,
                    int64_t* removed_host, void* stream);
 
-/* (7) Whole IBP loop kept on the device (single rank): rounds x (folds, fit, s, prune).
+/* (7) Whole IBP loop kept on the device: rounds x (folds, fit, [vote all-reduce], s, prune).  With world > 1 the
+ * handle needs a communicator and every rank calls it; all ranks end with the same active mask.
  * removed_host [rounds]; s_per_round_dev [rounds][n] float32 or NULL. */
 int tst_ibp(tst_handle* h, const uint8_t* y_dev, uint8_t* active_dev, const int32_t* group_dev, int32_t n_groups,
             int32_t k, int32_t n_trees, int32_t n_classes, const tst_params* params, uint64_t seed,

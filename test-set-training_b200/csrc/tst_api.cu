@@ -1,5 +1,7 @@
 // tst_api.cu -- host side of libtst.so: the C ABI declared in include/tst.h.
 // One translation unit; kernels live in the .cuh files next to it.  sm_100a only, no CPU fallback.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -54,6 +56,34 @@ struct DevBuf {
 
 struct KeptTree { int32_t part, t; uint32_t arena, n_inbag; };
 
+// NCCL through dlopen: the library is optional at link time and shared with the host's own copy (torch) when present.
+typedef struct { char internal[128]; } tst_nccl_id;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(tst_nccl_id*) = nullptr;
+    int (*CommInitRank)(void**, int, tst_nccl_id, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return -1;
+    g_nccl.GetUniqueId = (int (*)(tst_nccl_id*))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, tst_nccl_id, int))dlsym(lib, "ncclCommInitRank");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) return -1;
+    g_nccl.lib = lib;
+    return 0;
+}
+#define NCCL_UINT32 3  /* ncclUint32 */
+
 struct tst_handle {
     int device = 0, rank = 0, world = 1;
     int sm_count = 148;
@@ -74,7 +104,8 @@ struct tst_handle {
     int32_t kept_C = 0, kept_n_trees = 0;
     uint64_t kept_node_stride = 0, kept_leafc_stride = 0;
     // ibp / predict scratch
-    DevBuf ibp_fold, ibp_votes, ibp_removed, pred_cm, pred_rm, sort_a, sort_b, sort_dk;
+    DevBuf ibp_fold, ibp_votes, ibp_removed, pred_cm, pred_rm, sort_a, sort_b, sort_dk, gather;
+    void* comm = nullptr;  // ncclComm_t
     uint32_t* h_pinned = nullptr;  // 16 words
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
     cudaStream_t s_mid = nullptr, s_small = nullptr;  // side streams: warp-per-node and warp-per-subtree kernels overlap the CTA kernel
@@ -99,9 +130,16 @@ static const size_t BIG_SMEM_BUDGET = 64 * 1024;
 extern "C" int tst_abi_version(void) { return TST_ABI_VERSION; }
 extern "C" const char* tst_last_error(void) { return g_err.c_str(); }
 
+extern "C" int tst_nccl_unique_id(void* out128) {
+    if (!out128) return fail(TST_ERR_INVALID, "tst_nccl_unique_id: null argument");
+    if (load_nccl()) return fail(TST_ERR_UNSUPPORTED, "tst_nccl_unique_id: libnccl.so.2 not found");
+    int rc = g_nccl.GetUniqueId((tst_nccl_id*)out128);
+    if (rc) return fail(TST_ERR_CUDA, std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    return TST_OK;
+}
+
 extern "C" int tst_create(tst_handle** out, int device, int rank, int world, const void* nccl_unique_id) {
     if (!out || world < 1 || rank < 0 || rank >= world) return fail(TST_ERR_INVALID, "tst_create: bad arguments");
-    (void)nccl_unique_id;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -126,6 +164,13 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     CK(cudaStreamCreateWithFlags(&h->s_mid, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_small, cudaStreamNonBlocking));
     if (const char* ev = getenv("TST_OVERLAP")) h->overlap = atoi(ev) != 0;
+    if (nccl_unique_id && world > 1) {
+        if (load_nccl()) { delete h; return fail(TST_ERR_UNSUPPORTED, "tst_create: libnccl.so.2 not found"); }
+        tst_nccl_id id;
+        memcpy(&id, nccl_unique_id, sizeof(id));
+        int rc = g_nccl.CommInitRank(&h->comm, world, id, rank);
+        if (rc) { delete h; return fail(TST_ERR_CUDA, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); }
+    }
     *out = h;
     return TST_OK;
 }
@@ -136,8 +181,9 @@ extern "C" int tst_destroy(tst_handle* h) {
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
                       &h->qmid0, &h->qmid1, &h->qsmall, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
-                      &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk};
+                      &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk, &h->gather};
     for (DevBuf* b : bufs) b->release();
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -706,6 +752,21 @@ extern "C" int tst_reduce_votes(tst_handle* h, const uint32_t* gathered_dev, int
     return TST_OK;
 }
 
+extern "C" int tst_allreduce_votes(tst_handle* h, uint32_t* votes_dev, int64_t nv, void* stream) {
+    if (!h || !votes_dev || nv < 0) return fail(TST_ERR_INVALID, "tst_allreduce_votes: bad argument");
+    if (h->world == 1 || nv == 0) return TST_OK;
+    if (!h->comm) return fail(TST_ERR_STATE, "tst_allreduce_votes: the handle was created without an NCCL unique id");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ENSURE(h->gather, (size_t)h->world * nv * 4);
+    int rc = g_nccl.AllGather(votes_dev, h->gather.p, (size_t)nv, NCCL_UINT32, h->comm, st);
+    if (rc) return fail(TST_ERR_CUDA, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    k_reduce_votes<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(h->gather.as<uint32_t>(), h->world, nv, votes_dev);
+    CKL();
+    h->stats.kernel_launches++;
+    return TST_OK;
+}
+
 extern "C" int tst_finalize(tst_handle* h, const uint32_t* votes_dev, const uint8_t* y_dev, const uint8_t* fold_dev,
                             const int32_t* group_dev, int32_t n_groups, int32_t k, int32_t n_trees, int32_t C, float* s_dev,
                             uint32_t* correct_dev, uint32_t* total_dev, void* stream) {
@@ -751,7 +812,7 @@ extern "C" int tst_ibp(tst_handle* h, const uint8_t* y_dev, uint8_t* active_dev,
                        int64_t batch, int64_t* removed_host, float* s_per_round_dev, void* stream) {
     if (!h || !y_dev || !active_dev || !prm || !removed_host || rounds < 1) return fail(TST_ERR_INVALID, "tst_ibp: bad argument");
     if (!h->n) return fail(TST_ERR_STATE, "tst_ibp: bin the table first");
-    if (h->world != 1) return fail(TST_ERR_UNSUPPORTED, "tst_ibp: multi-rank IBP is driven by the host (see INTEGRATION.md)");
+    if (h->world != 1 && !h->comm) return fail(TST_ERR_STATE, "tst_ibp: world > 1 needs a handle created with an NCCL unique id (or drive the rounds from the host, INTEGRATION.md)");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = h->n;
@@ -773,6 +834,7 @@ extern "C" int tst_ibp(tst_handle* h, const uint8_t* y_dev, uint8_t* active_dev,
         rc = tst_fit_oof(h, y_dev, h->ibp_fold.as<uint8_t>(), group_dev, n_groups, k, n_trees, C, prm, seed, (uint32_t)(r * per_round), 0,
                          n_trees, h->ibp_votes.as<uint32_t>(), stream);
         if (rc) return rc;
+        if ((rc = tst_allreduce_votes(h, h->ibp_votes.as<uint32_t>(), (int64_t)n * C, stream))) return rc;
         if (s_per_round_dev) {
             rc = tst_finalize(h, h->ibp_votes.as<uint32_t>(), y_dev, h->ibp_fold.as<uint8_t>(), group_dev, n_groups, k, n_trees, C,
                               s_per_round_dev + (size_t)r * n, nullptr, nullptr, stream);

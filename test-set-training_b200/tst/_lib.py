@@ -19,7 +19,7 @@ MAX_FEATURES = 1024
 MAX_ROWS = 0x7FFFFFF0
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 class TstError(RuntimeError):
@@ -78,7 +78,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.tst_last_error.restype = C.c_char_p
         for name in ("tst_create", "tst_destroy", "tst_bin", "tst_bin_auto", "tst_set_bins", "tst_get_bins", "tst_assign_folds",
-                     "tst_fit_oof", "tst_reduce_votes", "tst_finalize", "tst_ibp_select", "tst_ibp", "tst_predict",
+                     "tst_fit_oof", "tst_reduce_votes", "tst_allreduce_votes", "tst_nccl_unique_id", "tst_finalize", "tst_ibp_select", "tst_ibp", "tst_predict",
                      "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_abi_version"):
             getattr(L, name).restype = C.c_int
         _lib = L
@@ -86,7 +86,7 @@ def lib():
 
 
 EXPORTS = ["tst_abi_version", "tst_last_error", "tst_create", "tst_destroy", "tst_bin", "tst_bin_auto", "tst_set_bins", "tst_get_bins",
-           "tst_assign_folds", "tst_fit_oof", "tst_reduce_votes", "tst_finalize", "tst_ibp_select", "tst_ibp",
+           "tst_assign_folds", "tst_fit_oof", "tst_reduce_votes", "tst_allreduce_votes", "tst_nccl_unique_id", "tst_finalize", "tst_ibp_select", "tst_ibp",
            "tst_predict", "tst_export_tree", "tst_get_stats", "tst_reset_stats"]
 
 

@@ -85,7 +85,10 @@ def shard_trees(n_parts: int, n_trees: int, rank: int, world: int, t0: int = 0, 
 class Engine:
     """One tst_handle = one (process, device).  All tensors handed to it live on that device."""
 
-    def __init__(self, device: int | None = None, rank: int = 0, world: int = 1):
+    def __init__(self, device: int | None = None, rank: int = 0, world: int = 1, lib_nccl: bool | None = None):
+        """lib_nccl: let libtst own the NCCL communicator (unique id broadcast through torch.distributed) so the vote
+        exchange and the multi-rank IBP loop run inside the library; default: on when torch.distributed is initialised
+        with `world` ranks, off for emulated ranks (tests)."""
         torch = _torch()
         if not torch.cuda.is_available():
             raise TstError(-2, "no CUDA device: the TsT engine has no CPU fallback")
@@ -93,7 +96,21 @@ class Engine:
         self.dev = torch.device("cuda", self.device)
         self.rank, self.world = rank, world
         self._h = C.c_void_p()
-        check(_lib.lib().tst_create(C.byref(self._h), self.device, rank, world, None))
+        uid = None
+        if lib_nccl is None:
+            lib_nccl = world > 1 and dist_info() == (rank, world)
+        if lib_nccl and world > 1:
+            import torch.distributed as dist
+
+            buf = (C.c_char * 128)()
+            if rank == 0:
+                check(_lib.lib().tst_nccl_unique_id(buf))
+            t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(self.dev)
+            dist.broadcast(t, src=0)
+            uid = (C.c_char * 128).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+        self.lib_nccl = uid is not None
+        with torch.cuda.device(self.dev):
+            check(_lib.lib().tst_create(C.byref(self._h), self.device, rank, world, uid))
         self.n = self.d = 0
         self.edges = self.n_edges = None
 
@@ -189,6 +206,9 @@ class Engine:
     def allreduce_votes(self, votes):
         """The path's one exchange step: NCCL all-gather of the per-rank votes, then a rank-ordered integer sum."""
         if self.world == 1:
+            return votes
+        if self.lib_nccl:  # in place, inside libtst: ncclAllGather + k_reduce_votes
+            check(_lib.lib().tst_allreduce_votes(self._h, self._ptr(votes), C.c_int64(votes.numel()), self._stream()))
             return votes
         torch = _torch()
         import torch.distributed as dist
@@ -358,7 +378,7 @@ def ibp(X, y, rounds: int = 10, k: int = 5, n_trees: int = 200, tau: float = 0.5
     active = torch.ones(n, dtype=torch.uint8, device=eng.dev)
     prm = make_params(eng.d, max_depth, min_samples_split, min_samples_leaf, max_features)
     eng.stats(reset=True)
-    if eng.world == 1:
+    if eng.world == 1 or eng.lib_nccl:  # the whole loop runs inside libtst (every rank calls it)
         removed, s = eng.ibp(y_dev, active, k, n_trees, n_classes, prm, seed, rounds, tau, batch, g_dev, n_groups, want_s)
     else:  # the per-round vote all-gather is issued from the host; data stays on the device
         removed = np.zeros(rounds, np.int64)

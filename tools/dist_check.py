@@ -22,11 +22,17 @@ s, _, _ = H.finalize(votes, y, fold, 5, 23)
 assert np.array_equal(res.oof_votes, votes), f"rank {rank}: votes differ"
 assert np.array_equal(res.s.view(np.uint32), s.view(np.uint32))
 assert res.stats["trees"] == len(tst.shard_trees(5, 23, rank, world))
+# same through the host-side exchange (torch.distributed all_gather + tst_reduce_votes)
+eng_host = tst.Engine(local, rank, world, lib_nccl=False)
+res2 = tst.run_tst(X, y, k=5, n_trees=23, seed=6, engine=eng_host)
+assert np.array_equal(res2.oof_votes, votes) and not eng_host.lib_nccl and tst.get_engine().lib_nccl
+r2 = tst.ibp(X, y, rounds=3, k=5, n_trees=10, tau=0.45, batch=100, seed=2, engine=eng_host)
 r = tst.ibp(X, y, rounds=3, k=5, n_trees=10, tau=0.45, batch=100, seed=2)
+assert np.array_equal(r.keep_mask, r2.keep_mask) and r.removed_per_round.tolist() == r2.removed_per_round.tolist()
 oact, orem, os_ = H.ibp(bins, y, 5, 10, 4, H.make_params(24), seed=2, rounds=3, tau=0.45, batch=100)
 assert r.removed_per_round.tolist() == orem.tolist() and np.array_equal(r.keep_mask, oact.astype(bool))
 assert np.array_equal(r.s_per_round.view(np.uint32), os_.view(np.uint32))
 dist.barrier()
 if rank == 0:
-    print(f"dist_check ok: world={world}, votes / s(x) / IBP bit-exact vs the single-rank CPU oracle")
+    print(f"dist_check ok: world={world}, votes / s(x) / IBP bit-exact vs the single-rank CPU oracle (in-library NCCL and host-side exchange)")
 dist.destroy_process_group()
