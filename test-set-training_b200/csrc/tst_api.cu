@@ -108,8 +108,6 @@ struct tst_handle {
     void* comm = nullptr;  // ncclComm_t
     uint32_t* h_pinned = nullptr;  // 16 words
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
-    cudaStream_t s_mid = nullptr, s_small = nullptr;  // side streams: warp-per-node and warp-per-subtree kernels overlap the CTA kernel
-    bool overlap = false;  // TST_OVERLAP=1: measured on B200, the tiers each fill the SMs, co-scheduling gains nothing
     tst_stats stats;
     bool attrs_set = false;
 };
@@ -161,9 +159,6 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->ev2));
     CK(cudaEventCreate(&h->evm0)); CK(cudaEventCreate(&h->evm1)); CK(cudaEventCreate(&h->evs0)); CK(cudaEventCreate(&h->evs1));
-    CK(cudaStreamCreateWithFlags(&h->s_mid, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->s_small, cudaStreamNonBlocking));
-    if (const char* ev = getenv("TST_OVERLAP")) h->overlap = atoi(ev) != 0;
     if (nccl_unique_id && world > 1) {
         if (load_nccl()) { delete h; return fail(TST_ERR_UNSUPPORTED, "tst_create: libnccl.so.2 not found"); }
         tst_nccl_id id;
@@ -189,8 +184,6 @@ extern "C" int tst_destroy(tst_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1}) if (e) cudaEventDestroy(e);
-    if (h->s_mid) cudaStreamDestroy(h->s_mid);
-    if (h->s_small) cudaStreamDestroy(h->s_small);
     delete h;
     return TST_OK;
 }
@@ -353,8 +346,6 @@ static void set_l2_window(tst_handle* h, cudaStream_t st, bool on) {
         attr.accessPolicyWindow.num_bytes = 0;
     }
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
-    if (h->s_mid) cudaStreamSetAttribute(h->s_mid, cudaStreamAttributeAccessPolicyWindow, &attr);
-    if (h->s_small) cudaStreamSetAttribute(h->s_small, cudaStreamAttributeAccessPolicyWindow, &attr);
     cudaGetLastError();
 }
 struct L2Window {  // RAII: every return path of tst_fit_oof clears the window
@@ -527,8 +518,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         CK(cudaMemsetAsync(h->y_pad.p, 0, (size_t)h->ld, st));
         CK(cudaMemcpyAsync(h->y_pad.p, y_dev, (size_t)n, cudaMemcpyDeviceToDevice, st));
     }
-    uint32_t* counters = h->counters.as<uint32_t>();  // [0],[1] big queue counts, [2] small count, [3],[4] mid queue counts
-    g.qsmall_count = counters + 2;
+    uint32_t* counters = h->counters.as<uint32_t>();  // [2p], [2p+1] big / mid queue counts of parity p, [4] small, [5] tiny, [6+r] tiny histogram
+    g.qsmall_count = counters + 4;
     g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
     g.tiny_max = (C <= 4 && d <= TINY_FY_MAX && B <= 65535) ? TINY_MAX : 0;  // packed 4-class thread-per-subtree tier
     if (const char* ev = getenv("TST_TINY_MAX")) g.tiny_max = std::min<uint32_t>(g.tiny_max, (uint32_t)atoi(ev));
@@ -576,7 +567,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 h->stats.kernel_launches += 2; h->stats.launches_root += 2;
             }
             g.qnext = h->qbig0.as<Task>(); g.qnext_count = counters + 0;
-            g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 3;
+            g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 1;
             k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb);
             CKL();
             h->stats.kernel_launches += 5;
@@ -586,88 +577,74 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         CK(cudaStreamSynchronize(st));
         { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_prep += ms; }
 
-        // ---- level-synchronous growth: CTA per node (> mid_max rows) and warp per node (33 .. mid_max rows)
+        // ---- level-synchronous growth: CTA per node (> mid_max rows) and warp per node (33 .. mid_max rows).
+        // One host round trip per level sizes the grids exactly.  Once a level is thin (the long tail of an unbalanced
+        // tree: a few nodes per level for dozens of levels) up to 4 levels are launched back to back with grids that are
+        // upper bounds (children <= 2 x parents) and the kernels read the real counts on the device.
         int cur = 0;
         uint64_t level_guard = 0;
-        uint32_t small_done = 0;
         bool small_started = false, tiny_timed = false;
-        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[3];
+        int blind_levels = 4;
+        if (const char* ev = getenv("TST_BLIND_LEVELS")) blind_levels = std::max(1, std::min(8, atoi(ev)));
+        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1];
         while (nbig > 0 || nmid > 0) {
-            Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
-            Task* qmcur = cur ? h->qmid1.as<Task>() : h->qmid0.as<Task>();
-            g.qnext = cur ? h->qbig0.as<Task>() : h->qbig1.as<Task>();
-            g.qnext_count = counters + (cur ^ 1);
-            g.qmid_next = cur ? h->qmid0.as<Task>() : h->qmid1.as<Task>();
-            g.qmid_next_count = counters + 3 + (cur ^ 1);
-            CK(cudaMemsetAsync(g.qnext_count, 0, 4, st));
-            CK(cudaMemsetAsync(g.qmid_next_count, 0, 4, st));
-            CK(cudaEventRecord(h->ev0, st));
-            const bool side = h->overlap && nmid > 0;
-            cudaStream_t sm = side ? h->s_mid : st;
-            if (side) {  // the two kernels of a level are independent: run them side by side
-                CK(cudaStreamWaitEvent(h->s_mid, h->ev0, 0));
-                CK(cudaEventRecord(h->evm0, h->s_mid));
+            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid <= 2048;
+            const int J = thin ? blind_levels : 1;
+            uint64_t ub_big = nbig, ub_mid = nmid;
+            for (int j = 0; j < J; ++j) {
+                Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
+                Task* qmcur = cur ? h->qmid1.as<Task>() : h->qmid0.as<Task>();
+                g.qnext = cur ? h->qbig0.as<Task>() : h->qbig1.as<Task>();
+                g.qnext_count = counters + 2 * (cur ^ 1);
+                g.qmid_next = cur ? h->qmid0.as<Task>() : h->qmid1.as<Task>();
+                g.qmid_next_count = counters + 2 * (cur ^ 1) + 1;
+                CK(cudaMemsetAsync(g.qnext_count, 0, 8, st));  // both counters of the next level
+                const uint32_t gb = (uint32_t)std::min<uint64_t>(ub_big, g.qbig_cap), gm = (uint32_t)std::min<uint64_t>(ub_mid, g.qbig_cap);
+                const uint32_t* cb = j ? counters + 2 * cur : nullptr;  // j == 0: counts are exact, no device read needed
+                const uint32_t* cm = j ? counters + 2 * cur + 1 : nullptr;
+                if (!thin) CK(cudaEventRecord(h->ev0, st));
+                if (gb) {
+                    k_grow_big<BIG_THREADS><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
+                    CKL();
+                    h->stats.kernel_launches++; h->stats.launches_grow_big++;
+                }
+                if (!thin) CK(cudaEventRecord(h->ev1, st));
+                if (gm) {
+                    if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
+                    else k_grow_mid<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
+                    CKL();
+                    h->stats.kernel_launches++; h->stats.launches_grow_mid++;
+                }
+                if (!thin) CK(cudaEventRecord(h->ev2, st));
+                h->stats.levels++;
+                cur ^= 1;
+                const uint64_t nb2 = 2 * ub_big, nm2 = 2 * (ub_big + ub_mid);
+                ub_big = nb2; ub_mid = nm2;
+                if (++level_guard > n_cap + 8) return fail(TST_ERR_STATE, "tree growth did not terminate");
             }
-            if (nbig) {
-                k_grow_big<BIG_THREADS><<<nbig, BIG_THREADS, big_smem, st>>>(g, qcur, nbig);
-                CKL();
-                h->stats.kernel_launches++; h->stats.launches_grow_big++;
-            }
-            CK(cudaEventRecord(h->ev1, st));
-            if (nmid) {
-                if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(nmid + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, sm>>>(g, qmcur, nmid);
-                else k_grow_mid<MID_WARPS, MID_R><<<(nmid + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, sm>>>(g, qmcur, nmid);
-                CKL();
-                h->stats.kernel_launches++; h->stats.launches_grow_mid++;
-            }
-            if (side) {
-                CK(cudaEventRecord(h->evm1, h->s_mid));
-                CK(cudaStreamWaitEvent(st, h->evm1, 0));
-            }
-            CK(cudaEventRecord(h->ev2, st));
             CK(cudaMemcpyAsync(h->h_pinned, counters, 32, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_big += ms;
-              if (side) cudaEventElapsedTime(&ms, h->evm0, h->evm1); else cudaEventElapsedTime(&ms, h->ev1, h->ev2);
-              h->stats.ms_grow_mid += ms; }
-            h->stats.levels++;
-            cur ^= 1;
-            nbig = h->h_pinned[cur];
-            nmid = h->h_pinned[3 + cur];
-            if (++level_guard > n_cap + 2) return fail(TST_ERR_STATE, "tree growth did not terminate");
-            if (nbig > g.qbig_cap || nmid > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
-            // subtrees with <= 32 rows that this level produced start right away on their own stream
-            if (h->overlap && (nbig > 0 || nmid > 0)) {
-                const uint32_t now = std::min<uint32_t>(h->h_pinned[2], g.qsmall_cap);
-                if (now > small_done + 4096u) {
-                    const uint32_t cnt = now - small_done;
-                    uint32_t blocks = std::min<uint32_t>((cnt + SMALL_WARPS - 1) / SMALL_WARPS, (uint32_t)h->sm_count * 64u);
-                    if (!small_started) { CK(cudaEventRecord(h->evs0, h->s_small)); small_started = true; }
-                    if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, h->s_small>>>(g, g.qsmall + small_done, cnt);
-                    else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, h->s_small>>>(g, g.qsmall + small_done, cnt);
-                    CKL();
-                    h->stats.kernel_launches++; h->stats.launches_grow_small++;
-                    small_done = now;
-                }
+            if (!thin) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_big += ms;
+                cudaEventElapsedTime(&ms, h->ev1, h->ev2); h->stats.ms_grow_mid += ms;
             }
+            nbig = h->h_pinned[2 * cur];
+            nmid = h->h_pinned[2 * cur + 1];
+            if (nbig > g.qbig_cap || nmid > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
-        // ---- remaining subtrees with <= 32 rows: one warp each
-        const uint32_t nsmall = h->h_pinned[2];
+        // ---- subtrees with 7..32 rows: one warp each
+        const uint32_t nsmall = h->h_pinned[4];
         if (nsmall > g.qsmall_cap) return fail(TST_ERR_OVERFLOW, "small-node queue overflowed");
-        if (nsmall > small_done) {
-            const uint32_t cnt = nsmall - small_done;
-            uint32_t blocks = std::min<uint32_t>((cnt + SMALL_WARPS - 1) / SMALL_WARPS, (uint32_t)h->sm_count * 64u);
-            cudaStream_t ss = h->overlap ? h->s_small : st;
-            if (!small_started) { CK(cudaEventRecord(h->evs0, ss)); small_started = true; }
-            if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, ss>>>(g, g.qsmall + small_done, cnt);
-            else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, ss>>>(g, g.qsmall + small_done, cnt);
+        if (nsmall) {
+            uint32_t blocks = std::min<uint32_t>((nsmall + SMALL_WARPS - 1) / SMALL_WARPS, (uint32_t)h->sm_count * 64u);
+            CK(cudaEventRecord(h->evs0, st));
+            small_started = true;
+            if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
             CKL();
+            CK(cudaEventRecord(h->evs1, st));
             h->stats.kernel_launches++; h->stats.launches_grow_small++;
-        }
-        if (small_started) {
-            cudaStream_t ss = h->overlap ? h->s_small : st;
-            CK(cudaEventRecord(h->evs1, ss));
-            if (h->overlap) CK(cudaStreamWaitEvent(st, h->evs1, 0));
         }
         // ---- subtrees with <= TINY_MAX rows: one thread each (tasks come from every other tier)
         if (g.tiny_max) {

@@ -184,7 +184,7 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
 
 // ---------------------------------------------------------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     constexpr int NW = THREADS / 32;
     extern __shared__ uint32_t s_hist[];  // [MB][FS] histogram, then (row tile) [THREADS][dstride/4 + 1]
     __shared__ uint16_t s_perm[TST_MAX_FEATURES];
@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     __shared__ __align__(8) uint64_t s_bar[NW][ENT_STAGES];
 #endif
 
+    // thin levels are launched without a host round trip: the grid is an upper bound, the real count is on the device
+    if (ntasks_dev) ntasks = min(ntasks, *ntasks_dev);
     if (blockIdx.x >= ntasks) return;
     const Task t = tasks[blockIdx.x];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;

@@ -20,7 +20,7 @@ __device__ __forceinline__ void warp_argmax_db(double& gn, uint32_t& key) {
 }
 
 template <int WARPS, int R>
-__global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     extern __shared__ uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int C = g.C, d = g.d, m = g.m;
@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
     const uint8_t* __restrict__ bins = g.bins_rm;
     const uint32_t dstride = g.dstride;
     const uint32_t ti = blockIdx.x * WARPS + warp;
+    if (ntasks_dev) ntasks = min(ntasks, *ntasks_dev);
     if (ti >= ntasks) return;
 
     const Task t = tasks[ti];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 #define MID_MINB 3
 #endif
 template <int WARPS, int R>
-__global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     static_assert(32 * R * 255 < 65536, "packed 16-bit class counts need <= 256 rows per node");
     extern __shared__ uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
     const uint8_t* __restrict__ bins = g.bins_rm;
     const uint32_t dstride = g.dstride;
     const uint32_t ti = blockIdx.x * WARPS + warp;
+    if (ntasks_dev) ntasks = min(ntasks, *ntasks_dev);
     if (ti >= ntasks) return;
 
     const Task t = tasks[ti];
