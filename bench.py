@@ -9,7 +9,8 @@
 A "step" = one pass of the hot path: this rank's 10 folds x TREES_PER_FOLD trees (Philox bootstrap ->
 histogram / Gini split / partition growth -> OOF inference), the vote all-gather, and s(x).  Step s
 builds trees [s*T, (s+1)*T) of the 10-fold x 1000-tree job, so K steps are K disjoint slices of that
-job.  Weak scaling: every rank builds TREES_PER_FOLD trees per fold per step.
+job.  Weak scaling: every rank builds TREES_PER_FOLD (default 64: 640 trees in flight, ~36 GB of the 180 GB
+HBM; the per-level host round trips are then < 5 % of a step even on a slow host) trees per fold per step.
 
 value  : trees/s with the binned table resident in HBM (CUDA events, barrier both sides, max over ranks)
 e2e    : trees/s through tst.run_tst on HOST arrays -- pinned X/y H2D, bin-edge selection, binning, folds,
@@ -165,7 +166,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--trees-per-fold", type=int, default=int(os.environ.get("TST_BENCH_TREES_PER_FOLD", "32")))
+    ap.add_argument("--trees-per-fold", type=int, default=int(os.environ.get("TST_BENCH_TREES_PER_FOLD", "64")))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
