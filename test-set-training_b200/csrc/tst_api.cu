@@ -122,7 +122,10 @@ static const int SMALL_WARPS = 4;
 #endif
 static const int TINY_MAX = TINY_MAX_ROWS;   // thread-per-subtree tier: rows held in registers by one thread
 static const int MID_WARPS = 8;
-static const int MID_R = 8;  // warp-per-node tier holds up to 32 * MID_R rows in registers
+#ifndef MID_R_N
+#define MID_R_N 8
+#endif
+static const int MID_R = MID_R_N;  // warp-per-node tier holds up to 32 * MID_R rows in registers
 static const size_t BIG_SMEM_BUDGET = 64 * 1024;
 
 extern "C" int tst_abi_version(void) { return TST_ABI_VERSION; }
@@ -528,6 +531,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                                              : (uint32_t)g.FS + 2u * (uint32_t)C + (uint32_t)((d + 1) / 2);
     const size_t mid_smem = (size_t)MID_WARPS * mid_per_warp * 4;
     g.mid_max = mid_smem <= 200 * 1024 ? 32u * MID_R : SMALL_MAX;
+    g.mid_packed = mid_packed ? 1u : 0u;
     if (const char* ev = getenv("TST_MID_MAX")) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)atoi(ev)));
 
     for (size_t b0 = 0; b0 < total_trees; b0 += B) {

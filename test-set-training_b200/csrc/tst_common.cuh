@@ -110,6 +110,7 @@ struct GrowCtx {
     Task* qmid_next;  // warp-per-node queue for the next level (SMALL_MAX < rows <= mid_max)
     uint32_t* qmid_next_count;
     uint32_t mid_max; // == SMALL_MAX disables the mid tier
+    uint32_t mid_packed; // k_grow_mid4: 16-bit packed class counts, nodes must weigh <= 65535
     Task* qsmall;
     uint32_t* qsmall_count;
     uint32_t qsmall_cap;

@@ -65,7 +65,8 @@ __device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint
             const uint32_t cr = ce - cb;
             if (cr <= g.tiny_max) tiny_push(g, t.tree, cb, cr, t.depth + 1u, cslot);
             else if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
-            else if (cr > SMALL_MAX) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
+            else if (cr > SMALL_MAX && (Nc <= 65535u || !g.mid_packed)) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
+            else if (cr > SMALL_MAX) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);  // too heavy for 16-bit packed counts
             else queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
         }
     }

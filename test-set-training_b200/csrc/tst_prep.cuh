@@ -319,7 +319,8 @@ __global__ void k_init_roots(GrowCtx g, uint32_t n_trees) {
     if (g.rsplit && td.n_inbag > g.mid_max) k.pad0 = 1;  // pre-split by k_root_hist / k_root_split
     if (td.n_inbag <= g.tiny_max) tiny_push(g, t, 0u, td.n_inbag, 0u, 0u);
     else if (td.n_inbag > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, k);
-    else if (td.n_inbag > SMALL_MAX) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, k);
+    else if (td.n_inbag > SMALL_MAX && (td.n_train <= 65535u || !g.mid_packed)) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, k);
+    else if (td.n_inbag > SMALL_MAX) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, k);
     else queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, k);
 }
 
