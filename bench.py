@@ -104,9 +104,10 @@ def dram_traffic_per_launch(kernel):
     """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_final_traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")) as f:
-            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+            e = json.load(f).get(kernel, {})
+            return e.get("dram_bytes_per_launch"), e.get("captured")
     except Exception:
-        return None
+        return None, None
 
 
 # --------------------------------------------------------------------------------------------- reference arm
@@ -257,8 +258,9 @@ def main():
                            algorithmic_bytes_per_launch=ab / max(1, nl), avg_launch_ms=tms / max(1, nl))
     dom = max(tiers, key=lambda k: tiers[k]["ms"])
     T_ = tiers[dom]
+    traffic, traffic_of = dram_traffic_per_launch(dom)
     roofline = dict(bound="hbm", kernel=dom, achieved=T_["achieved"], peak=peak, unit="GB/s", frac=T_["frac"],
-                    traffic=dram_traffic_per_launch(dom), peak_source=peak_src,
+                    traffic=traffic, traffic_launches=traffic_of, peak_source=peak_src,
                     algorithmic_bytes_per_launch=T_["algorithmic_bytes_per_launch"], avg_launch_ms=T_["avg_launch_ms"],
                     launches=T_["launches"], kernel_share_of_step=T_["share_of_step"], tiers=tiers,
                     whole_tree=dict(algorithmic_bytes_per_tree=((15 + m) * (st["row_visits_big"] + st["row_visits_mid"] + st["row_visits_small"])
