@@ -504,7 +504,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const size_t big_smem = (size_t)g.MB * g.FS * 4 + big_tile_bytes;
     if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
     const bool small_packed = C <= 4;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
-    const uint32_t small_per_warp = small_packed ? 32u + 96u + (uint32_t)((d + 1) / 2)
+    const uint32_t small_per_warp = small_packed ? ((64u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
     // dense root histograms (tst_root.cuh): big tables only; needs m <= 8 and the histogram + 2 TMA stages in shared memory
@@ -527,7 +527,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.tiny_max = (C <= 4 && d <= TINY_FY_MAX && B <= 65535) ? TINY_MAX : 0;  // packed 4-class thread-per-subtree tier
     if (const char* ev = getenv("TST_TINY_MAX")) g.tiny_max = std::min<uint32_t>(g.tiny_max, (uint32_t)atoi(ev));
     const bool mid_packed = C <= 4;  // packed 16-bit class counts (k_grow_mid4)
-    const uint32_t mid_per_warp = mid_packed ? MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2)
+    const uint32_t mid_per_warp = mid_packed ? ((MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                              : (uint32_t)g.FS + 2u * (uint32_t)C + (uint32_t)((d + 1) / 2);
     const size_t mid_smem = (size_t)MID_WARPS * mid_per_warp * 4;
     g.mid_max = mid_smem <= 200 * 1024 ? 32u * MID_R : SMALL_MAX;

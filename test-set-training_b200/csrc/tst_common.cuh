@@ -40,6 +40,39 @@ __host__ __device__ __forceinline__ uint32_t pick4(const uint4& v, uint32_t i) {
 
 __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 
+// The first m positions of a node's partial Fisher-Yates draw, by one warp: lane b evaluates Philox block b
+// (4 positions per block) so the blocks run side by side, lane 0 walks the swaps in order.  s_perm[0..d) must
+// hold the identity on entry.  Same draw as the serial loops elsewhere (oracle/hist_rf.c: draw_features).
+__device__ __forceinline__ void warp_draw_primary(uint16_t* s_perm, int d, int m, uint32_t begin, uint32_t depth, uint32_t gid,
+                                                  uint32_t k0, uint32_t k1, uint32_t lane) {
+    for (int base = 0; base < m; base += 128) {
+        const int lim = min(m, base + 128), nblk = (lim - base + 3) >> 2;
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        if ((int)lane < nblk) rnd = philox4x32_10(begin, depth, gid, TST_PURPOSE_FEAT | ((uint32_t)((base >> 2) + (int)lane) << 8), k0, k1);
+        for (int i = base; i < lim; ++i) {
+            const uint32_t v = __shfl_sync(0xffffffffu, pick4(rnd, (uint32_t)i & 3u), (i - base) >> 2);
+            if (lane == 0) {
+                const int j = i + (int)mulhi32(v, (uint32_t)(d - i));
+                const uint16_t fj = s_perm[j];
+                s_perm[j] = s_perm[i];
+                s_perm[i] = fj;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// Warp argmax of (gain desc, key asc) with three REDUX instead of a 64-bit shuffle butterfly.  Valid gains are
+// positive doubles (>= 2), whose bit patterns order like unsigned integers; key == 0xFFFFFFFF marks "no candidate".
+__device__ __forceinline__ void warp_argmax_redux(double& gn, uint32_t& key) {
+    const unsigned long long bits = key != 0xFFFFFFFFu ? (unsigned long long)__double_as_longlong(gn) : 0ull;
+    const uint32_t hi = (uint32_t)(bits >> 32), mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t lo = hi == mh ? (uint32_t)bits : 0u, ml = __reduce_max_sync(0xffffffffu, lo);
+    const uint32_t k = (hi == mh && lo == ml) ? key : 0xFFFFFFFFu;
+    key = __reduce_min_sync(0xffffffffu, k);
+    gn = key != 0xFFFFFFFFu ? __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml)) : -1.0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // One in-bag row of one tree: x = row id, y = bootstrap multiplicity | class << 8.  Real entries have
 // multiplicity >= 1, so y == 0 marks padding.  64-bit entries keep the class next to the row id
@@ -143,6 +176,17 @@ __device__ __forceinline__ double gini_gain(unsigned long long SL, uint32_t NL, 
     // two IEEE divisions and one add -- no multiply, so nothing can be contracted into an FMA.
     return __dadd_rn(__ddiv_rn(__ull2double_rn(SL), __uint2double_rn(NL)),
                      __ddiv_rn(__ull2double_rn(SR), __uint2double_rn(NR)));
+}
+
+// fp32 ESTIMATE of the same quantity, used only to decide which candidates get the exact fp64 evaluation:
+// (SL*NR + SR*NL) / (NL*NR) with one MUFU reciprocal.  All terms are positive, so the relative error is
+// bounded by the sum of the roundings: 2 conversions + 3 products/fma (2^-24 each) + __fdividef (2 ulp)
+// < 2^-21.  A candidate whose estimate is below TST_EST_MARGIN x (the largest estimate seen) cannot have
+// the largest exact gain (margin 2^-18 = 8x the bound), so skipping it never changes the argmax or its
+// tie-break; the winner itself is always evaluated exactly.  Results stay bit-identical to oracle/hist_rf.c.
+#define TST_EST_MARGIN 0.99999619f  // 1 - 2^-18
+__device__ __forceinline__ float gain_estimate(float SL, float NL, float SR, float NR) {
+    return __fdividef(fmaf(SL, NR, SR * NL), NL * NR);
 }
 
 // ---------------------------------------------------------------------------------------------

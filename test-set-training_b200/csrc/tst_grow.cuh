@@ -115,16 +115,27 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
         }
     }
     if (N_out && lane == 0) *N_out = N;
+    // fp32 estimates first; only the candidates within TST_EST_MARGIN of the warp's best estimate get the fp64 gain
+    float ge[8], lmax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        ge[i] = -1.0f;
+        if ((occ >> i) & 1u) {  // an empty bin repeats the previous partition and would lose the tie anyway
+            uint32_t NL = nL[i], NR = N - NL;
+            if (NL >= msl && NR >= msl) {
+                ge[i] = gain_estimate(__ull2float_rn(sL[i]), __uint2float_rn(NL), __ull2float_rn(sR[i]), __uint2float_rn(NR));
+                lmax = fmaxf(lmax, ge[i]);
+            }
+        }
+    }
+    const float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lmax))) * TST_EST_MARGIN;
     double bg = -1.0;
     uint32_t bb = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        if ((occ >> i) & 1u) {  // an empty bin repeats the previous partition and would lose the tie anyway
-            uint32_t NL = nL[i], NR = N - NL;
-            if (NL >= msl && NR >= msl) {
-                double gn = gini_gain(sL[i], NL, sR[i], NR);
-                if (gn > bg) { bg = gn; bb = lane * 8u + i; }
-            }
+        if (ge[i] >= thr) {
+            double gn = gini_gain(sL[i], nL[i], sR[i], N - nL[i]);
+            if (gn > bg) { bg = gn; bb = lane * 8u + i; }
         }
     }
 #pragma unroll

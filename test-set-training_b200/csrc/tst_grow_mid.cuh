@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 // shuffle chain for all classes), and only the OCCUPIED bins are turned into candidates, compacted
 // into a shared list and spread evenly over the lanes, so the fp64 gain is evaluated ~rows/32 times
 // per lane instead of 8.  The next feature's bins are prefetched while the current one is scanned.
-#define MID4_HIST 544u   // 32 lanes x (8 bins x 2 words + 1 pad)
-#define MID4_CAND 768u   // 256 candidates x (P0, P1, bin)
+#define MID4_HIST 640u   // 32 lanes x (8 bins x 2 words + 4 pad): 80-byte lane segments, conflict-free 128-bit access
+#define MID4_CAND 1024u  // 256 candidates x (P0 | P1 | bin | gain estimate), structure of arrays
 
 #ifndef MID_MINB
 #define MID_MINB 3
@@ -179,10 +179,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 template <int WARPS, int R>
 __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     static_assert(32 * R * 255 < 65536, "packed 16-bit class counts need <= 256 rows per node");
-    extern __shared__ uint32_t s_mem[];
+    extern __shared__ __align__(16) uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int C = g.C, d = g.d, m = g.m;
-    const uint32_t per_warp = MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2);
+    const uint32_t per_warp = (MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2) + 3u) & ~3u;  // 16-byte aligned warp slices
     uint32_t* s_hist = s_mem + warp * per_warp;
     uint32_t* s_cand = s_hist + MID4_HIST;
     uint32_t* s_tot = s_cand + MID4_CAND;  // [4] totals, [4] left counts of the best split (for emit_split)
@@ -211,17 +211,7 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
     for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
     __syncwarp();
     uint4 rnd = make_uint4(0, 0, 0, 0);
-    if (lane == 0) {  // the first m positions of the node's Fisher-Yates draw
-        for (int i = 0; i < m; ++i) {
-            if ((i & 3) == 0)
-                rnd = philox4x32_10(t.begin, t.depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);
-            int j = i + (int)mulhi32(pick4(rnd, i & 3), (uint32_t)(d - i));
-            uint16_t fj = s_perm[j];
-            s_perm[j] = s_perm[i];
-            s_perm[i] = fj;
-        }
-    }
-    __syncwarp();
+    warp_draw_primary(s_perm, d, m, t.begin, t.depth, td.gid, g.k0, g.k1, lane);  // the first m positions of the node's draw
 
     bool found = false, stop = false;
     double best_gain = -1.0;
@@ -262,18 +252,22 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
             for (int k = 0; k < R; ++k) b[k] = e[k].y ? (uint32_t)bins[(uint64_t)e[k].x * dstride + f] : 0u;
         }
         // packed class histogram of this feature
-        for (uint32_t w = lane; w < MID4_HIST; w += 32) s_hist[w] = 0;
+        {   // the lane's own 8 bins are zeroed here and read back below with 128-bit accesses
+            uint4* hz = (uint4*)(s_hist + lane * 20u);
+            hz[0] = hz[1] = hz[2] = hz[3] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < R; ++k)
-            if (e[k].y) atomicAdd(&s_hist[(b[k] >> 3) * 17u + (b[k] & 7u) * 2u + (ent_cls(e[k]) >> 1)], ent_w(e[k]) << (16u * (ent_cls(e[k]) & 1u)));
+            if (e[k].y) atomicAdd(&s_hist[(b[k] >> 3) * 20u + (b[k] & 7u) * 2u + (ent_cls(e[k]) >> 1)], ent_w(e[k]) << (16u * (ent_cls(e[k]) & 1u)));
         __syncwarp();
         // packed prefix scan over bins
-        const uint32_t* hl = s_hist + lane * 17u;
+        const uint4* hl = (const uint4*)(s_hist + lane * 20u);
         uint32_t p0[8], p1[8], run0 = 0, run1 = 0, occ = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            uint32_t h0 = hl[2 * q], h1 = hl[2 * q + 1];
+            const uint4 hq = hl[q >> 1];  // two bins per 128-bit load (the compiler keeps one load per pair)
+            const uint32_t h0 = (q & 1) ? hq.z : hq.x, h1 = (q & 1) ? hq.w : hq.y;
             occ |= ((h0 | h1) ? 1u : 0u) << q;
             run0 += h0; run1 += h1;
             p0[q] = run0; p1[q] = run1;
@@ -296,37 +290,55 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
             const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
             if (stop_rule(g, N, t.depth, pure)) { stop = true; break; }
         }
-        // candidate list = occupied bins in ascending order: (left counts packed, bin)
+        // candidate list = occupied bins in ascending order: left counts packed | bin | fp32 gain estimate (SoA)
         {
             uint32_t j = cincl - cnt;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
                 if ((occ >> q) & 1u) {
-                    s_cand[j * 3u] = e0 + p0[q];
-                    s_cand[j * 3u + 1u] = e1 + p1[q];
-                    s_cand[j * 3u + 2u] = lane * 8u + q;
+                    s_cand[j] = e0 + p0[q];
+                    s_cand[256u + j] = e1 + p1[q];
+                    s_cand[512u + j] = lane * 8u + q;
                     ++j;
                 }
         }
         __syncwarp();
         const uint32_t t0 = T0 & 0xFFFFu, t1 = T0 >> 16, t2 = T1 & 0xFFFFu, t3 = T1 >> 16;
+        // pass 1: fp32 estimates (a node here weighs < 2^16, so the sums of squares fit 32 bits)
+        float lmax = 0.0f;
+        for (uint32_t j = lane; j < n_cand; j += 32) {
+            const uint32_t P0 = s_cand[j], P1 = s_cand[256u + j];
+            const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
+            const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+            float ge = -1.0f;
+            if (NL >= g.msl && NR >= g.msl) {
+                const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
+                const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+                ge = gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR));
+                lmax = fmaxf(lmax, ge);
+            }
+            s_cand[768u + j] = __float_as_uint(ge);
+        }
+        float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lmax)));  // positive floats order like integers
+        if (i < m && found) thr = fmaxf(thr, __double2float_rd(best_gain));  // a feature that cannot reach the node's best is skipped
+        thr *= TST_EST_MARGIN;
+        // pass 2: exact fp64 gain of the contenders only
         double bg = -1.0;
         uint32_t bb = 0xFFFFFFFFu, bP0 = 0, bP1 = 0;
         for (uint32_t j = lane; j < n_cand; j += 32) {
-            const uint32_t P0 = s_cand[j * 3u], P1 = s_cand[j * 3u + 1u], bin = s_cand[j * 3u + 2u];
-            const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
-            const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
-            if (NL >= g.msl && NR >= g.msl) {
+            if (__uint_as_float(s_cand[768u + j]) >= thr) {
+                const uint32_t P0 = s_cand[j], P1 = s_cand[256u + j], bin = s_cand[512u + j];
+                const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
+                const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
                 const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
-                unsigned long long SL = (unsigned long long)L0 * L0 + (unsigned long long)L1 * L1 + (unsigned long long)L2 * L2 + (unsigned long long)L3 * L3;
-                unsigned long long SR = (unsigned long long)R0 * R0 + (unsigned long long)R1 * R1 + (unsigned long long)R2 * R2 + (unsigned long long)R3 * R3;
-                double gn = gini_gain(SL, NL, SR, NR);
+                const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+                const double gn = gini_gain(SL, NL, SR, NR);
                 if (gn > bg) { bg = gn; bb = bin; bP0 = P0; bP1 = P1; }  // ascending bins: strict > keeps the lowest
             }
         }
         double wg = bg;
         uint32_t wb = bb;
-        warp_argmax_db(wg, wb);
+        warp_argmax_redux(wg, wb);
         if (wb != 0xFFFFFFFFu) {
             const uint32_t key = (f << 8) | wb;
             bool newbest;

@@ -34,12 +34,13 @@ __device__ __forceinline__ void warp_argmax(double& gn, uint32_t& key) {
 #endif
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
-    extern __shared__ uint32_t s_mem[];
+    extern __shared__ __align__(16) uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int C = g.C, d = g.d, m = g.m;
-    // per-warp shared layout (words): src[32] | stack[32][3] | perm[(d+1)/2]
-    const uint32_t per_warp = 32u + 96u + (uint32_t)((d + 1) / 2);
-    uint32_t* s_src = s_mem + warp * per_warp;
+    // per-warp shared layout (words): P[32] u64 | src[32] | stack[32][3] | perm[(d+1)/2], rounded to 16 bytes
+    const uint32_t per_warp = (64u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u;
+    unsigned long long* s_P = (unsigned long long*)(s_mem + warp * per_warp);
+    uint32_t* s_src = s_mem + warp * per_warp + 64;
     uint32_t* s_stack = s_src + 32;
     uint16_t* s_perm = (uint16_t*)(s_stack + 96);
     const uint8_t* __restrict__ bins = g.bins_rm;
@@ -99,53 +100,76 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                 const uint8_t* __restrict__ rowp = bins + (uint64_t)e_g.x * dstride;
                 for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
                 __syncwarp();
+                warp_draw_primary(s_perm, d, m, abs_begin, depth, td.gid, g.k0, g.k1, lane);
+                // bin <= b  <=>  high word of P <= (b << 20) | 0xFFFFF (bits 32..51 hold class counts)
+                uint4 rnd = make_uint4(0, 0, 0, 0);
                 for (int pos0 = 0; pos0 < d;) {
                     if (pos0 >= m && found) break;
                     const int limit = pos0 < m ? m : d;
                     const int nfc = min((int)nf, limit - pos0);
-                    if (lane == 0) {  // extend the node's Fisher-Yates draw to positions [pos0, pos0 + nfc)
-                        uint4 rnd = make_uint4(0, 0, 0, 0);
-                        for (int i = pos0; i < pos0 + nfc; ++i) {
-                            if (i == pos0 || (i & 3) == 0)
-                                rnd = philox4x32_10(abs_begin, depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);
-                            int j = i + (int)mulhi32(pick4(rnd, i & 3), (uint32_t)(d - i));
-                            uint16_t fj = s_perm[j];
-                            s_perm[j] = s_perm[i];
-                            s_perm[i] = fj;
+                    if (pos0 >= m) {  // fallback: extend the draw lazily (rare)
+                        if (lane == 0) {
+                            for (int i = pos0; i < pos0 + nfc; ++i) {
+                                if (i == pos0 || (i & 3) == 0)
+                                    rnd = philox4x32_10(abs_begin, depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);
+                                int j = i + (int)mulhi32(pick4(rnd, i & 3), (uint32_t)(d - i));
+                                uint16_t fj = s_perm[j];
+                                s_perm[j] = s_perm[i];
+                                s_perm[i] = fj;
+                            }
+                            if (pos0 == m) n_fb++;
                         }
-                        if (pos0 == m) n_fb++;
+                        __syncwarp();
                     }
-                    __syncwarp();
                     const bool pvalid = (int)gi < nfc;
                     const uint32_t pos = (uint32_t)pos0 + (pvalid ? gi : 0u);
                     const uint32_t f = s_perm[pos];
                     const bool lv = gvalid && pvalid;
                     const uint32_t b = lv ? (uint32_t)rowp[f] : 0u;
                     const unsigned long long P = cw_g | ((unsigned long long)b << 52);
+                    // weights left of my threshold: every lane of the group reads the group's rows from shared memory
+                    // (two rows per 128-bit broadcast load); lanes past the node's rows hold P = 0 and add nothing
+                    __syncwarp();
+                    s_P[lane] = P;
+                    __syncwarp();
+                    const uint32_t cmp = (b << 20) | 0xFFFFFu;
                     unsigned long long acc = 0;
-                    for (uint32_t kk = 0; kk < rr; ++kk) {
-                        unsigned long long Pk = __shfl_sync(0xffffffffu, P, gbase + kk);
-                        if ((uint32_t)(Pk >> 52) <= b) acc += Pk;
+                    const ulonglong2* gp = (const ulonglong2*)(s_P + gbase);
+                    for (uint32_t kk = 0; kk < rr; kk += 4) {  // G >= 4 is a multiple of 4: never reads past the group
+                        const ulonglong2 a = gp[kk >> 1], c = gp[(kk >> 1) + 1];
+                        if ((uint32_t)(a.x >> 32) <= cmp) acc += a.x;
+                        if ((uint32_t)(a.y >> 32) <= cmp) acc += a.y;
+                        if ((uint32_t)(c.x >> 32) <= cmp) acc += c.x;
+                        if ((uint32_t)(c.y >> 32) <= cmp) acc += c.y;
                     }
                     const uint32_t L0 = F13(acc, 0), L1 = F13(acc, 1), L2 = F13(acc, 2), L3 = F13(acc, 3);
                     const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
                     const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
                     const bool ok = lv && NL >= g.msl && NR >= g.msl;
+                    // a node here weighs < 2^13: the sums of squares fit 32 bits
+                    const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
                     double gn = -1.0;
                     uint32_t key = 0xFFFFFFFFu;
-                    if (ok) {
-                        unsigned long long SL = (unsigned long long)L0 * L0 + (unsigned long long)L1 * L1 + (unsigned long long)L2 * L2 + (unsigned long long)L3 * L3;
-                        unsigned long long SR = (unsigned long long)R0 * R0 + (unsigned long long)R1 * R1 + (unsigned long long)R2 * R2 + (unsigned long long)R3 * R3;
-                        gn = gini_gain(SL, NL, SR, NR);
-                        key = (f << 8) | b;
-                    }
                     if (pos0 < m) {
-                        warp_argmax(gn, key);
+                        // fp32 estimate first; the exact fp64 gain only where it can still win (tst_common.cuh: gain_estimate)
+                        const float ge = ok ? gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR)) : 0.0f;
+                        float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ge)));
+                        if (found) thr = fmaxf(thr, __double2float_rd(best_gain));
+                        thr *= TST_EST_MARGIN;
+                        if (ok && ge >= thr) {
+                            gn = gini_gain(SL, NL, SR, NR);
+                            key = (f << 8) | b;
+                        }
+                        warp_argmax_redux(gn, key);
                         if (key != 0xFFFFFFFFu && (gn > best_gain || (gn == best_gain && key < best_key))) {
                             best_gain = gn; best_key = key; found = true;
                         }
                     } else {
                         // fallback: the first position in draw order that has any valid split
+                        if (ok) {
+                            gn = gini_gain(SL, NL, SR, NR);
+                            key = (f << 8) | b;
+                        }
                         uint32_t mp = ok ? pos : 0xFFFFFFFFu;
 #pragma unroll
                         for (int off = 16; off >= 1; off >>= 1) mp = min(mp, __shfl_xor_sync(0xffffffffu, mp, off));

@@ -27,6 +27,24 @@ print(sorted(seen)[0][:100] if seen else '')
 tot_s = sum(num(r['# Samples']) for _, r in rows) or 1
 tot_i = sum(num(r['Instructions Executed']) for _, r in rows) or 1
 print(f"total samples {tot_s:.0f}, warp instructions {tot_i:.3e} (all captured launches of all kernels in the report)")
+# one row per (file, line): the report repeats every line once per captured launch
+agg = {}
+for f, r in rows:
+    k = (f, r['Line No'])
+    if k not in agg:
+        agg[k] = dict(r); agg[k]['_n'] = 1
+        for kk, v in r.items():
+            if kk.startswith('stall_') or kk in ('# Samples', 'Instructions Executed', 'Avg. Threads Executed'): agg[k][kk] = num(v)
+    else:
+        a = agg[k]; a['_n'] += 1
+        for kk, v in r.items():
+            if kk.startswith('stall_') or kk in ('# Samples', 'Instructions Executed', 'Avg. Threads Executed'): a[kk] += num(v)
+rows = []
+for (f, ln), a in agg.items():
+    a['Avg. Threads Executed'] = f"{a['Avg. Threads Executed'] / a['_n']:.0f}"
+    for kk in list(a):
+        if kk.startswith('stall_') or kk in ('# Samples', 'Instructions Executed'): a[kk] = str(a[kk])
+    rows.append((f, a))
 rows.sort(key=lambda fr: -num(fr[1]['# Samples']))
 for f, r in rows[:top]:
     ns = max(1, num(r['# Samples']))
