@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "tst_common.cuh"
@@ -97,7 +98,7 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qmid0, qmid1, qsmall, qtiny, qtiny2, counters, dstats, infer_parts, ghist, rsplit, y_pad;
+        qmid0, qmid1, qsmall, qtiny, qtiny2, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
@@ -108,6 +109,8 @@ struct tst_handle {
     void* comm = nullptr;  // ncclComm_t
     uint32_t* h_pinned = nullptr;  // 16 words
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
+    cudaEvent_t ev_lvl[8][3] = {};  // per level of a group of blind levels: before big, between, after mid
+    size_t l2_carve_set = 0;
     tst_stats stats;
     bool attrs_set = false;
 };
@@ -162,6 +165,7 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->ev2));
     CK(cudaEventCreate(&h->evm0)); CK(cudaEventCreate(&h->evm1)); CK(cudaEventCreate(&h->evs0)); CK(cudaEventCreate(&h->evs1));
+    for (auto& lv : h->ev_lvl) for (auto& e : lv) CK(cudaEventCreate(&e));
     if (nccl_unique_id && world > 1) {
         if (load_nccl()) { delete h; return fail(TST_ERR_UNSUPPORTED, "tst_create: libnccl.so.2 not found"); }
         tst_nccl_id id;
@@ -178,7 +182,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk, &h->gather};
     for (DevBuf* b : bufs) b->release();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -187,6 +191,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1}) if (e) cudaEventDestroy(e);
+    for (auto& lv : h->ev_lvl) for (auto& e : lv) if (e) cudaEventDestroy(e);
     delete h;
     return TST_OK;
 }
@@ -339,7 +344,7 @@ static void set_l2_window(tst_handle* h, cudaStream_t st, bool on) {
     memset(&attr, 0, sizeof(attr));
     if (on) {
         const size_t carve = std::min(bytes, h->l2_persist_max);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        if (h->l2_carve_set != carve) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve); h->l2_carve_set = carve; }  // device-wide and slow: only when it changes
         attr.accessPolicyWindow.base_ptr = h->bins_rm.p;
         attr.accessPolicyWindow.num_bytes = std::min(bytes, h->l2_window_max);
         attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
@@ -387,6 +392,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     if ((uint64_t)n_groups * k * n_trees + gid_base > 0xFFFFFFFFull) return fail(TST_ERR_INVALID, "tst_fit_oof: tree id overflows 32 bits");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
+    const bool trace = getenv("TST_TRACE") != nullptr;  // host wall-clock phases of every batch on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+    const auto t_entry = now();
     int rc = set_kernel_attrs(h);
     if (rc) return rc;
 
@@ -442,12 +451,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint64_t leafc_stride = (n_cap / 2 + 1) * (uint64_t)C;
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / 8 + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
-    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 2 * n_cap * sizeof(Entry) + (4 * qbig_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + 3 * n_cap * sizeof(Entry) + (4 * qbig_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
-                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qsmall.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap;
+                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qsmall.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
     size_t budget = (size_t)((free_b + reclaim) * 0.6);
     if (keep) {
         size_t need = total_trees * arena_bytes;
@@ -501,6 +510,14 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const size_t big_tile_bytes = g.big_tile ? (size_t)BIG_THREADS * ((h->dstride >> 2) + 1) * 4 : 0;
     g.big_tma = 1;
     if (const char* ev = getenv("TST_BIG_TMA")) g.big_tma = atoi(ev) != 0;
+    // the histogram pass of k_grow_big leaves the m sampled bins of every row in a stash (8 bytes per row, coalesced) so
+    // that its partition pass does not gather the split feature's byte from the table again
+    bool use_stash = g.big_tile && g.m <= 8 && g.m <= g.MB;
+    if (const char* ev = getenv("TST_STASH")) use_stash = use_stash && atoi(ev) != 0;
+    if (use_stash) {
+        ENSURE(h->stash, B * n_cap * sizeof(uint2));
+        g.stash = h->stash.as<uint2>();
+    }
     const size_t big_smem = (size_t)g.MB * g.FS * 4 + big_tile_bytes;
     if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
     const bool small_packed = C <= 4;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
@@ -534,7 +551,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.mid_packed = mid_packed ? 1u : 0u;
     if (const char* ev = getenv("TST_MID_MAX")) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)atoi(ev)));
 
+    if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[tst trace] setup %.3f ms\n", ms_since(t_entry)); }
     for (size_t b0 = 0; b0 < total_trees; b0 += B) {
+        const auto t_batch = now();
+        double tr_boot = 0, tr_levels = 0, tr_tail = 0;
         const uint32_t nb = (uint32_t)std::min(B, total_trees - b0);
         for (uint32_t i = 0; i < nb; ++i) all[b0 + i].arena = keep ? (uint32_t)(b0 + i) : i;
         CK(cudaMemcpyAsync(h->trees.p, all.data() + b0, (size_t)nb * sizeof(TreeDesc), cudaMemcpyHostToDevice, st));
@@ -580,6 +600,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         CK(cudaMemcpyAsync(h->h_pinned, counters, 32, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_prep += ms; }
+        tr_boot = ms_since(t_batch);
 
         // ---- level-synchronous growth: CTA per node (> mid_max rows) and warp per node (33 .. mid_max rows).
         // One host round trip per level sizes the grids exactly.  Once a level is thin (the long tail of an unbalanced
@@ -591,7 +612,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         int blind_levels = 4;
         if (const char* ev = getenv("TST_BLIND_LEVELS")) blind_levels = std::max(1, std::min(8, atoi(ev)));
         uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1];
+        double tr_gap = 0; int tr_groups = 0;
         while (nbig > 0 || nmid > 0) {
+            const auto t_level = now();
             const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid <= 2048;
             const int J = thin ? blind_levels : 1;
             uint64_t ub_big = nbig, ub_mid = nmid;
@@ -606,20 +629,20 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 const uint32_t gb = (uint32_t)std::min<uint64_t>(ub_big, g.qbig_cap), gm = (uint32_t)std::min<uint64_t>(ub_mid, g.qbig_cap);
                 const uint32_t* cb = j ? counters + 2 * cur : nullptr;  // j == 0: counts are exact, no device read needed
                 const uint32_t* cm = j ? counters + 2 * cur + 1 : nullptr;
-                if (!thin) CK(cudaEventRecord(h->ev0, st));
+                CK(cudaEventRecord(h->ev_lvl[j][0], st));
                 if (gb) {
                     k_grow_big<BIG_THREADS><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
                     CKL();
                     h->stats.kernel_launches++; h->stats.launches_grow_big++;
                 }
-                if (!thin) CK(cudaEventRecord(h->ev1, st));
+                CK(cudaEventRecord(h->ev_lvl[j][1], st));
                 if (gm) {
                     if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
                     else k_grow_mid<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
                     CKL();
                     h->stats.kernel_launches++; h->stats.launches_grow_mid++;
                 }
-                if (!thin) CK(cudaEventRecord(h->ev2, st));
+                CK(cudaEventRecord(h->ev_lvl[j][2], st));
                 h->stats.levels++;
                 cur ^= 1;
                 const uint64_t nb2 = 2 * ub_big, nm2 = 2 * (ub_big + ub_mid);
@@ -628,15 +651,21 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             }
             CK(cudaMemcpyAsync(h->h_pinned, counters, 32, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            if (!thin) {
-                float ms = 0;
-                cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_grow_big += ms;
-                cudaEventElapsedTime(&ms, h->ev1, h->ev2); h->stats.ms_grow_mid += ms;
+            {   // every level is timed, also the ones launched blind (the top levels of a small batch of trees are "thin" too)
+                float ms_b = 0, ms_m = 0;
+                for (int j = 0; j < J; ++j) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, h->ev_lvl[j][0], h->ev_lvl[j][1]); ms_b += ms;
+                    cudaEventElapsedTime(&ms, h->ev_lvl[j][1], h->ev_lvl[j][2]); ms_m += ms;
+                }
+                h->stats.ms_grow_big += ms_b; h->stats.ms_grow_mid += ms_m;
+                if (trace) { tr_gap += ms_since(t_level) - ms_b - ms_m; ++tr_groups; }
             }
             nbig = h->h_pinned[2 * cur];
             nmid = h->h_pinned[2 * cur + 1];
             if (nbig > g.qbig_cap || nmid > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
+        tr_levels = ms_since(t_batch);
         // ---- subtrees with 7..32 rows: one warp each
         const uint32_t nsmall = h->h_pinned[4];
         if (nsmall > g.qsmall_cap) return fail(TST_ERR_OVERFLOW, "small-node queue overflowed");
@@ -705,7 +734,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             h->stats.kernel_launches++;
         }
         CK(cudaStreamSynchronize(st));
-        if (small_started) { float ms = 0; cudaEventElapsedTime(&ms, h->evs0, h->evs1); h->stats.ms_grow_small += ms; }  // span when overlapped
+        if (small_started) { float ms = 0; cudaEventElapsedTime(&ms, h->evs0, h->evs1); h->stats.ms_grow_small += ms; }
         if (tiny_timed) { float ms = 0; cudaEventElapsedTime(&ms, h->evm0, h->evm1); h->stats.ms_grow_tiny += ms; }
         if (evi0) {
             float ms = 0; cudaEventElapsedTime(&ms, evi0, evi1); h->stats.ms_infer += ms;
@@ -719,7 +748,11 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         }
         h->stats.trees += nb;
         if ((rc = pull_stats(h, st))) return rc;
+        tr_tail = ms_since(t_batch);
+        if (trace) fprintf(stderr, "[tst trace] batch of %u trees: boot+roots %.3f ms, levels %.3f ms (%d host round trips, %.3f ms outside the level kernels), small+tiny+infer+stats %.3f ms\n",
+                           nb, tr_boot, tr_levels - tr_boot, tr_groups, tr_gap, tr_tail - tr_levels);
     }
+    if (trace) fprintf(stderr, "[tst trace] fit_oof total %.3f ms\n", ms_since(t_entry));
     return TST_OK;
 }
 

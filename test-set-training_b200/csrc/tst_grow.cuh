@@ -165,6 +165,10 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
         for (int q = 0; q < 4; ++q) {
             uint32_t idx = i0 + q * 32u + lane;
             rs[q] = idx >> lp; pt[q] = idx & (P - 1u);
+            // 64-byte rows (P = 4, pitch 17 words): one instruction covers rows {4q..4q+3} and {16+4q..16+4q+3} instead of
+            // 8 consecutive rows, so the 32 (row, piece) word addresses of every store below fall into 32 different banks
+            // (consecutive rows collide pairwise: 2 wavefronts per store)
+            if (P == 4u) rs[q] = 4u * (uint32_t)q + ((lane >> 2) & 3u) + ((lane >> 4) << 4);
             uint32_t rid = __shfl_sync(0xffffffffu, row, rs[q] & 31u);
             ok[q] = __shfl_sync(0xffffffffu, has ? 1u : 0u, rs[q] & 31u) && idx < 32u * P;
             if (ok[q]) v[q] = __ldg((const uint4*)(bins + (uint64_t)rid * dstride) + pt[q]);
@@ -184,6 +188,9 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
 #endif
 #ifndef BIG_PART_SCAN
 #define BIG_PART_SCAN 1
+#endif
+#ifndef BIG_PART_PREFETCH
+#define BIG_PART_PREFETCH 0
 #endif
 // TMA ring for the row-index tiles of the histogram pass.  Measured on B200 (1M x 64, 320 trees in flight): the
 // ring adds mbarrier bookkeeping and registers to a kernel that sits at 80 registers / 3 CTAs per SM and is
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     __shared__ uint32_t s_wl[2][4][NW], s_wr[2][4][NW];
 #endif
     __shared__ double s_bgain;
-    __shared__ uint32_t s_bkey, s_found, s_newj, s_N, s_stop;
+    __shared__ uint32_t s_bkey, s_found, s_newj, s_N, s_stop, s_sj;  // s_sj: position of the best split's feature in the stash (or none)
 #if BIG_TMA_RING
     __shared__ __align__(16) Entry s_ent[NW][ENT_STAGES][32];  // TMA-staged row-index tiles, one ring per warp
     __shared__ __align__(8) uint64_t s_bar[NW][ENT_STAGES];
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     uint32_t* s_tile = s_hist + g.MB * g.FS + wid * 32u * pitch;  // this warp's rows
 
     for (int f = tid; f < d; f += THREADS) s_perm[f] = (uint16_t)f;
-    if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; }
+    if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; s_sj = 0xFFFFFFFFu; }
 #if BIG_TMA_RING
     const bool use_tma = use_tile && g.big_tma != 0 && dstride <= 64;
     if (use_tma && lane == 0) {
@@ -285,6 +292,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 
         // ---- class histogram: hist[j][bin][class] += multiplicity (SK/.../histogram.pyx:336-425 pattern)
         if (use_tile && nb <= 8) {
+            uint2* stash_w = (!BIG_TMA_RING && g.stash != nullptr && pos == 0) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
             uint32_t featr[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) featr[jj] = jj < nb ? s_feat[jj] : 0u;
@@ -319,15 +327,27 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                 }
             } else
 #endif
+            // the entry of the NEXT tile is requested before this tile's rows: the two dependent latencies
+            // (entry list from HBM, then the row gather from L2) overlap across iterations
+            Entry e_next = t.begin + tid < t.end ? ent_load(ent_in + t.begin + tid) : make_uint2(0u, 0u);
             for (uint32_t base = t.begin; base < t.end; base += THREADS) {
-                const uint32_t idx = base + tid;
-                const Entry e = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
+                const Entry e = e_next;
+                {
+                    const uint32_t nidx = base + THREADS + tid;
+                    e_next = nidx < t.end ? ent_load(ent_in + nidx) : make_uint2(0u, 0u);
+                }
                 fetch_rows32(bins, dstride, e.x, e.y != 0u, s_tile, lane);
                 if (e.y) {
                     const uint32_t cls = ent_cls(e), w = ent_w(e);
+                    uint32_t sb0 = 0, sb1 = 0;  // the row's sampled bins, byte jj = feature jj of the draw
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj)
-                        if (jj < nb) atomicAdd(&s_hist[jj * g.FS + hist_index(trow[featr[jj]], cls, C)], w);
+                        if (jj < nb) {
+                            const uint32_t bj = trow[featr[jj]];
+                            if (jj < 4) sb0 |= bj << (8 * jj); else sb1 |= bj << (8 * (jj - 4));
+                            atomicAdd(&s_hist[jj * g.FS + hist_index(bj, cls, C)], w);
+                        }
+                    if (stash_w) __stcg(stash_w + (base + tid), make_uint2(sb0, sb1));
                 }
                 __syncwarp();
             }
@@ -376,12 +396,13 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                     uint32_t key = (s_feat[j] << 8) | s_fbin[j];  // ties: lowest feature, then lowest bin
                     if (s_fgain[j] > s_bgain || (s_fgain[j] == s_bgain && key < s_bkey)) {
                         s_bgain = s_fgain[j]; s_bkey = key; s_newj = j; s_found = 1;
+                        s_sj = (!BIG_TMA_RING && pos == 0 && g.stash != nullptr && use_tile && nb <= 8) ? (uint32_t)j : 0xFFFFFFFFu;
                     }
                 }
             } else {
                 for (int j = 0; j < nb; ++j) {
                     if (s_fbin[j] == 0xFFFFFFFFu) continue;
-                    s_bgain = s_fgain[j]; s_bkey = (s_feat[j] << 8) | s_fbin[j]; s_newj = j; s_found = 1;
+                    s_bgain = s_fgain[j]; s_bkey = (s_feat[j] << 8) | s_fbin[j]; s_newj = j; s_found = 1; s_sj = 0xFFFFFFFFu;
                     break;  // fallback: first feature in draw order with a valid split
                 }
             }
@@ -427,20 +448,49 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     // ---- row partition (SK/tree/_partitioner.pyx:248-279): left rows packed from the front in order,
     // right rows from the back; tree structure depends only on the sets, not on the order.
     const uint32_t bf = s_bkey >> 8, bb = s_bkey & 0xFFu;
+    const uint32_t sj = s_sj;
+    const uint2* stash_r = (g.stash != nullptr && sj != 0xFFFFFFFFu) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
     uint32_t lbase = 0, rbase = 0;
     int par = 0;
     constexpr int PU = 4;  // chunks per barrier
+#if BIG_PART_PREFETCH
+    Entry e_nx[PU];  // entries of the next iteration, requested one iteration ahead
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+        uint32_t idx = t.begin + u * THREADS + tid;
+        e_nx[u] = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
+    }
+#endif
     for (uint32_t c0 = t.begin; c0 < t.end; c0 += THREADS * PU, par ^= 1) {
         Entry e[PU];
         uint32_t balL[PU], balR[PU];
         bool goL[PU];
+#if BIG_PART_PREFETCH
+#pragma unroll
+        for (int u = 0; u < PU; ++u) {
+            e[u] = e_nx[u];
+            uint32_t idx = c0 + THREADS * PU + u * THREADS + tid;
+            e_nx[u] = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
+        }
+#else
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
             uint32_t idx = c0 + u * THREADS + tid;
             e[u] = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
         }
+#endif
+        if (stash_r) {  // the split feature's bin of every row was left in the stash by the histogram pass
 #pragma unroll
-        for (int u = 0; u < PU; ++u) goL[u] = e[u].y && bins[(uint64_t)e[u].x * dstride + bf] <= bb;
+            for (int u = 0; u < PU; ++u) {
+                const uint32_t idx = c0 + u * THREADS + tid;
+                uint2 sv = make_uint2(0u, 0u);
+                if (e[u].y) sv = __ldcs(stash_r + idx);
+                goL[u] = e[u].y && (((sj < 4u ? sv.x : sv.y) >> (8u * (sj & 3u))) & 0xFFu) <= bb;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < PU; ++u) goL[u] = e[u].y && bins[(uint64_t)e[u].x * dstride + bf] <= bb;
+        }
 #if BIG_PART_SCAN
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
