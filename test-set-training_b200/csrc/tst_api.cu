@@ -396,8 +396,11 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     const auto t_entry = now();
+    if (trace) cudaStreamSynchronize(st);  // work queued by the caller before this call is not ours
+    const double tr_wait = ms_since(t_entry);
     int rc = set_kernel_attrs(h);
     if (rc) return rc;
+    const double tr_attrs = ms_since(t_entry);
 
     // ---- partitions: rows sorted by (group, fold slot, row)
     const int np = n_groups * (k + 1);
@@ -441,7 +444,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const size_t total_trees = all.size();
     h->kept.clear();
     if (total_trees == 0) return TST_OK;
+    const double tr_parts = ms_since(t_entry);
     L2Window l2w(h, st);
+    const double tr_l2 = ms_since(t_entry);
 
     // ---- sizes (everything for B trees in flight stays resident in HBM)
     const uint64_t n_cap = std::max<uint64_t>(4, ((uint64_t)max_train + 3) / 4 * 4);
@@ -551,7 +556,11 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.mid_packed = mid_packed ? 1u : 0u;
     if (const char* ev = getenv("TST_MID_MAX")) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)atoi(ev)));
 
-    if (trace) { cudaStreamSynchronize(st); fprintf(stderr, "[tst trace] setup %.3f ms\n", ms_since(t_entry)); }
+    if (trace) {
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[tst trace] setup %.3f ms: caller's queued work %.3f, kernel attributes %.3f, partitions %.3f, L2 window %.3f, buffers %.3f\n", ms_since(t_entry),
+                tr_wait, tr_attrs - tr_wait, tr_parts - tr_attrs, tr_l2 - tr_parts, ms_since(t_entry) - tr_l2);
+    }
     for (size_t b0 = 0; b0 < total_trees; b0 += B) {
         const auto t_batch = now();
         double tr_boot = 0, tr_levels = 0, tr_tail = 0;
@@ -686,19 +695,19 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             const uint32_t ntiny = h->h_pinned[5];
             if (ntiny > g.qtiny_cap) return fail(TST_ERR_OVERFLOW, "tiny-node queue overflowed");
             if (ntiny) {
-                // bucket offsets, largest subtrees first; counters[6 + r] holds the number of tasks with r rows
-                uint32_t cur[TINY_MAX + 1], acc = 0;
-                for (int rr = TINY_MAX; rr >= 0; --rr) { cur[rr] = acc; acc += h->h_pinned[6 + rr]; }
-                for (int rr = 0; rr <= TINY_MAX; ++rr) h->h_pinned[32 + rr] = cur[rr];
-                CK(cudaMemcpyAsync(counters + 32, h->h_pinned + 32, (TINY_MAX + 1) * 4, cudaMemcpyHostToDevice, st));
+                // bucket offsets, largest subtrees first: counters[6 + r] = number of tasks with r rows, counters[32 + r] = cursor
                 CK(cudaEventRecord(h->evm0, st));
+                k_tiny_hist<<<(ntiny + 255) / 256, 256, 0, st>>>((const uint4*)h->qtiny.p, ntiny, counters + 6);
+                CKL();
+                k_tiny_cursors<<<1, 32, 0, st>>>(counters + 6, TINY_MAX, counters + 32);
+                CKL();
                 k_tiny_sort<<<(ntiny + 255) / 256, 256, 0, st>>>((const uint4*)h->qtiny.p, ntiny, counters + 32, (uint4*)h->qtiny2.p);
                 CKL();
                 k_grow_tiny4<TINY_MAX><<<(ntiny + 127) / 128, 128, 0, st>>>(g, (const uint4*)h->qtiny2.p, ntiny);
                 CKL();
                 CK(cudaEventRecord(h->evm1, st));
                 tiny_timed = true;
-                h->stats.kernel_launches += 2; h->stats.launches_grow_tiny++;
+                h->stats.kernel_launches += 4; h->stats.launches_grow_tiny++;
             }
         }
         // ---- OOF inference of this batch's trees on their held-out rows

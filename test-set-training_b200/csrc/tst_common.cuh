@@ -223,8 +223,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ void tiny_push(const GrowCtx& g, uint32_t tree, uint32_t begin, uint32_t rows, uint32_t depth, uint32_t slot) {
     // TinyTask = (begin, slot, depth, tree | rows << 16)
-    uint32_t i = atomicAdd(g.qtiny_count, 1u);
-    atomicAdd(g.qtiny_count + 1u + rows, 1u);  // histogram by row count: the tasks are sorted by size before they run
+    uint32_t i = atomicAdd(g.qtiny_count, 1u);  // (the size histogram for the sort is taken by k_tiny_hist, not here)
     if (i < g.qtiny_cap) ((uint4*)g.qtiny)[i] = make_uint4(begin, slot, depth, tree | (rows << 16));
     else g.stats->error = 2;
 }

@@ -13,11 +13,35 @@
 #define TINY_FY_MAX 64  // positions of the draw that can be recorded (host enables the tier only for d <= 64)
 
 // Counting sort of the tiny tasks by row count (largest first): lanes of a warp then own subtrees of the same size.
+// k_tiny_hist counts the tasks per size (one atomic per warp and size), k_tiny_cursors turns the counts into bucket
+// offsets, k_tiny_sort scatters.
+__global__ void __launch_bounds__(256) k_tiny_hist(const uint4* __restrict__ in, uint32_t n, uint32_t* __restrict__ hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = i < n ? (in[i].w >> 16) : 0xFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, r);
+    if (i < n && (threadIdx.x & 31u) == __ffs(peers) - 1u) atomicAdd(&hist[r], (uint32_t)__popc(peers));
+}
+
+__global__ void k_tiny_cursors(const uint32_t* __restrict__ hist, int tmax, uint32_t* __restrict__ cursor) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int r = tmax; r >= 0; --r) { cursor[r] = acc; acc += hist[r]; }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_tiny_sort(const uint4* __restrict__ in, uint32_t n, uint32_t* __restrict__ cursor, uint4* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint4 t = in[i];
-    out[atomicAdd(&cursor[t.w >> 16], 1u)] = t;
+    const bool live = i < n;
+    uint4 t = make_uint4(0u, 0u, 0u, 0u);
+    if (live) t = in[i];
+    // one atomic per (warp, size class) instead of one per task: the 7 cursors are the only contended addresses
+    const uint32_t r = live ? (t.w >> 16) : 0xFFFFu;
+    const uint32_t peers = __match_any_sync(0xffffffffu, r);
+    const uint32_t leader = __ffs(peers) - 1u, lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (live && lane == leader) base = atomicAdd(&cursor[r], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live) out[base + __popc(peers & ((1u << lane) - 1u))] = t;
 }
 
 template <int TMAX>
