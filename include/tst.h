@@ -57,8 +57,13 @@ typedef struct {
     int32_t max_features;       /* m in [1, d]; host resolves "sqrt" -> max(1, floor(sqrt(d))) */
     int32_t trees_in_flight;    /* <= 0: sized from free HBM */
     int32_t keep_forest;        /* != 0: node arrays stay resident for tst_export_tree / tst_predict */
-    int32_t reserved[2];
+    int32_t criterion;          /* TST_GINI (0) or TST_SQUARED_ERROR (1): the labels 0..C-1 are then the ordinal levels of a
+                                   uniformly quantised numeric target and splits maximise S_L^2/N_L + S_R^2/N_R with
+                                   S = sum_c c * count_c (SK/tree/_criterion.pyx:707-1000, MSE.proxy_impurity_improvement) */
+    int32_t reserved;
 } tst_params;
+
+enum { TST_GINI = 0, TST_SQUARED_ERROR = 1 };
 
 typedef struct {
     uint64_t row_visits_big;    /* distinct in-bag rows summed over nodes searched by the per-node CTA kernel */

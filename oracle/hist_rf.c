@@ -44,6 +44,8 @@ typedef struct {
     int32_t min_samples_split; /* >= 2            (SK/tree/_classes.py:317-328) */
     int32_t min_samples_leaf;  /* >= 1 */
     int32_t max_features;      /* m in [1, d]; "sqrt" resolved by the caller (SK/tree/_classes.py:330-345) */
+    int32_t criterion;         /* 0 = Gini (classification); 1 = squared error on ordinal levels: the labels 0..C-1 are
+                                  the levels of a uniformly quantised numeric target (SK/tree/_criterion.pyx:707-1000) */
 } orc_params;
 
 typedef struct {
@@ -243,6 +245,17 @@ static inline double gain_of(uint64_t SL, uint64_t NL, uint64_t SR, uint64_t NR)
     return a + b;
 }
 
+/* squared-error proxy (SK/tree/_criterion.pyx MSE.proxy_impurity_improvement): sum_left^2 / n_left +
+ * sum_right^2 / n_right with S = sum over levels c of c * count_c (exact uint64); one multiply, one divide per
+ * side, one add, each rounded once. */
+static inline double gain_mse(uint64_t SL, uint64_t NL, uint64_t SR, uint64_t NR) {
+    volatile double sl = (double)SL, sr = (double)SR;
+    volatile double pl = sl * sl, pr = sr * sr;
+    volatile double a = pl / (double)NL;
+    volatile double b = pr / (double)NR;
+    return a + b;
+}
+
 static int grow_tree(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, int32_t C,
                      const orc_params* prm, uint32_t k0, uint32_t k1, uint32_t gid, entry_t* ent,
                      entry_t* tmp, uint32_t n_inbag, node_store* S, orc_stats* st) {
@@ -310,8 +323,14 @@ static int grow_tree(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t
                     uint64_t NR = N - NL;
                     if (NL < msl || NR < msl) continue;
                     uint64_t SL = 0, SR = 0;
-                    for (int32_t c = 0; c < C; ++c) { uint64_t l = cum[c], r = tot[c] - l; SL += l * l; SR += r * r; }
-                    double g = gain_of(SL, NL, SR, NR);
+                    double g;
+                    if (prm->criterion == 1) {
+                        for (int32_t c = 0; c < C; ++c) { uint64_t l = cum[c], r = tot[c] - l; SL += (uint64_t)c * l; SR += (uint64_t)c * r; }
+                        g = gain_mse(SL, NL, SR, NR);
+                    } else {
+                        for (int32_t c = 0; c < C; ++c) { uint64_t l = cum[c], r = tot[c] - l; SL += l * l; SR += r * r; }
+                        g = gain_of(SL, NL, SR, NR);
+                    }
                     if (!f_found || g > f_gain) { f_found = 1; f_gain = g; f_bin = b; }
                 }
                 for (int32_t b = lo; b <= hi; ++b) for (int32_t c = 0; c < C; ++c) hist[(size_t)b * C + c] = 0;
@@ -356,7 +375,8 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
                 int32_t nthreads) {
     if (n < 0 || n >= 0x7FFFFFF0LL || d < 1 || C < 1 || C > 256 || k < 1 || k > 250 || n_trees < 1 ||
         n_trees > 65535 || t0 < 0 || t1 > n_trees || t0 > t1 || world < 1 || rank < 0 || rank >= world ||
-        prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2)
+        prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2 ||
+        prm->criterion < 0 || prm->criterion > 1)
         return -1;
     orc_parts P;
     int rc = build_parts(fold, group, n_groups, n, k, &P);

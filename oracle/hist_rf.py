@@ -23,7 +23,7 @@ MAX_EDGES = 255
 
 class OrcParams(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("min_samples_split", C.c_int32),
-                ("min_samples_leaf", C.c_int32), ("max_features", C.c_int32)]
+                ("min_samples_leaf", C.c_int32), ("max_features", C.c_int32), ("criterion", C.c_int32)]
 
 
 class OrcStats(C.Structure):
@@ -153,9 +153,12 @@ def resolve_max_features(max_features, d: int) -> int:
     return int(max_features)
 
 
-def make_params(d, max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt"):
+CRITERIA = {"gini": 0, "squared_error": 1}
+
+
+def make_params(d, max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt", criterion="gini"):
     return OrcParams(0 if max_depth is None else int(max_depth), int(min_samples_split),
-                     int(min_samples_leaf), resolve_max_features(max_features, d))
+                     int(min_samples_leaf), resolve_max_features(max_features, d), CRITERIA[criterion])
 
 
 @dataclass

@@ -199,6 +199,7 @@ extern "C" int tst_destroy(tst_handle* h) {
 static int set_kernel_attrs(tst_handle* h) {
     if (h->attrs_set) return 0;
     CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -389,6 +390,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         return fail(TST_ERR_INVALID, "tst_fit_oof: bad k / n_trees / classes / tree range");
     if (prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2)
         return fail(TST_ERR_INVALID, "tst_fit_oof: bad growth parameters");
+    if (prm->criterion != TST_GINI && prm->criterion != TST_SQUARED_ERROR) return fail(TST_ERR_INVALID, "tst_fit_oof: unknown criterion");
     if ((uint64_t)n_groups * k * n_trees + gid_base > 0xFFFFFFFFull) return fail(TST_ERR_INVALID, "tst_fit_oof: tree id overflows 32 bits");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -503,6 +505,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     memset(&g, 0, sizeof(g));
     g.bins_rm = h->bins_rm.as<uint8_t>(); g.dstride = h->dstride; g.d = d; g.C = C; g.m = prm->max_features;
     g.max_depth = prm->max_depth; g.mss = (uint32_t)prm->min_samples_split; g.msl = (uint32_t)prm->min_samples_leaf;
+    g.criterion = (uint32_t)prm->criterion;
     g.k0 = (uint32_t)seed; g.k1 = (uint32_t)(seed >> 32);
     g.entA = h->entA.as<Entry>(); g.entB = h->entB.as<Entry>(); g.n_cap = n_cap;
     g.nodes = nodes_p; g.node_stride = node_stride; g.leafc = leafc_p; g.leafc_stride = leafc_stride;
@@ -525,7 +528,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     }
     const size_t big_smem = (size_t)g.MB * g.FS * 4 + big_tile_bytes;
     if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
-    const bool small_packed = C <= 4;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
+    const bool packed_ok = C <= 4 && prm->criterion == TST_GINI;  // the packed 4-class kernels implement the Gini criterion only
+    const bool small_packed = packed_ok;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
     const uint32_t small_per_warp = small_packed ? ((64u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
@@ -546,9 +550,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     uint32_t* counters = h->counters.as<uint32_t>();  // [2p], [2p+1] big / mid queue counts of parity p, [4] small, [5] tiny, [6+r] tiny histogram
     g.qsmall_count = counters + 4;
     g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
-    g.tiny_max = (C <= 4 && d <= TINY_FY_MAX && B <= 65535) ? TINY_MAX : 0;  // packed 4-class thread-per-subtree tier
+    g.tiny_max = (packed_ok && d <= TINY_FY_MAX && B <= 65535) ? TINY_MAX : 0;  // packed 4-class thread-per-subtree tier
     if (const char* ev = getenv("TST_TINY_MAX")) g.tiny_max = std::min<uint32_t>(g.tiny_max, (uint32_t)atoi(ev));
-    const bool mid_packed = C <= 4;  // packed 16-bit class counts (k_grow_mid4)
+    const bool mid_packed = packed_ok;  // packed 16-bit class counts (k_grow_mid4)
     const uint32_t mid_per_warp = mid_packed ? ((MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                              : (uint32_t)g.FS + 2u * (uint32_t)C + (uint32_t)((d + 1) / 2);
     const size_t mid_smem = (size_t)MID_WARPS * mid_per_warp * 4;
@@ -635,12 +639,14 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 g.qmid_next = cur ? h->qmid0.as<Task>() : h->qmid1.as<Task>();
                 g.qmid_next_count = counters + 2 * (cur ^ 1) + 1;
                 CK(cudaMemsetAsync(g.qnext_count, 0, 8, st));  // both counters of the next level
-                const uint32_t gb = (uint32_t)std::min<uint64_t>(ub_big, g.qbig_cap), gm = (uint32_t)std::min<uint64_t>(ub_mid, g.qbig_cap);
+                const uint32_t gb = (uint32_t)std::min<uint64_t>(ub_big, g.qbig_cap);
+                const uint32_t gm = g.mid_max > SMALL_MAX ? (uint32_t)std::min<uint64_t>(ub_mid, g.qbig_cap) : 0u;  // tier off: its histogram does not fit
                 const uint32_t* cb = j ? counters + 2 * cur : nullptr;  // j == 0: counts are exact, no device read needed
                 const uint32_t* cm = j ? counters + 2 * cur + 1 : nullptr;
                 CK(cudaEventRecord(h->ev_lvl[j][0], st));
                 if (gb) {
-                    k_grow_big<BIG_THREADS><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
+                    if (g.criterion == 1u) k_grow_big<BIG_THREADS, true><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
+                    else k_grow_big<BIG_THREADS><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
                     CKL();
                     h->stats.kernel_launches++; h->stats.launches_grow_big++;
                 }

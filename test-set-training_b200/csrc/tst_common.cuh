@@ -128,6 +128,7 @@ struct GrowCtx {
     int32_t d, C, m;
     int32_t max_depth;
     uint32_t mss, msl;
+    uint32_t criterion;  // 0 = Gini; 1 = squared error on ordinal levels (labels are the levels of a quantised numeric target)
     uint32_t k0, k1;  // Philox key = seed
     Entry* entA;      // [trees][n_cap] ping
     Entry* entB;      // pong
@@ -177,6 +178,17 @@ __device__ __forceinline__ double gini_gain(unsigned long long SL, uint32_t NL, 
     // two IEEE divisions and one add -- no multiply, so nothing can be contracted into an FMA.
     return __dadd_rn(__ddiv_rn(__ull2double_rn(SL), __uint2double_rn(NL)),
                      __ddiv_rn(__ull2double_rn(SR), __uint2double_rn(NR)));
+}
+
+// Squared-error proxy (SK/tree/_criterion.pyx MSE.proxy_impurity_improvement): S_L^2/N_L + S_R^2/N_R with
+// S = sum over levels c of c * count_c; one multiply and one divide per side and one add, each rounded once
+// (oracle/hist_rf.c: gain_mse).
+__device__ __forceinline__ double mse_gain(unsigned long long SL, uint32_t NL, unsigned long long SR, uint32_t NR) {
+    const double sl = __ull2double_rn(SL), sr = __ull2double_rn(SR);
+    return __dadd_rn(__ddiv_rn(__dmul_rn(sl, sl), __uint2double_rn(NL)), __ddiv_rn(__dmul_rn(sr, sr), __uint2double_rn(NR)));
+}
+__device__ __forceinline__ float mse_gain_estimate(float SL, float NL, float SR, float NR) {
+    return fmaf(SL, __fdividef(SL, NL), SR * __fdividef(SR, NR));  // no S^2 * N product: cannot overflow fp32
 }
 
 // fp32 ESTIMATE of the same quantity, used only to decide which candidates get the exact fp64 evaluation:

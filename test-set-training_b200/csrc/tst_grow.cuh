@@ -79,8 +79,9 @@ __device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint
 // Split scan of one feature histogram by one warp.  Lane l owns bins [8l, 8l+8).  Per class: local
 // inclusive prefix, warp-shuffle exclusive scan of the lane totals, then L/R sums of squares are
 // accumulated exactly in uint64.  Returns the warp-wide best (gain, bin) with ties -> lowest bin.
-__device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, int C, uint32_t msl, uint32_t lane,
-                                             double& best_gain, uint32_t& best_bin, uint32_t* tot_out, uint32_t* N_out) {
+template <bool mse>  // mse: sL / sR hold sum_c c * count_c instead of sum_c count_c^2 (squared-error criterion on ordinal levels)
+__device__ __forceinline__ void scan_feature_t(const uint32_t* __restrict__ hf, int C, uint32_t msl, uint32_t lane,
+                                               double& best_gain, uint32_t& best_bin, uint32_t* tot_out, uint32_t* N_out) {
     unsigned long long sL[8], sR[8];
     uint32_t nL[8];
 #pragma unroll
@@ -109,8 +110,8 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             uint32_t L = excl + p[i], R = tot - L;
-            sL[i] += (unsigned long long)L * L;
-            sR[i] += (unsigned long long)R * R;
+            sL[i] += (unsigned long long)L * (mse ? (uint32_t)c : L);
+            sR[i] += (unsigned long long)R * (mse ? (uint32_t)c : R);
             nL[i] += L;
         }
     }
@@ -123,7 +124,8 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
         if ((occ >> i) & 1u) {  // an empty bin repeats the previous partition and would lose the tie anyway
             uint32_t NL = nL[i], NR = N - NL;
             if (NL >= msl && NR >= msl) {
-                ge[i] = gain_estimate(__ull2float_rn(sL[i]), __uint2float_rn(NL), __ull2float_rn(sR[i]), __uint2float_rn(NR));
+                ge[i] = mse ? mse_gain_estimate(__ull2float_rn(sL[i]), __uint2float_rn(NL), __ull2float_rn(sR[i]), __uint2float_rn(NR))
+                            : gain_estimate(__ull2float_rn(sL[i]), __uint2float_rn(NL), __ull2float_rn(sR[i]), __uint2float_rn(NR));
                 lmax = fmaxf(lmax, ge[i]);
             }
         }
@@ -134,7 +136,7 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (ge[i] >= thr) {
-            double gn = gini_gain(sL[i], nL[i], sR[i], N - nL[i]);
+            double gn = mse ? mse_gain(sL[i], nL[i], sR[i], N - nL[i]) : gini_gain(sL[i], nL[i], sR[i], N - nL[i]);
             if (gn > bg) { bg = gn; bb = lane * 8u + i; }
         }
     }
@@ -146,6 +148,12 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
     }
     best_gain = bg;
     best_bin = bb;
+}
+
+__device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, int C, uint32_t msl, uint32_t lane,
+                                             double& best_gain, uint32_t& best_bin, uint32_t* tot_out, uint32_t* N_out, uint32_t criterion) {
+    if (criterion == 1u) scan_feature_t<true>(hf, C, msl, lane, best_gain, best_bin, tot_out, N_out);
+    else scan_feature_t<false>(hf, C, msl, lane, best_gain, best_bin, tot_out, N_out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -202,7 +210,7 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
 #define ENT_STAGES 4  // 32-entry (256-byte) TMA tiles in flight per warp
 
 // ---------------------------------------------------------------------------------------------
-template <int THREADS>
+template <int THREADS, bool MSE = false>  // MSE: squared-error criterion on ordinal levels (its own instantiation: the Gini one keeps its registers)
 __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     constexpr int NW = THREADS / 32;
     extern __shared__ uint32_t s_hist[];  // [MB][FS] histogram, then (row tile) [THREADS][dstride/4 + 1]
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
         for (int j = wid; j < nb; j += NW) {
             double bg; uint32_t bb;
             bool want_tot = (pos == 0 && j == 0);
-            scan_feature(s_hist + j * g.FS, C, g.msl, lane, bg, bb, want_tot ? s_tot : nullptr, want_tot ? &s_N : nullptr);
+            scan_feature_t<MSE>(s_hist + j * g.FS, C, g.msl, lane, bg, bb, want_tot ? s_tot : nullptr, want_tot ? &s_N : nullptr);
             if (lane == 0) { s_fgain[j] = bg; s_fbin[j] = bb; }
         }
         __syncthreads();
@@ -635,13 +643,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task
                     for (int c = 0; c < C; ++c) {
                         uint32_t L = s_L[c * 32 + lane], R = s_tot[c] - L;
                         NL += L;
-                        SL += (unsigned long long)L * L;
-                        SR += (unsigned long long)R * R;
+                        SL += (unsigned long long)L * (g.criterion == 1u ? (uint32_t)c : L);
+                        SR += (unsigned long long)R * (g.criterion == 1u ? (uint32_t)c : R);
                     }
                     const uint32_t NR = N - NL;
                     double gn = -1.0;
                     uint32_t gb = 0xFFFFFFFFu;
-                    if (active && NL >= g.msl && NR >= g.msl) { gn = gini_gain(SL, NL, SR, NR); gb = b; }
+                    if (active && NL >= g.msl && NR >= g.msl) { gn = g.criterion == 1u ? mse_gain(SL, NL, SR, NR) : gini_gain(SL, NL, SR, NR); gb = b; }
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
                         double og = __shfl_xor_sync(0xffffffffu, gn, off);

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
         __syncwarp();
         double bg;
         uint32_t bb;
-        scan_feature(s_hist, C, g.msl, lane, bg, bb, i == 0 ? s_tot : nullptr, i == 0 ? &N : nullptr);
+        scan_feature(s_hist, C, g.msl, lane, bg, bb, i == 0 ? s_tot : nullptr, i == 0 ? &N : nullptr, g.criterion);
         if (i == 0) {
             N = __shfl_sync(0xffffffffu, N, 0);
             __syncwarp();

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_root_split(GrowCtx g, const uint32_t* _
     __syncthreads();
     for (int j = wid; j < m; j += 8) {
         double bg; uint32_t bb;
-        scan_feature(s_hist + j * g.FS, C, g.msl, lane, bg, bb, j == 0 ? s_tot : nullptr, j == 0 ? &s_N : nullptr);
+        scan_feature(s_hist + j * g.FS, C, g.msl, lane, bg, bb, j == 0 ? s_tot : nullptr, j == 0 ? &s_N : nullptr, g.criterion);
         if (lane == 0) { s_fgain[j] = bg; s_fbin[j] = bb; }
     }
     __syncthreads();

@@ -31,7 +31,7 @@ class TstError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("min_samples_split", C.c_int32), ("min_samples_leaf", C.c_int32),
                 ("max_features", C.c_int32), ("trees_in_flight", C.c_int32), ("keep_forest", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("criterion", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -40,12 +40,17 @@ def resolve_max_features(max_features, d: int) -> int:
     return max(1, min(d, int(max_features)))
 
 
+CRITERIA = {"gini": 0, "squared_error": 1}  # include/tst.h: TST_GINI, TST_SQUARED_ERROR
+
+
 def make_params(d, max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt",
-                trees_in_flight=0, keep_forest=False) -> Params:
+                trees_in_flight=0, keep_forest=False, criterion="gini") -> Params:
     if min_samples_split < 2 or min_samples_leaf < 1:
         raise ValueError("min_samples_split >= 2 and min_samples_leaf >= 1 required")
+    if criterion not in CRITERIA:
+        raise ValueError(f"criterion must be one of {sorted(CRITERIA)}")
     return Params(0 if max_depth is None else int(max_depth), int(min_samples_split), int(min_samples_leaf),
-                  resolve_max_features(max_features, d), int(trees_in_flight), int(bool(keep_forest)))
+                  resolve_max_features(max_features, d), int(trees_in_flight), int(bool(keep_forest)), CRITERIA[criterion])
 
 
 def encode_labels(y):
@@ -341,6 +346,72 @@ def run_tst(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, max_depth=No
     return TsTResult(s_h, votes_h, fold_dev.cpu().numpy(), acc, classes, eng.stats())
 
 
+# ------------------------------------------------------------------------------------------------- numeric answers
+# the squared-error criterion (SK/tree/_criterion.pyx:707-1000) for question types whose answer is a
+# number.  The target is uniformly quantised into <= 32 ordinal levels on the host; the kernels grow the same
+# histogram trees with S = sum_c c * count_c in place of the class-count squares, leaves keep level counts, and the
+# prediction is the vote-weighted mean level mapped back to the target's scale.
+def quantise_target(y, n_levels: int = 32):
+    """-> (levels uint8 [n], lo, step): level = floor((y - lo) / step), step = (max - min) / n_levels."""
+    if not 2 <= n_levels <= 32:
+        raise ValueError("n_levels must be in [2, 32]")
+    y = np.asarray(y, dtype=np.float64)
+    if y.size == 0 or not np.all(np.isfinite(y)):
+        raise ValueError("numeric target must be non-empty and finite")
+    lo, hi = float(y.min()), float(y.max())
+    step = (hi - lo) / n_levels if hi > lo else 1.0
+    lev = np.minimum(np.floor((y - lo) / step), n_levels - 1).astype(np.uint8)
+    return lev, lo, step
+
+
+def votes_to_value(votes, lo: float, step: float) -> np.ndarray:
+    """Vote-weighted mean level -> target scale (level c stands for the centre of its interval); NaN without votes."""
+    v = np.asarray(votes).astype(np.float64)
+    tot = v.sum(axis=1)
+    mean_level = np.divide(v @ np.arange(v.shape[1], dtype=np.float64), tot, out=np.full(v.shape[0], np.nan), where=tot > 0)
+    return lo + (mean_level + 0.5) * step
+
+
+@dataclass
+class TsTRegressionResult:
+    y_pred: np.ndarray          # [n] float64 out-of-fold blind prediction of the numeric answer (NaN if never held out)
+    s: np.ndarray               # [n] float64 bias score 1 - |y_pred - y| / (max(y) - min(y)) in [0, 1]
+    oof_votes: np.ndarray       # [n, n_levels] uint32 Q0.16 vote sums
+    fold_id: np.ndarray
+    levels: np.ndarray          # [n] uint8 quantised target
+    lo: float = 0.0
+    step: float = 1.0
+    stats: dict = field(default_factory=dict)
+
+
+def run_tst_regression(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, n_levels: int = 32, max_depth=None,
+                       min_samples_split=2, min_samples_leaf=1, max_features=1.0, n_bins=256, group=None,
+                       engine: Engine | None = None, trees_in_flight=0) -> TsTRegressionResult:
+    """k-fold x n_trees diagnostic for numeric answers (max_features default 1.0 as in RandomForestRegressor)."""
+    torch = _torch()
+    eng = engine or get_engine()
+    lev, lo, step = quantise_target(y, n_levels)
+    eng.bin(X, n_bins=n_bins)
+    y_dev = eng.to_dev(lev, torch.uint8)
+    g_dev, n_groups = None, 1
+    if group is not None:
+        gi = np.asarray(group, dtype=np.int32)
+        n_groups = int(gi.max()) + 1
+        g_dev = eng.to_dev(gi, torch.int32)
+    active = torch.ones(eng.n, dtype=torch.uint8, device=eng.dev)
+    fold_dev = eng.assign_folds(y_dev, active, k, n_levels, g_dev, n_groups)  # folds stratified by level
+    prm = make_params(eng.d, max_depth, min_samples_split, min_samples_leaf, max_features, trees_in_flight,
+                      criterion="squared_error")
+    votes = eng.new_votes(n_levels)
+    eng.stats(reset=True)
+    eng.fit_oof(y_dev, fold_dev, k, n_trees, n_levels, prm, seed=seed, group_dev=g_dev, n_groups=n_groups, votes=votes)
+    votes_h = eng.allreduce_votes(votes).cpu().numpy().view(np.uint32)
+    y_pred = votes_to_value(votes_h, lo, step)
+    span = n_levels * step
+    s = 1.0 - np.minimum(1.0, np.abs(y_pred - np.asarray(y, dtype=np.float64)) / span)
+    return TsTRegressionResult(y_pred, s, votes_h, fold_dev.cpu().numpy(), lev, lo, step, eng.stats())
+
+
 # ------------------------------------------------------------------------------------------------- IBP
 @dataclass
 class IBPResult:
@@ -404,24 +475,29 @@ class TsTForest:
     """sklearn-like classifier over the same kernels (argument names: SK/ensemble/_forest.py:1515-1537)."""
 
     def __init__(self, n_estimators=100, max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt",
-                 n_bins=256, random_state=0, engine: Engine | None = None):
+                 n_bins=256, random_state=0, engine: Engine | None = None, criterion="gini", n_levels=32):
         self.n_estimators, self.max_depth = n_estimators, max_depth
         self.min_samples_split, self.min_samples_leaf = min_samples_split, min_samples_leaf
         self.max_features, self.n_bins, self.random_state = max_features, n_bins, random_state
+        self.criterion, self.n_levels = criterion, n_levels  # "squared_error": y is numeric, predict() returns numbers
         self._engine = engine
 
     def fit(self, X, y):
         torch = _torch()
         # a kept forest lives in its engine: use a private one unless the caller shares one
         self._eng = self._engine or Engine(torch.cuda.current_device() if torch.cuda.is_available() else 0)
-        self.classes_, yi = encode_labels(y)
+        if self.criterion == "squared_error":
+            yi, self._lo, self._step = quantise_target(y, self.n_levels)
+            self.classes_ = np.arange(self.n_levels)
+        else:
+            self.classes_, yi = encode_labels(y)
         self.n_classes_ = int(self.classes_.shape[0])
         self._eng.bin(X, n_bins=self.n_bins)
         self.n_features_in_ = self._eng.d
         y_dev = self._eng.to_dev(yi, torch.uint8)
         fold = torch.full((self._eng.n,), FOLD_TRAIN_ONLY, dtype=torch.uint8, device=self._eng.dev)
         prm = make_params(self._eng.d, self.max_depth, self.min_samples_split, self.min_samples_leaf, self.max_features,
-                          keep_forest=True)
+                          keep_forest=True, criterion=self.criterion)
         self._eng.fit_oof(y_dev, fold, 1, self.n_estimators, self.n_classes_, prm, seed=int(self.random_state or 0))
         return self
 
@@ -433,6 +509,8 @@ class TsTForest:
         return v / v.sum(axis=1, keepdims=True)
 
     def predict(self, X):
+        if self.criterion == "squared_error":
+            return votes_to_value(self.predict_votes(X), self._lo, self._step)
         return self.classes_[np.argmax(self.predict_votes(X), axis=1)]
 
     def export_tree(self, t: int):

@@ -31,6 +31,16 @@ def vsi_table(n: int = 5000, d: int = 32, n_classes: int = 4, seed: int = 0):
     return X.astype(np.float32), y
 
 
+def numeric_table(n: int = 4000, d: int = 16, seed: int = 0):
+    """Numeric-answer question type (object counts, distances ...): the same column mix as vsi_table with a positive
+    real-valued answer that a blind model can partly predict from a few columns (non-linear, heteroscedastic)."""
+    X, _ = vsi_table(n, d, 2, seed)
+    rng = np.random.default_rng(seed + 7919)
+    Z = (X - X.mean(0)) / (X.std(0) + 1e-9)
+    y = 5.0 + 2.0 * Z[:, 0] + 1.5 * (Z[:, 1] > 0.3) + Z[:, 2] * Z[:, d // 2] + 0.8 * rng.standard_normal(n)
+    return X, np.exp(0.35 * y).astype(np.float64)
+
+
 def scaleup_table(n: int = 1_000_000, d: int = 64, n_classes: int = 4, seed: int = 0):
     """Scale-up table: standard-normal float32, labels = argmax(X W + 1.5 noise), W 25 % dense."""
     rng = np.random.default_rng(seed)

@@ -58,7 +58,29 @@ def spec_vectors():
                         ibp_active=act, ibp_removed=removed, ibp_s=s_rounds)
 
 
+def spec_regression_vectors():
+    """Squared-error criterion on ordinal levels: frozen oracle output."""
+    from oracle import hist_rf as H
+    from tst import quantise_target, synth
+
+    X, y = synth.numeric_table(500, 10, seed=3)
+    lev, lo, step = quantise_target(y, 16)
+    edges, ne = H.find_edges(X)
+    bins = H.bin_table(X, edges, ne)
+    fold = H.assign_folds(lev, np.ones(len(lev), np.uint8), 3, 16)
+    prm = H.make_params(10, max_features=1.0, criterion="squared_error")
+    votes, st, forest = H.fit_oof(bins, lev, fold, 3, 5, 16, prm, seed=21, keep=True, nthreads=1)
+    t = forest.tree(1, 2)
+    np.savez_compressed(os.path.join(HERE, "spec_regression.npz"), X=X, y=y, levels=lev, lo=lo, step=step, bins=bins, fold=fold,
+                        votes=votes, tree_nodes=t.nodes, tree_counts=t.counts,
+                        stats=np.array([st[k] for k in ("row_visits", "nodes", "leaves", "searched", "fallback", "inbag_rows", "max_depth")]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "regression":
+        spec_regression_vectors()
+        sys.exit(0)
     sklearn_vectors()
     spec_vectors()
+    spec_regression_vectors()
     print("wrote", sorted(os.listdir(HERE)))

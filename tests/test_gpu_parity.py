@@ -183,12 +183,15 @@ def _edge_case_tables():
     out["const"] = (b, (b[3] > 100).astype(np.uint8) + (b[3] > 200).astype(np.uint8), 3)
     # many classes, wide table
     out["manyclass"] = (rng.integers(0, 64, (40, 900)).astype(np.uint8), rng.integers(0, 13, 900).astype(np.uint8), 13)
+    # the class limit (32): the warp-per-node tier is off (its histogram does not fit shared memory) and every
+    # node above 32 rows goes through the CTA kernel, also in the levels launched without a host round trip
+    out["maxclass"] = (rng.integers(0, 200, (12, 2500)).astype(np.uint8), rng.integers(0, 32, 2500).astype(np.uint8), 32)
     # tiny
     out["tiny"] = (rng.integers(0, 5, (2, 7)).astype(np.uint8), rng.integers(0, 2, 7).astype(np.uint8), 2)
     return out
 
 
-@pytest.mark.parametrize("name", ["lowcard", "dups", "oneclass", "const", "manyclass", "tiny"])
+@pytest.mark.parametrize("name", ["lowcard", "dups", "oneclass", "const", "manyclass", "maxclass", "tiny"])
 @pytest.mark.parametrize("pk", [dict(), dict(max_depth=3), dict(min_samples_leaf=3, min_samples_split=8), dict(max_features=None)])
 def test_edge_cases_bit_exact(eng, name, pk):
     bins, y, C = _edge_case_tables()[name]
@@ -428,6 +431,66 @@ def test_public_api_run_tst_and_forest(vsi_small):
     assert imp.shape == (16,) and abs(imp.sum() - 1.0) < 1e-9 and (imp >= 0).all()
     sk = clf.sklearn_tree(0)
     assert sk["threshold"].shape == sk["feature"].shape and np.isfinite(sk["threshold"]).all()
+
+
+# --------------------------------------------------------------------------------------------- squared-error criterion
+@pytest.mark.parametrize("n,d,L,k,mf,pk", [(3000, 10, 16, 3, 1.0, {}), (5000, 20, 32, 2, "sqrt", {}), (700, 6, 8, 4, None, {}),
+                                            (20000, 12, 32, 2, 4, {}), (2500, 9, 4, 3, 3, {}), (4000, 8, 2, 2, "sqrt", dict(max_depth=6)),
+                                            (1500, 14, 24, 3, 0.5, dict(min_samples_leaf=4, min_samples_split=10))])
+def test_squared_error_criterion_bit_exact(eng, n, d, L, k, mf, pk):
+    """Numeric answers: labels are ordinal levels, splits maximise S_L^2/N_L + S_R^2/N_R (every tier's generic kernel;
+    L <= 4 checks that the packed Gini kernels are NOT used for this criterion)."""
+    from tst import quantise_target, synth
+
+    X, y = synth.numeric_table(n, d, seed=n)
+    lev, lo, step = quantise_target(y, L)
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(lev, np.ones(n, np.uint8), k, L)
+    gv, ov, gst, ost, forest = run_both(eng, bins, lev, fold, k, 4, L, seed=3, keep=True, criterion="squared_error", max_features=mf, **pk)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    for part, t in ((0, 0), (k - 1, 3)):
+        gn, gc = eng.export_tree(part, t, L)
+        ot = forest.tree(part, t)
+        compare_tree(gn, gc, ot.nodes, ot.counts, f"regression tree({part},{t})")
+
+
+def test_squared_error_dense_root_bit_exact(eng, monkeypatch):
+    monkeypatch.setenv("TST_ROOT_DENSE", "2")
+    from tst import quantise_target, synth
+
+    X, y = synth.numeric_table(4000, 16, seed=9)
+    lev, lo, step = quantise_target(y, 20)
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(lev, np.ones(len(lev), np.uint8), 3, 20)
+    gv, ov, gst, ost, forest = run_both(eng, bins, lev, fold, 3, 4, 20, seed=1, keep=True, criterion="squared_error", max_features=6)
+    assert gst["launches_root"] > 0
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    gn, gc = eng.export_tree(1, 2, 20)
+    ot = forest.tree(1, 2)
+    compare_tree(gn, gc, ot.nodes, ot.counts, "dense-root regression tree")
+
+
+def test_regression_golden_and_public_api(eng):
+    import os
+
+    import tst
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spec_regression.npz"))
+    gv, ov, gst, ost, forest = run_both(eng, g["bins"], g["levels"], g["fold"], 3, 5, 16, seed=21, keep=True, criterion="squared_error", max_features=1.0)
+    assert np.array_equal(gv, g["votes"]) and np.array_equal(ov, g["votes"])
+    gn, gc = eng.export_tree(1, 2, 16)
+    compare_tree(gn, gc, g["tree_nodes"], g["tree_counts"], "golden regression tree")
+    # host-to-host call
+    res = tst.run_tst_regression(g["X"], g["y"], k=3, n_trees=5, seed=21, n_levels=16, engine=eng)
+    assert np.array_equal(res.fold_id, g["fold"]) and np.array_equal(res.oof_votes, g["votes"]) and np.array_equal(res.levels, g["levels"])
+    assert np.allclose(res.y_pred, tst.votes_to_value(g["votes"], float(g["lo"]), float(g["step"])))
+    assert ((res.s >= 0) & (res.s <= 1)).all()
+    # sklearn-like regressor: fully grown trees reproduce the training targets up to the quantisation step
+    reg = tst.TsTForest(n_estimators=20, criterion="squared_error", n_levels=32, max_features=1.0, random_state=2).fit(g["X"], g["y"])
+    err = np.abs(reg.predict(g["X"]) - g["y"])
+    assert np.median(err) < 2.0 * (g["y"].max() - g["y"].min()) / 32
 
 
 # --------------------------------------------------------------------------------------------- full size (BASELINE.json configs[4])

@@ -1,0 +1,139 @@
+"""Squared-error criterion on ordinal levels: CPU oracle checks.
+
+  * the root split of every tree is the arg-max of S_L^2/N_L + S_R^2/N_R over (feature, bin) on the
+    tree's own bootstrap sample, brute-forced in numpy from the restated Philox bootstrap;
+  * the frozen fixture tests/golden/spec_regression.npz;
+  * statistical agreement with sklearn's RandomForestRegressor on the same quantised target.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hist_rf as H
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def bootstrap_multiplicities(n, gid, seed):
+    """oracle/hist_rf.c:417-424 restated: n draws u = mulhi32(philox(j >> 2, 0, gid, BOOT)[j & 3], n)."""
+    k0, k1 = seed & 0xFFFFFFFF, seed >> 32
+    mult = np.zeros(n, dtype=np.int64)
+    for j0 in range(0, n, 4):
+        r = H.philox([j0 >> 2, 0, gid, 1], [k0, k1])
+        for q in range(min(4, n - j0)):
+            mult[(int(r[q]) * n) >> 32] += 1
+    return mult
+
+
+def brute_force_root(bins, lev, w, C):
+    """Best (proxy, feature, bin) over all candidate thresholds; ties -> lowest feature, then lowest bin."""
+    d, n = bins.shape
+    best = None
+    N, S = int(w.sum()), int((w * lev).sum())
+    for f in range(d):
+        b = bins[f]
+        for thr in np.unique(b[w > 0])[:-1]:
+            left = (b <= thr) & (w > 0)
+            NL, SL = int(w[left].sum()), int((w[left] * lev[left]).sum())
+            NR, SR = N - NL, S - SL
+            g = (float(SL) * float(SL)) / float(NL) + (float(SR) * float(SR)) / float(NR)
+            if best is None or g > best[0]:
+                best = (g, f, int(thr))
+    return best
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_root_split_is_the_squared_error_argmax(seed):
+    from tst import quantise_target, synth
+
+    X, y = synth.numeric_table(300, 6, seed=seed)
+    lev, lo, step = quantise_target(y, 12)
+    edges, ne = H.find_edges(X, 32)
+    bins = H.bin_table(X, edges, ne)
+    fold = np.full(len(lev), H.FOLD_TRAIN_ONLY, np.uint8)
+    prm = H.make_params(6, max_depth=1, max_features=None, criterion="squared_error")
+    _, st, forest = H.fit_oof(bins, lev, fold, 1, 5, 12, prm, seed=seed, keep=True, nthreads=1)
+    for t in range(5):
+        tr = forest.tree(0, t)
+        w = bootstrap_multiplicities(len(lev), t, seed)  # gid = part * n_trees + t = t
+        assert np.array_equal(tr.counts[0], np.bincount(lev, weights=w, minlength=12).astype(np.uint32))
+        g, f, b = brute_force_root(bins, lev.astype(np.int64), w, 12)
+        assert (int(tr.nodes["feature"][0]), int(tr.nodes["bin"][0])) == (f, b), (seed, t)
+
+
+def test_gini_and_squared_error_differ_only_in_the_criterion():
+    """Two levels: Gini and squared error rank splits identically in exact arithmetic (N - 2 T1 + 2 (L1^2/NL + R1^2/NR));
+    the trees agree except where fp64 rounding breaks a tie differently -> identical vote totals per row, near-identical votes."""
+    from tst import synth
+
+    X, y = synth.vsi_table(600, 8, 2, seed=4)
+    edges, ne = H.find_edges(X)
+    bins = H.bin_table(X, edges, ne)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 3, 2)
+    va, _, _ = H.fit_oof(bins, y, fold, 3, 20, 2, H.make_params(8), seed=2)
+    vb, _, _ = H.fit_oof(bins, y, fold, 3, 20, 2, H.make_params(8, criterion="squared_error"), seed=2)
+    pa = va[:, 1] / va.sum(1)
+    pb = vb[:, 1] / vb.sum(1)
+    assert np.corrcoef(pa, pb)[0, 1] > 0.98
+
+
+def test_regression_spec_frozen():
+    g = np.load(os.path.join(GOLD, "spec_regression.npz"))
+    from tst import quantise_target
+
+    lev, lo, step = quantise_target(g["y"], 16)
+    assert np.array_equal(lev, g["levels"]) and lo == float(g["lo"]) and step == float(g["step"])
+    edges, ne = H.find_edges(g["X"])
+    bins = H.bin_table(g["X"], edges, ne)
+    assert np.array_equal(bins, g["bins"])
+    fold = H.assign_folds(lev, np.ones(len(lev), np.uint8), 3, 16)
+    assert np.array_equal(fold, g["fold"])
+    prm = H.make_params(10, max_features=1.0, criterion="squared_error")
+    votes, st, forest = H.fit_oof(bins, lev, fold, 3, 5, 16, prm, seed=21, keep=True, nthreads=2)
+    assert np.array_equal(votes, g["votes"])
+    t = forest.tree(1, 2)
+    assert np.array_equal(t.nodes, g["tree_nodes"]) and np.array_equal(t.counts, g["tree_counts"])
+    assert [st[k] for k in ("row_visits", "nodes", "leaves", "searched", "fallback", "inbag_rows", "max_depth")] == g["stats"].tolist()
+
+
+def test_out_of_fold_r2_close_to_sklearn_regressor():
+    """Same procedure with sklearn's RandomForestRegressor on the quantised target (level centres): the
+    out-of-fold R^2 must be within 0.05 of sklearn's (printed next to it)."""
+    from sklearn.ensemble import RandomForestRegressor
+    from tst import quantise_target, synth, votes_to_value
+
+    X, y = synth.numeric_table(1500, 12, seed=1)
+    L = 32
+    lev, lo, step = quantise_target(y, L)
+    yq = lo + (lev + 0.5) * step
+    edges, ne = H.find_edges(X)
+    bins = H.bin_table(X, edges, ne)
+    k, T = 4, 60
+    fold = H.assign_folds(lev, np.ones(len(lev), np.uint8), k, L)
+    prm = H.make_params(12, max_features=1.0, criterion="squared_error")
+    votes, _, _ = H.fit_oof(bins, lev, fold, k, T, L, prm, seed=5)
+    ours = votes_to_value(votes, lo, step)
+    sk = np.zeros_like(ours)
+    for f in range(k):
+        tr, te = fold != f, fold == f
+        rf = RandomForestRegressor(n_estimators=T, max_features=1.0, random_state=f, n_jobs=2).fit(X[tr], yq[tr])
+        sk[te] = rf.predict(X[te])
+
+    def r2(p):
+        return 1.0 - ((p - yq) ** 2).sum() / ((yq - yq.mean()) ** 2).sum()
+
+    print(f"out-of-fold R2: ours {r2(ours):.4f}  sklearn {r2(sk):.4f}  corr {np.corrcoef(ours, sk)[0, 1]:.4f}")
+    assert r2(ours) > r2(sk) - 0.05
+    assert np.corrcoef(ours, sk)[0, 1] > 0.95
+
+
+def test_criterion_is_validated():
+    with pytest.raises(KeyError):
+        H.make_params(4, criterion="entropy")
+    import tst
+
+    with pytest.raises(ValueError):
+        tst.make_params(4, criterion="entropy")
+    with pytest.raises(ValueError):
+        tst.quantise_target([1.0, 2.0], 64)
