@@ -53,6 +53,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None  # the timed region; only the samples that arrive inside it are summarised
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
@@ -66,7 +73,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -79,7 +86,9 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t0 is not None and (ts < self.t0 or (self.t1 is not None and ts > self.t1 + 0.3)):
+                continue  # nvidia-smi is started before the warm-up so that its start-up does not fall into the timed region
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -226,18 +235,20 @@ def main():
         total = eng.allreduce_votes(votes)
         return eng.finalize(total, y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES)
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    eng.stats(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
+        for i in range(args.warmup):
+            step(i)
         barrier()
+        eng.stats(reset=True)
+        barrier()
+        clk.mark_start()
         ev0.record()
         for i in range(args.steps):
             s_dev, _, _ = step(args.warmup + i)
         ev1.record()
         barrier()
+        clk.mark_end()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     st = eng.stats()
     trees_per_rank = int(st["trees"])
@@ -298,12 +309,11 @@ def main():
                 max_depth=int(st["max_depth"]))
 
     if rank == 0 and world == 1:
-        if not args.no_cpu:
-            bins_cm = eng.get_bins()
-            fold_h = fold_dev.cpu().numpy()
-            line["cpu_baseline"], _ = cpu_baseline_port(X, yi, bins_cm, fold_h)
-        if not args.no_secondary:
+        bins_cm, fold_h = (eng.get_bins(), fold_dev.cpu().numpy()) if not args.no_cpu else (None, None)
+        if not args.no_secondary:  # before the CPU leg: idle OpenMP workers spin for a while and disturb millisecond latencies
             line["secondary"] = secondary_wallclock(tst, synth, eng)
+        if not args.no_cpu:
+            line["cpu_baseline"], _ = cpu_baseline_port(X, yi, bins_cm, fold_h)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

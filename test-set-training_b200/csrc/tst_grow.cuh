@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 
         // ---- class histogram: hist[j][bin][class] += multiplicity (SK/.../histogram.pyx:336-425 pattern)
         if (use_tile && nb <= 8) {
-            uint2* stash_w = (!BIG_TMA_RING && g.stash != nullptr && pos == 0) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
+            uint2* stash_w = (!BIG_TMA_RING && g.stash != nullptr && pos == 0 && t.end - t.begin <= g.stash_max_rows) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
             uint32_t featr[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) featr[jj] = jj < nb ? s_feat[jj] : 0u;
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                     uint32_t key = (s_feat[j] << 8) | s_fbin[j];  // ties: lowest feature, then lowest bin
                     if (s_fgain[j] > s_bgain || (s_fgain[j] == s_bgain && key < s_bkey)) {
                         s_bgain = s_fgain[j]; s_bkey = key; s_newj = j; s_found = 1;
-                        s_sj = (!BIG_TMA_RING && pos == 0 && g.stash != nullptr && use_tile && nb <= 8) ? (uint32_t)j : 0xFFFFFFFFu;
+                        s_sj = (!BIG_TMA_RING && pos == 0 && g.stash != nullptr && use_tile && nb <= 8 && t.end - t.begin <= g.stash_max_rows) ? (uint32_t)j : 0xFFFFFFFFu;
                     }
                 }
             } else {

@@ -270,6 +270,22 @@ def test_dense_root_kernels_bit_exact(eng, monkeypatch, n, d, C, k):
     check_stats(gst, ost)
 
 
+def test_partition_stash_option_bit_exact(eng, monkeypatch):
+    """TST_STASH=1: k_grow_big keeps the sampled bins of every row for its partition pass (off by default)."""
+    from tst import synth
+
+    monkeypatch.setenv("TST_STASH", "1")
+    X, y = synth.vsi_table(30000, 24, 4, seed=8)
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 2, 4)
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, 2, 3, 4, seed=4, keep=True)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    gn, gc = eng.export_tree(1, 2, 4)
+    ot = forest.tree(1, 2)
+    compare_tree(gn, gc, ot.nodes, ot.counts, "stash tree")
+
+
 @pytest.mark.parametrize("d,C,mf", [(100, 3, "sqrt"), (200, 4, "sqrt"), (130, 6, 40), (70, 2, None)])
 def test_wide_tables_bit_exact(eng, d, C, mf):
     """d > 64: rows wider than the shared row tile (byte-gather path), more than 8 sampled features per node
