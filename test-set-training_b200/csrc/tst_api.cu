@@ -518,6 +518,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.big_tile = h->dstride <= 64 ? 1 : 0;  // cooperative whole-row fetch into a shared tile (rows of <= 64 bytes)
     const size_t big_tile_bytes = g.big_tile ? (size_t)BIG_THREADS * ((h->dstride >> 2) + 1) * 4 : 0;
     g.big_tma = 1;
+    g.big_packed = 1;
+    if (const char* ev = getenv("TST_BIG_PACKED")) g.big_packed = atoi(ev) != 0;
     if (const char* ev = getenv("TST_BIG_TMA")) g.big_tma = atoi(ev) != 0;
     // Option (TST_STASH=1, off by default): the histogram pass of k_grow_big leaves the m sampled bins of every row in a
     // stash (8 bytes per row, coalesced) so that its partition pass does not gather the split feature's byte from the

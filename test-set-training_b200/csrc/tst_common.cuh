@@ -154,6 +154,7 @@ struct GrowCtx {
     uint32_t tiny_max; // 0 disables the tier
     DevStats* stats;
     const RootSplit* rsplit;  // non-null: big roots were split by the dense root kernels (Task.pad0 == 1)
+    uint32_t big_packed;  // k_grow_big: packed 16-bit histogram + scan for nodes that weigh < 2^16 (<= 4 classes, m <= 8)
     uint32_t stash_max_rows;  // nodes above this size gather instead: their stash would stream through HBM (the table itself is L2-resident)
     uint2* stash;             // non-null: [tree][n_cap] the m <= 8 sampled bins of each row, written by the histogram pass of k_grow_big for its partition pass
     int32_t big_tile; // k_grow_big stages whole rows in shared memory (dstride <= 128)

@@ -61,7 +61,8 @@ __device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint
         } else {
             Task ct;
             ct.tree = t.tree; ct.begin = cb; ct.end = ce; ct.depth = t.depth + 1u; ct.slot = cslot;
-            ct.pad0 = ct.pad1 = ct.pad2 = 0;
+            ct.pad0 = ct.pad2 = 0;
+            ct.pad1 = Nc;  // the node's weight: k_grow_big picks its packed path from it
             const uint32_t cr = ce - cb;
             if (cr <= g.tiny_max) tiny_push(g, t.tree, cb, cr, t.depth + 1u, cslot);
             else if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
@@ -157,6 +158,78 @@ __device__ __forceinline__ void scan_feature(const uint32_t* __restrict__ hf, in
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same scan for a node that weighs < 2^16 with <= 4 classes, on a PACKED histogram: a cell is two words holding
+// four 16-bit class counts, lane l owns bins [8l, 8l+8) in an 80-byte segment (conflict-free 128-bit reads), one 64-bit
+// shuffle chain scans all classes, sums of squares fit 32 bits.  ~2.4x fewer instructions than scan_feature_t; the
+// small nodes of the CTA tier (levels 8+ of a 1M-row tree) spend 40 % of their instructions in the scan.
+#define BIGP_FS 640u  // words per feature of the packed histogram: 32 lanes x (8 bins x 2 words + 4 pad)
+__device__ __forceinline__ void scan_feature_packed4(const uint32_t* __restrict__ hf, uint32_t msl, uint32_t lane, double& best_gain,
+                                                     uint32_t& best_bin, uint32_t& bestP0, uint32_t& bestP1, uint32_t& T0, uint32_t& T1) {
+    const uint4* hl = (const uint4*)(hf + lane * 20u);
+    uint32_t p0[8], p1[8], run0 = 0, run1 = 0, occ = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint4 hq = hl[q >> 1];
+        const uint32_t h0 = (q & 1) ? hq.z : hq.x, h1 = (q & 1) ? hq.w : hq.y;
+        occ |= ((h0 | h1) ? 1u : 0u) << q;
+        run0 += h0; run1 += h1;
+        p0[q] = run0; p1[q] = run1;
+    }
+    const unsigned long long run = (unsigned long long)run0 | ((unsigned long long)run1 << 32);
+    unsigned long long incl = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long a = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= (uint32_t)off) incl += a;
+    }
+    const unsigned long long excl = incl - run, tot = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t e0 = (uint32_t)excl, e1 = (uint32_t)(excl >> 32);
+    T0 = (uint32_t)tot; T1 = (uint32_t)(tot >> 32);
+    const uint32_t t0 = T0 & 0xFFFFu, t1 = T0 >> 16, t2 = T1 & 0xFFFFu, t3 = T1 >> 16, N = t0 + t1 + t2 + t3;
+    float ge[8], lmax = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        ge[q] = -1.0f;
+        if ((occ >> q) & 1u) {
+            const uint32_t P0 = e0 + p0[q], P1 = e1 + p1[q];
+            const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
+            const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+            if (NL >= msl && NR >= msl) {
+                const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
+                const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+                ge[q] = gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR));
+                lmax = fmaxf(lmax, ge[q]);
+            }
+        }
+    }
+    const float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lmax))) * TST_EST_MARGIN;
+    double bg = -1.0;
+    uint32_t bb = 0xFFFFFFFFu, bP0 = 0, bP1 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (ge[q] >= thr) {
+            const uint32_t P0 = e0 + p0[q], P1 = e1 + p1[q];
+            const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
+            const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+            const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
+            const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+            const double gn = gini_gain(SL, NL, SR, NR);
+            if (gn > bg) { bg = gn; bb = lane * 8u + q; bP0 = P0; bP1 = P1; }  // ascending bins: strict > keeps the lowest
+        }
+    }
+    double wg = bg;
+    uint32_t wb = bb;
+    warp_argmax_redux(wg, wb);
+    if (wb != 0xFFFFFFFFu) {
+        const uint32_t winner = __ffs(__ballot_sync(0xffffffffu, bb == wb && bg == wg)) - 1;
+        bestP0 = __shfl_sync(0xffffffffu, bP0, winner);
+        bestP1 = __shfl_sync(0xffffffffu, bP1, winner);
+    }
+    best_gain = wg;
+    best_bin = wb;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Warp-cooperative fetch of 32 binned rows (row-major table, `dstride` bytes each) into a shared tile.
 // Lane l owns row l of the tile; 16-byte pieces of a row are loaded by neighbouring lanes in ONE
 // instruction, so a 64-byte row costs one L1 wavefront and two L2 sectors instead of one sector per
@@ -213,7 +286,8 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
 template <int THREADS, bool MSE = false>  // MSE: squared-error criterion on ordinal levels (its own instantiation: the Gini one keeps its registers)
 __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     constexpr int NW = THREADS / 32;
-    extern __shared__ uint32_t s_hist[];  // [MB][FS] histogram, then (row tile) [THREADS][dstride/4 + 1]
+    extern __shared__ __align__(16) uint32_t s_hist[];  // [MB][FS] histogram, then (row tile) [THREADS][dstride/4 + 1]
+    __shared__ uint32_t s_fL[8][4];  // packed nodes: left class counts of each feature's best split
     __shared__ uint16_t s_perm[TST_MAX_FEATURES];
     __shared__ uint32_t s_tot[TST_MAX_CLASSES];
     __shared__ uint32_t s_bestL[TST_MAX_CLASSES];
@@ -246,6 +320,9 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     const uint8_t* __restrict__ bins = g.bins_rm;
     const uint32_t dstride = g.dstride;
     const bool use_tile = g.big_tile != 0;
+    // a node that weighs < 2^16 (its parent wrote the weight into the task) uses the packed histogram and scan
+    const bool packed = !MSE && g.big_packed != 0u && use_tile && C <= 4 && g.MB <= 8 && t.pad1 != 0u && t.pad1 <= 65535u;
+    const uint32_t HFS = packed ? BIGP_FS : (uint32_t)g.FS;  // histogram words per feature
     const uint32_t pitch = (dstride >> 2) + 1u;
     uint32_t* s_tile = s_hist + g.MB * g.FS + wid * 32u * pitch;  // this warp's rows
 
@@ -295,7 +372,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
             s_newj = 0xFFFFFFFFu;
             if (pos == m) atomicAdd(&g.stats->fallback, 1ull);
         }
-        for (int i = tid; i < nb * g.FS; i += THREADS) s_hist[i] = 0;
+        for (int i = tid; i < nb * (int)HFS; i += THREADS) s_hist[i] = 0;
         __syncthreads();
 
         // ---- class histogram: hist[j][bin][class] += multiplicity (SK/.../histogram.pyx:336-425 pattern)
@@ -348,13 +425,24 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                 if (e.y) {
                     const uint32_t cls = ent_cls(e), w = ent_w(e);
                     uint32_t sb0 = 0, sb1 = 0;  // the row's sampled bins, byte jj = feature jj of the draw
+                    if (packed) {
+                        const uint32_t coff = cls >> 1, val = w << (16u * (cls & 1u));
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj)
-                        if (jj < nb) {
-                            const uint32_t bj = trow[featr[jj]];
-                            if (jj < 4) sb0 |= bj << (8 * jj); else sb1 |= bj << (8 * (jj - 4));
-                            atomicAdd(&s_hist[jj * g.FS + hist_index(bj, cls, C)], w);
-                        }
+                        for (int jj = 0; jj < 8; ++jj)
+                            if (jj < nb) {
+                                const uint32_t bj = trow[featr[jj]];
+                                if (jj < 4) sb0 |= bj << (8 * jj); else sb1 |= bj << (8 * (jj - 4));
+                                atomicAdd(&s_hist[jj * BIGP_FS + (bj >> 3) * 20u + (bj & 7u) * 2u + coff], val);
+                            }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj)
+                            if (jj < nb) {
+                                const uint32_t bj = trow[featr[jj]];
+                                if (jj < 4) sb0 |= bj << (8 * jj); else sb1 |= bj << (8 * (jj - 4));
+                                atomicAdd(&s_hist[jj * g.FS + hist_index(bj, cls, C)], w);
+                            }
+                    }
                     if (stash_w) __stcg(stash_w + (base + tid), make_uint2(sb0, sb1));
                 }
                 __syncwarp();
@@ -388,7 +476,19 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
         for (int j = wid; j < nb; j += NW) {
             double bg; uint32_t bb;
             bool want_tot = (pos == 0 && j == 0);
-            scan_feature_t<MSE>(s_hist + j * g.FS, C, g.msl, lane, bg, bb, want_tot ? s_tot : nullptr, want_tot ? &s_N : nullptr);
+            if (packed) {
+                uint32_t P0 = 0, P1 = 0, T0, T1;
+                scan_feature_packed4(s_hist + j * BIGP_FS, g.msl, lane, bg, bb, P0, P1, T0, T1);
+                if (lane == 0) {
+                    s_fL[j][0] = P0 & 0xFFFFu; s_fL[j][1] = P0 >> 16; s_fL[j][2] = P1 & 0xFFFFu; s_fL[j][3] = P1 >> 16;
+                    if (want_tot) {
+                        s_tot[0] = T0 & 0xFFFFu; s_tot[1] = T0 >> 16; s_tot[2] = T1 & 0xFFFFu; s_tot[3] = T1 >> 16;
+                        s_N = (T0 & 0xFFFFu) + (T0 >> 16) + (T1 & 0xFFFFu) + (T1 >> 16);
+                    }
+                }
+            } else {
+                scan_feature_t<MSE>(s_hist + j * g.FS, C, g.msl, lane, bg, bb, want_tot ? s_tot : nullptr, want_tot ? &s_N : nullptr);
+            }
             if (lane == 0) { s_fgain[j] = bg; s_fbin[j] = bb; }
         }
         __syncthreads();
@@ -415,9 +515,11 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                 }
             }
         }
+        if (tid == 0 && packed && s_newj != 0xFFFFFFFFu)
+            for (int c = 0; c < C; ++c) s_bestL[c] = s_fL[s_newj][c];
         __syncthreads();
         if (s_stop) break;
-        if (s_newj != 0xFFFFFFFFu) {
+        if (s_newj != 0xFFFFFFFFu && !packed) {
             // left class counts of the new best split, kept because the histogram may be overwritten
             const uint32_t bb = s_bkey & 0xFFu;
             const uint32_t* hl = s_hist + s_newj * g.FS + lane * (8u * C + 1u);
