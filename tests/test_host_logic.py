@@ -27,6 +27,35 @@ def test_library_exports_every_declared_symbol():
     assert L.tst_abi_version() == 1
 
 
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The ctypes mirrors in tst/_lib.py must have the size and field offsets gcc gives include/tst.h."""
+    import subprocess
+
+    from tst import _lib
+
+    prog = tmp_path / "layout.c"
+    fields_p = [n for n, _ in _lib.Params._fields_]
+    fields_s = [n for n, _ in _lib.Stats._fields_]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "tst.h"', 'int main(void) {',
+             'printf("%zu %zu %zu\\n", sizeof(tst_params), sizeof(tst_stats), sizeof(tst_node));']
+    lines += [f'printf("p {f} %zu\\n", offsetof(tst_params, {f}));' for f in fields_p]
+    lines += [f'printf("s {f} %zu\\n", offsetof(tst_stats, {f}));' for f in fields_s]
+    lines += ['return 0; }']
+    prog.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(prog)])
+    out = subprocess.check_output([str(exe)], text=True).splitlines()
+    sp, ss, sn = map(int, out[0].split())
+    assert sp == ctypes.sizeof(_lib.Params) and ss == ctypes.sizeof(_lib.Stats)
+    for l in out[1:]:
+        kind, name, off = l.split()
+        cls = _lib.Params if kind == "p" else _lib.Stats
+        assert getattr(cls, name).offset == int(off), (kind, name)
+    from oracle import hist_rf as H
+
+    assert sn == H.NODE_DTYPE.itemsize  # tst_export_tree fills the oracle's node layout
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device every entry point must fail loudly -- never route through the oracle."""
     import torch
