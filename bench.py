@@ -61,7 +61,30 @@ class ClockSampler:
     def mark_end(self):
         self.t1 = time.time()
 
+    def _nvml_loop(self):
+        import pynvml as N
+
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        names = [("hw_slowdown", N.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksThrottleReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", N.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksThrottleReasonSwPowerCap)]
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        while not self.stop.is_set():
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            pw = N.nvmlDeviceGetPowerUsage(h) / 1e3
+            r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append((time.time(), [str(sm), str(mx), str(pw)] + ["Active" if r & bit else "Not Active" for _, bit in names]))
+            self.stop.wait(0.25)
+
     def __enter__(self):
+        self.mode = os.environ.get("TST_BENCH_CLOCKS", "smi")  # smi = the recipe's nvidia-smi -lms loop; nvml = same counters in-process; off
+        if self.mode == "off":
+            return self
+        if self.mode == "nvml":
+            self.stop = threading.Event()
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,6 +99,8 @@ class ClockSampler:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
+        if getattr(self, "stop", None) is not None:
+            self.stop.set()
         if self.proc:
             self.proc.terminate()
             try:
