@@ -203,6 +203,8 @@ static int set_kernel_attrs(tst_handle* h) {
     CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid<4, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid<2, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_root_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_root_split, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -562,7 +564,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const bool mid_packed = packed_ok;  // packed 16-bit class counts (k_grow_mid4)
     const uint32_t mid_per_warp = mid_packed ? ((MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                              : (uint32_t)g.FS + 2u * (uint32_t)C + (uint32_t)((d + 1) / 2);
-    const size_t mid_smem = (size_t)MID_WARPS * mid_per_warp * 4;
+    // warps per CTA of the warp-per-node tier: 8, or fewer when the unpacked histograms of many classes would not fit
+    int mid_warps = MID_WARPS;
+    if (!mid_packed) while (mid_warps > 2 && (size_t)mid_warps * mid_per_warp * 4 > 200 * 1024) mid_warps >>= 1;
+    const size_t mid_smem = (size_t)mid_warps * mid_per_warp * 4;
     g.mid_max = mid_smem <= 200 * 1024 ? 32u * MID_R : SMALL_MAX;
     g.mid_packed = mid_packed ? 1u : 0u;
     if (const char* ev = getenv("TST_MID_MAX")) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)atoi(ev)));
@@ -660,7 +665,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 CK(cudaEventRecord(h->ev_lvl[j][1], st));
                 if (gm) {
                     if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
-                    else k_grow_mid<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
+                    else if (mid_warps == 8) k_grow_mid<8, MID_R><<<(gm + 7) / 8, 256, mid_smem, st>>>(g, qmcur, gm, cm);
+                    else if (mid_warps == 4) k_grow_mid<4, MID_R><<<(gm + 3) / 4, 128, mid_smem, st>>>(g, qmcur, gm, cm);
+                    else k_grow_mid<2, MID_R><<<(gm + 1) / 2, 64, mid_smem, st>>>(g, qmcur, gm, cm);
                     CKL();
                     h->stats.kernel_launches++; h->stats.launches_grow_mid++;
                 }

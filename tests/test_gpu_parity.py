@@ -183,8 +183,7 @@ def _edge_case_tables():
     out["const"] = (b, (b[3] > 100).astype(np.uint8) + (b[3] > 200).astype(np.uint8), 3)
     # many classes, wide table
     out["manyclass"] = (rng.integers(0, 64, (40, 900)).astype(np.uint8), rng.integers(0, 13, 900).astype(np.uint8), 13)
-    # the class limit (32): the warp-per-node tier is off (its histogram does not fit shared memory) and every
-    # node above 32 rows goes through the CTA kernel, also in the levels launched without a host round trip
+    # the class limit (32): the warp-per-node tier runs with 2 warps per CTA (its unpacked histograms are 33 KB each)
     out["maxclass"] = (rng.integers(0, 200, (12, 2500)).astype(np.uint8), rng.integers(0, 32, 2500).astype(np.uint8), 32)
     # tiny
     out["tiny"] = (rng.integers(0, 5, (2, 7)).astype(np.uint8), rng.integers(0, 2, 7).astype(np.uint8), 2)
