@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 // into a shared list and spread evenly over the lanes, so the fp64 gain is evaluated ~rows/32 times
 // per lane instead of 8.  The next feature's bins are prefetched while the current one is scanned.
 #define MID4_HIST 640u   // 32 lanes x (8 bins x 2 words + 4 pad): 80-byte lane segments, conflict-free 128-bit access
-#define MID4_CAND 1024u  // 256 candidates x (P0 | P1 | bin | gain estimate), structure of arrays
+#define MID4_CAND 1024u  // 256 candidates: (P0, P1) pairs [0, 512) | bin [512, 768) | gain estimate [768, 1024)
 
 #ifndef MID_MINB
 #define MID_MINB 3
@@ -296,8 +296,7 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
 #pragma unroll
             for (int q = 0; q < 8; ++q)
                 if ((occ >> q) & 1u) {
-                    s_cand[j] = e0 + p0[q];
-                    s_cand[256u + j] = e1 + p1[q];
+                    ((uint2*)s_cand)[j] = make_uint2(e0 + p0[q], e1 + p1[q]);  // one 64-bit store for both packed words
                     s_cand[512u + j] = lane * 8u + q;
                     ++j;
                 }
@@ -307,7 +306,8 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         // pass 1: fp32 estimates (a node here weighs < 2^16, so the sums of squares fit 32 bits)
         float lmax = 0.0f;
         for (uint32_t j = lane; j < n_cand; j += 32) {
-            const uint32_t P0 = s_cand[j], P1 = s_cand[256u + j];
+            const uint2 PP = ((const uint2*)s_cand)[j];
+            const uint32_t P0 = PP.x, P1 = PP.y;
             const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
             const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
             float ge = -1.0f;
@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         uint32_t bb = 0xFFFFFFFFu, bP0 = 0, bP1 = 0;
         for (uint32_t j = lane; j < n_cand; j += 32) {
             if (__uint_as_float(s_cand[768u + j]) >= thr) {
-                const uint32_t P0 = s_cand[j], P1 = s_cand[256u + j], bin = s_cand[512u + j];
+                const uint2 PP = ((const uint2*)s_cand)[j];
+                const uint32_t P0 = PP.x, P1 = PP.y, bin = s_cand[512u + j];
                 const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
                 const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
                 const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
