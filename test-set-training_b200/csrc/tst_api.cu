@@ -489,8 +489,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->qmid0, B * qbig_per * sizeof(Task));
     ENSURE(h->qmid1, B * qbig_per * sizeof(Task));
     ENSURE(h->qsmall, B * qsmall_per * sizeof(Task));
-    ENSURE(h->qtiny, B * qtiny_per * 16);
-    ENSURE(h->qtiny2, B * qtiny_per * 16);
+    // every warp of k_grow_small4 may leave up to TINY_RESERVE - 1 reserved slots unused
+    const uint64_t qtiny_slack = (uint64_t)h->sm_count * 64u * SMALL_WARPS * TINY_RESERVE;
+    ENSURE(h->qtiny, (B * qtiny_per + qtiny_slack) * 16);
+    ENSURE(h->qtiny2, (B * qtiny_per + qtiny_slack) * 16);
     ENSURE(h->infer_parts, (size_t)n_groups * k * sizeof(InferPart));
     uint2* nodes_p; uint32_t* leafc_p;
     if (keep) {
@@ -585,7 +587,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         CK(cudaMemcpyAsync(h->trees.p, all.data() + b0, (size_t)nb * sizeof(TreeDesc), cudaMemcpyHostToDevice, st));
         g.qbig_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qbig_per);
         g.qsmall_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qsmall_per);
-        g.qtiny_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qtiny_per);
+        g.qtiny_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qtiny_per + qtiny_slack);
 
         // ---- bootstrap + compaction
         CK(cudaEventRecord(h->ev0, st));

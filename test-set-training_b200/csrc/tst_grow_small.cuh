@@ -32,6 +32,7 @@ __device__ __forceinline__ void warp_argmax(double& gn, uint32_t& key) {
 #ifndef SMALL_MINB
 #define SMALL_MINB 8
 #endif
+#define TINY_RESERVE 8u  // tiny-queue slots a warp of k_grow_small4 reserves per atomic
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     extern __shared__ __align__(16) uint32_t s_mem[];
@@ -46,6 +47,11 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
     const uint8_t* __restrict__ bins = g.bins_rm;
     const uint32_t dstride = g.dstride;
 
+    // Work counters and tiny-task slots are kept per warp across its tasks: one atomic per 8 pushed tasks and six at
+    // the end instead of one per push / six per task (the queue counter is a single contended address).
+    unsigned long long visits = 0, n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0;
+    uint32_t maxd = 0;
+    uint32_t res_i = 0, res_end = 0;  // lane 0: reserved tiny-queue slots [res_i, res_end)
     for (uint32_t ti = blockIdx.x * WARPS + warp; ti < ntasks; ti += gridDim.x * WARPS) {
         const Task t = tasks[ti];
         const TreeDesc td = g.trees[t.tree];
@@ -55,8 +61,6 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
         const uint32_t r = t.end - t.begin;
         Entry e = lane < r ? ent_load(ent + t.begin + lane) : make_uint2(0u, 0u);
         uint32_t lo = 0, hi = r, depth = t.depth, slot = t.slot, sp = 0;
-        unsigned long long visits = 0, n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0;
-        uint32_t maxd = 0;
         while (true) {
             const bool active = lane >= lo && lane < hi;
             const uint32_t rr = hi - lo;
@@ -71,7 +75,12 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                 // hand the node to the thread-per-subtree tier: park its rows in the entry buffer of its depth
                 Entry* eb = ((depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
                 if (active) ent_store(eb + t.begin + lane, e);
-                if (lane == 0) tiny_push(g, t.tree, abs_begin, rr, depth, slot);
+                if (lane == 0) {
+                    if (res_i == res_end) { res_i = atomicAdd(g.qtiny_count, TINY_RESERVE); res_end = res_i + TINY_RESERVE; }
+                    if (res_i < g.qtiny_cap) ((uint4*)g.qtiny)[res_i] = make_uint4(abs_begin, slot, depth, t.tree | (rr << 16));
+                    else g.stats->error = 2;
+                    ++res_i;
+                }
                 if (sp == 0) break;
                 --sp;
                 uint32_t lh = s_stack[sp * 3];
@@ -230,7 +239,12 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
             depth += 1u;
             slot += 1u;
         }
-        if (lane == 0) {
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (; res_i < res_end; ++res_i)  // unused reserved slots become empty tasks (0 rows): sorted last, skipped by k_grow_tiny4
+            if (res_i < g.qtiny_cap) ((uint4*)g.qtiny)[res_i] = make_uint4(0u, 0u, 0u, 0u);
+        if (n_nodes) {
             atomicAdd(&g.stats->row_visits_small, visits);
             atomicAdd(&g.stats->nodes, n_nodes);
             atomicAdd(&g.stats->leaves, n_leaves);
@@ -238,6 +252,5 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
             if (n_fb) atomicAdd(&g.stats->fallback, n_fb);
             atomicMax(&g.stats->max_depth, maxd);
         }
-        __syncwarp();
     }
 }

@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(128) k_grow_tiny4(GrowCtx g, const uint4* __re
     const uint32_t dstride = g.dstride;
     unsigned long long visits = 0;
     uint32_t n_nodes = 0, n_leaves = 0, n_search = 0, n_fb = 0, maxd = 0;
-    if (live) {
-        const uint4 tk = tasks[ti];
+    uint4 tk = make_uint4(0u, 0u, 0u, 0u);
+    if (live) tk = tasks[ti];
+    if (live && (tk.w >> 16) != 0u) {  // 0 rows: an unused slot of a warp's reservation in k_grow_small4
         const uint32_t tree = tk.w & 0xFFFFu, r = tk.w >> 16;
         const uint32_t gid = g.trees[tree].gid, arena = g.trees[tree].arena;
         const Entry* __restrict__ ent = ((tk.z & 1u) ? g.entB : g.entA) + (uint64_t)tree * g.n_cap + tk.x;
