@@ -151,3 +151,53 @@ def test_random_small_tables(n, d, C, card, k, seed, msl):
             check_tree_invariants(forest.tree(p, t), C)
     if k > 1:
         assert (votes.sum(1) <= 2 * 65536).all()
+
+
+# --------------------------------------------------------------------------------------------- fp32 gain estimate (tst_common.cuh)
+def _f32(x):
+    return np.asarray(x, dtype=np.float64).astype(np.float32)
+
+
+def _estimate_gini(SL, NL, SR, NR):
+    """tst_common.cuh: gain_estimate restated in IEEE float32 (numpy), the division exact-then-rounded."""
+    SLf, NLf, SRf, NRf = _f32(SL), _f32(NL), _f32(SR), _f32(NR)
+    t = (SRf * NLf).astype(np.float32)
+    num = _f32(SLf.astype(np.float64) * NRf.astype(np.float64) + t.astype(np.float64))  # fmaf: one rounding
+    den = (NLf * NRf).astype(np.float32)
+    return (num / den).astype(np.float32)
+
+
+def _estimate_mse(SL, NL, SR, NR):
+    SLf, NLf, SRf, NRf = _f32(SL), _f32(NL), _f32(SR), _f32(NR)
+    a = (SLf / NLf).astype(np.float32)
+    b = (SRf / NRf).astype(np.float32)
+    t = (SRf * b).astype(np.float32)
+    return _f32(SLf.astype(np.float64) * a.astype(np.float64) + t.astype(np.float64))
+
+
+@pytest.mark.parametrize("scale", [6, 200, 60000, 5_000_000, 2_000_000_000])
+def test_gain_estimate_error_is_far_inside_the_margin(scale):
+    """The CUDA split search evaluates the exact fp64 gain only for candidates whose fp32 estimate is within
+    TST_EST_MARGIN = 1 - 2^-18 of the best estimate.  That is only sound if the estimate's relative error is well
+    below 2^-19; the arithmetic bound is 2^-21 (+ 2 ulp = 2^-22 for __fdividef's reciprocal, CUDA C Programming
+    Guide, intrinsic error table).  Checked here on random class-count configurations of every node size."""
+    rng = np.random.default_rng(scale)
+    C = 4
+    L = rng.integers(0, scale, (20000, C)).astype(object)
+    R = rng.integers(0, scale, (20000, C)).astype(object)
+    ok = (L.sum(1) > 0) & (R.sum(1) > 0)
+    L, R = L[ok], R[ok]
+    NL, NR = L.sum(1), R.sum(1)
+    SL, SR = (L * L).sum(1), (R * R).sum(1)
+    exact = np.array([float(a) / float(b) + float(c) / float(d) for a, b, c, d in zip(SL, NL, SR, NR)])
+    est = _estimate_gini(SL.astype(np.float64), NL.astype(np.float64), SR.astype(np.float64), NR.astype(np.float64)).astype(np.float64)
+    rel = np.abs(est - exact) / exact
+    assert rel.max() < 2.0 ** -21, rel.max()
+    # squared-error proxy on ordinal levels (S = sum_c c * count_c)
+    lev = np.arange(C, dtype=object)
+    S_L, S_R = (L * lev).sum(1), (R * lev).sum(1)
+    keep = (S_L + S_R) > 0
+    exact = np.array([float(a) ** 2 / float(b) + float(c) ** 2 / float(d) for a, b, c, d in zip(S_L[keep], NL[keep], S_R[keep], NR[keep])])
+    est = _estimate_mse(S_L[keep].astype(np.float64), NL[keep].astype(np.float64), S_R[keep].astype(np.float64), NR[keep].astype(np.float64)).astype(np.float64)
+    rel = np.abs(est - exact) / exact
+    assert rel.max() < 2.0 ** -21, rel.max()
