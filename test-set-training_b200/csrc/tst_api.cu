@@ -124,7 +124,10 @@ static const int SMALL_WARPS = 4;
 #define TINY_MAX_ROWS 6
 #endif
 static const int TINY_MAX = TINY_MAX_ROWS;   // thread-per-subtree tier: rows held in registers by one thread
-static const int MID_WARPS = 8;
+#ifndef MID_WARPS_N
+#define MID_WARPS_N 4  // with MID_MINB 5: 94 registers, no spills, 20 warps per SM: 192.6 ms per 640 trees vs 196.2 (8 warps x 3 CTAs, 80 registers, spills)
+#endif
+static const int MID_WARPS = MID_WARPS_N;
 #ifndef MID_R_N
 #define MID_R_N 8
 #endif

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 #define MID4_CAND 1024u  // 256 candidates: (P0, P1) pairs [0, 512) | bin [512, 768) | gain estimate [768, 1024)
 
 #ifndef MID_MINB
-#define MID_MINB 3
+#define MID_MINB 5
 #endif
 template <int WARPS, int R>
 __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
