@@ -303,7 +303,7 @@ def main():
                                                                 + st["inbag_rows"] + 9 * st["oof_steps"]) / max(1, trees_per_rank),
                                     achieved=((15 + m) * (st["row_visits_big"] + st["row_visits_mid"] + st["row_visits_small"]) + st["inbag_rows"]
                                               + 9 * st["oof_steps"]) / (ms / 1e3) / 1e9,
-                                    ms_infer=st["ms_infer"], ms_prep=st["ms_prep"]),
+                                    ms_infer=st["ms_infer"], ms_prep=st["ms_prep"], ms_tiny=st.get("ms_grow_tiny", 0.0)),
                     note="level kernels are bound by L2->SM gather latency / issue slots, not by DRAM: the binned table (64 MB) is L2-resident; see DESIGN.md section 4")
     gpu_launches = int(st["kernel_launches"])
 

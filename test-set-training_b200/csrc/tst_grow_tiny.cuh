@@ -44,8 +44,11 @@ __global__ void __launch_bounds__(256) k_tiny_sort(const uint4* __restrict__ in,
     if (live) out[base + __popc(peers & ((1u << lane) - 1u))] = t;
 }
 
+#ifndef TINY_MINB
+#define TINY_MINB 1
+#endif
 template <int TMAX>
-__global__ void __launch_bounds__(128) k_grow_tiny4(GrowCtx g, const uint4* __restrict__ tasks, uint32_t ntasks) {
+__global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const uint4* __restrict__ tasks, uint32_t ntasks) {
     const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = ti < ntasks;
     const int C = g.C, d = g.d, m = g.m;

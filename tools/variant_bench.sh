@@ -9,7 +9,7 @@ for spec in "$@"; do
 import json,sys
 try:
     d=json.loads(sys.argv[2]); t=d["roofline"]["tiers"]; w=d["roofline"]["whole_tree"]
-    print(sys.argv[1], "value %.1f ms %.1f |"%(d["value"], d["ms_per_step"]), {k[7:]:round(v["ms"]/d["steps"],1) for k,v in t.items()}, "tiny+other %.1f"%(d["ms_per_step"]-sum(v["ms"] for v in t.values())/d["steps"]), flush=True)
+    print(sys.argv[1], "value %.1f ms %.1f |"%(d["value"], d["ms_per_step"]), {k[7:]:round(v["ms"]/d["steps"],1) for k,v in t.items()}, "tiny %.1f prep %.1f infer %.1f rest %.1f"%(w.get("ms_tiny",0)/d["steps"], w["ms_prep"]/d["steps"], w["ms_infer"]/d["steps"], d["ms_per_step"]-(sum(v["ms"] for v in t.values())+w.get("ms_tiny",0)+w["ms_prep"]+w["ms_infer"])/d["steps"]), flush=True)
 except Exception as e:
     print(sys.argv[1], "FAILED", sys.argv[2][-300:])
 PY
