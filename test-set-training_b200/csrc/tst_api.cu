@@ -641,11 +641,13 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         bool small_started = false, tiny_timed = false;
         int blind_levels = 4;
         if (const char* ev = getenv("TST_BLIND_LEVELS")) blind_levels = std::max(1, std::min(8, atoi(ev)));
+        uint64_t thin_nodes = 2048;  // a level with at most this many nodes starts a group of blind levels
+        if (const char* ev = getenv("TST_THIN_NODES")) thin_nodes = (uint64_t)std::max(0, atoi(ev));
         uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1];
         double tr_gap = 0; int tr_groups = 0;
         while (nbig > 0 || nmid > 0) {
             const auto t_level = now();
-            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid <= 2048;
+            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid <= thin_nodes;
             const int J = thin ? blind_levels : 1;
             uint64_t ub_big = nbig, ub_mid = nmid;
             for (int j = 0; j < J; ++j) {
