@@ -530,6 +530,25 @@ class TsTForest:
         s = imp.sum()
         return imp / s if s > 0 else imp
 
+    def explain(self, X, y) -> tuple:
+        """Mean per-feature attribution of P(true class) over the forest's trees for the rows of X
+        (features.path_contributions on every exported tree): -> (prior [n], contributions [n, d]) with
+        prior + contributions.sum(1) == mean over trees of the leaf probability of the true class."""
+        from . import binning
+        from .features import path_contributions
+
+        bins_rows = binning.bin_rows(np.asarray(X, dtype=np.float32), self._eng.edges, self._eng.n_edges)
+        idx = {c: i for i, c in enumerate(self.classes_.tolist())}
+        cls = np.array([idx[v] for v in np.asarray(y).tolist()], dtype=np.int64)
+        prior = np.zeros(bins_rows.shape[0])
+        contrib = np.zeros((bins_rows.shape[0], self.n_features_in_))
+        for t in range(self.n_estimators):
+            nodes, counts = self.export_tree(t)
+            p, c = path_contributions(nodes, counts, bins_rows, cls, self.n_features_in_)
+            prior += p
+            contrib += c
+        return prior / self.n_estimators, contrib / self.n_estimators
+
     def sklearn_tree(self, t: int) -> dict:
         """Tree `t` as sklearn-style node arrays with raw-space thresholds (SK/tree/_tree.pxd:15-25)."""
         from .features import to_sklearn_arrays

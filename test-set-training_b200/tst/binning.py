@@ -48,3 +48,15 @@ def table_edges(X: np.ndarray, n_bins: int = 256):
         n_edges[f] = e.size
         edges[f, : e.size] = e
     return edges, n_edges
+
+
+def bin_rows(X: np.ndarray, edges: np.ndarray, n_edges: np.ndarray) -> np.ndarray:
+    """Host bin map for a few rows (interpretability helpers; the product path bins on the GPU with k_bin_map):
+    bin = number of edges strictly below x, NaN -> 255.  -> [n, d] uint8."""
+    X = np.asarray(X, dtype=np.float32)
+    out = np.empty(X.shape, dtype=np.uint8)
+    for f in range(X.shape[1]):
+        col = X[:, f].astype(np.float64)
+        b = np.searchsorted(edges[f, : int(n_edges[f])], col, side="left")
+        out[:, f] = np.where(np.isnan(col), 255, b).astype(np.uint8)
+    return out

@@ -141,3 +141,34 @@ def to_sklearn_arrays(nodes: np.ndarray, counts: np.ndarray, edges: np.ndarray |
                 value=np.divide(c, N[:, None], out=np.zeros_like(c), where=N[:, None] > 0)[:, None, :],
                 n_node_samples=(nodes["end"] - nodes["begin"]).astype(np.int64), weighted_n_node_samples=N,
                 impurity=1.0 - np.divide((c * c).sum(1), N * N, out=np.ones_like(N), where=N > 0))
+
+
+def path_contributions(nodes: np.ndarray, counts: np.ndarray, bins_rows: np.ndarray, cls: np.ndarray, n_features: int) -> tuple:
+    """Per-feature attribution of one tree's blind prediction ("interpretable auditing"):
+    walking the decision path of a row, the change of P(cls) from a node to the child it enters is credited to the
+    node's split feature.  prior + contributions.sum(1) == P(cls) in the reached leaf, exactly (telescoping sum).
+
+    nodes / counts: a canonical export (tst_export_tree / oracle Forest.tree); bins_rows [n, d] uint8; cls [n].
+    -> (prior [n], contributions [n, n_features])
+    """
+    c = counts.astype(np.float64)
+    N = np.maximum(c.sum(1), 1.0)
+    bins_rows = np.asarray(bins_rows)
+    cls = np.asarray(cls, dtype=np.int64)
+    n = bins_rows.shape[0]
+    prior = np.full(n, 0.0)
+    contrib = np.zeros((n, n_features), dtype=np.float64)
+    feat, thr, left, right = nodes["feature"], nodes["bin"], nodes["left"], nodes["right"]
+    cur = np.zeros(n, dtype=np.int64)
+    prior[:] = c[0, cls] / N[0]
+    active = feat[cur] >= 0
+    rows = np.arange(n)
+    while active.any():
+        i = rows[active]
+        nd = cur[i]
+        f = feat[nd]
+        nxt = np.where(bins_rows[i, f] <= thr[nd], left[nd], right[nd])
+        contrib[i, f] += c[nxt, cls[i]] / N[nxt] - c[nd, cls[i]] / N[nd]
+        cur[i] = nxt
+        active = feat[cur] >= 0
+    return prior, contrib

@@ -72,3 +72,35 @@ def test_gini_importances_and_sklearn_arrays():
     leaves = sk["children_left"] == -1
     assert (sk["feature"][leaves] == -2).all() and np.allclose(sk["value"].sum(-1), 1.0)
     assert sk["n_node_samples"][0] == tr.nodes["end"][0] and (sk["impurity"][leaves] == 0).all()
+
+
+def test_path_contributions_telescope_to_the_leaf_probability():
+    """Per-feature attribution: prior + sum of contributions == leaf P(class), and the mass
+    lands on the columns that carry the label."""
+    from oracle import hist_rf as H
+    from tst import binning, path_contributions
+
+    rng = np.random.default_rng(0)
+    n, d = 1500, 8
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    y = ((X[:, 2] > 0.2).astype(np.uint8) + 2 * (X[:, 5] > -0.1).astype(np.uint8)).astype(np.uint8)  # 4 classes from columns 2 and 5
+    edges, ne = H.find_edges(X)
+    bins = H.bin_table(X, edges, ne)
+    assert np.array_equal(binning.bin_rows(X, edges, ne), bins.T)  # host bin map == oracle bin map
+    fold = np.full(n, H.FOLD_TRAIN_ONLY, np.uint8)
+    _, _, forest = H.fit_oof(bins, y, fold, 1, 6, 4, H.make_params(d), seed=3, keep=True)
+    rows = bins.T[:300]
+    total = np.zeros(d)
+    for t in range(6):
+        tr = forest.tree(0, t)
+        prior, contrib = path_contributions(tr.nodes, tr.counts, rows, y[:300], d)
+        # leaf probability of the true class, by walking the tree independently
+        leaf = np.zeros(300)
+        for i in range(300):
+            nd = 0
+            while tr.nodes["feature"][nd] >= 0:
+                nd = tr.nodes["left"][nd] if rows[i, tr.nodes["feature"][nd]] <= tr.nodes["bin"][nd] else tr.nodes["right"][nd]
+            leaf[i] = tr.counts[nd, y[i]] / tr.counts[nd].sum()
+        assert np.allclose(prior + contrib.sum(1), leaf, atol=1e-12)
+        total += np.abs(contrib).sum(0)
+    assert set(np.argsort(total)[-2:]) == {2, 5}

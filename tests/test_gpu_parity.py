@@ -446,6 +446,10 @@ def test_public_api_run_tst_and_forest(vsi_small):
     assert imp.shape == (16,) and abs(imp.sum() - 1.0) < 1e-9 and (imp >= 0).all()
     sk = clf.sklearn_tree(0)
     assert sk["threshold"].shape == sk["feature"].shape and np.isfinite(sk["threshold"]).all()
+    # per-feature attribution of the blind prediction: telescopes to the forest's probability of the true class
+    prior, contrib = clf.explain(v["X"][:64], v["y"][:64])
+    p_true = proba[np.arange(64), np.searchsorted(clf.classes_, v["y"][:64])]
+    assert contrib.shape == (64, 16) and np.allclose(prior + contrib.sum(1), p_true, atol=1e-3)
 
 
 # --------------------------------------------------------------------------------------------- squared-error criterion
