@@ -148,7 +148,7 @@ def path_contributions(nodes: np.ndarray, counts: np.ndarray, bins_rows: np.ndar
     walking the decision path of a row, the change of P(cls) from a node to the child it enters is credited to the
     node's split feature.  prior + contributions.sum(1) == P(cls) in the reached leaf, exactly (telescoping sum).
 
-    nodes / counts: a canonical export (tst_export_tree / oracle Forest.tree); bins_rows [n, d] uint8; cls [n].
+    nodes / counts: a canonical export (tst_export_tree layout); bins_rows [n, d] uint8; cls [n].
     -> (prior [n], contributions [n, n_features])
     """
     c = counts.astype(np.float64)
