@@ -8,9 +8,14 @@
 
 A "step" = one pass of the hot path: this rank's 10 folds x TREES_PER_FOLD trees (Philox bootstrap ->
 histogram / Gini split / partition growth -> OOF inference), the vote all-gather, and s(x).  Step s
-builds trees [s*T, (s+1)*T) of the 10-fold x 1000-tree job, so K steps are K disjoint slices of that
-job.  Weak scaling: every rank builds TREES_PER_FOLD (default 64: 640 trees in flight, ~36 GB of the 180 GB
-HBM; the per-level host round trips are then < 5 % of a step even on a slow host) trees per fold per step.
+builds trees t in [0, T * world) of every fold with the RNG ids of the job's s-th batch (gid_base = s * 10,000), so
+every step is the same amount of work: exactly 10 * T trees per GPU.  Weak scaling: every rank builds TREES_PER_FOLD
+(default 64: 640 trees in flight, ~36 GB of the 180 GB HBM; the per-level host round trips are then < 5 % of a step
+even on a slow host) trees per fold per step.
+
+job    : strong scaling -- wall-clock of the WHOLE 10-fold x 1000-tree job (host arrays -> bin -> fit -> s(x) on the
+         host) through tst.run_tst at N GPUs.
+votes_crc32: CRC of the all-reduced votes of trees [0, 4) of every fold (seed 0) -- identical at every N.
 
 value  : trees/s with the binned table resident in HBM (CUDA events, barrier both sides, max over ranks)
 e2e    : trees/s through tst.run_tst on HOST arrays -- pinned X/y H2D, bin-edge selection, binning, folds,
@@ -157,10 +162,11 @@ def run_reference(args):
     fold = (np.arange(N_ROWS) % K_FOLDS).astype(np.uint8)
     train = fold != 0
     Xt = X[fold == 0]
+    Xtr, ytr = X[train], y[train]  # the fold's training table is prepared once, outside the timed region
     trees = max(1, cores)  # one tree per core per step: the smallest sample that keeps every core busy
     times = []
     for s in range(args.warmup + args.steps):
-        r = sklearn_tst.time_fit_sample(X, y, train, trees, seed=s, n_jobs=cores, X_test=Xt)
+        r = sklearn_tst.time_fit_sample(Xtr, ytr, None, trees, seed=s, n_jobs=cores, X_test=Xt)
         if s >= args.warmup:
             times.append(r["seconds"])
     total = float(sum(times))
@@ -181,18 +187,19 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------------- own arm
 def cpu_baseline_port(X, y, bins_cm, fold):
-    """CPU histogram-RF oracle (same algorithm, same Philox streams) on the host cores: bounded sample."""
+    """CPU histogram-RF oracle (same algorithm, same Philox streams) on the host cores: bounded sample.
+    -> (cpu_baseline dict, oracle stats, oracle votes, trees per fold of the sample)"""
     from oracle import hist_rf as H
 
     cores = len(os.sched_getaffinity(0))
     prm = H.make_params(N_FEAT)
     per_fold = max(1, (2 * cores + K_FOLDS - 1) // K_FOLDS)
     t = time.perf_counter()
-    _, st, _ = H.fit_oof(bins_cm, y, fold, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=0, t1=per_fold, nthreads=cores)
+    votes, st, _ = H.fit_oof(bins_cm, y, fold, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=0, t1=per_fold, nthreads=cores)
     dt = time.perf_counter() - t
     trees = K_FOLDS * per_fold
     return dict(value=trees / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"{trees} trees ({per_fold} per fold) of the same job with oracle/hist_rf.c (OpenMP, {cores} threads), {dt:.1f} s"), st
+                sample=f"{trees} trees ({per_fold} per fold) of the same job with oracle/hist_rf.c (OpenMP, {cores} threads), {dt:.1f} s"), st, votes, per_fold
 
 
 def main():
@@ -205,6 +212,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-job", action="store_true", help="skip the whole-job (10 x 1000 trees) wall-clock")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -252,11 +260,14 @@ def main():
     votes = eng.new_votes(N_CLASSES)
     m = prm.max_features
 
+    if T * world > N_TREES:
+        raise SystemExit(f"bench.py: --trees-per-fold {T} x {world} ranks exceeds the job's {N_TREES} trees per fold")
+    BATCH_IDS = K_FOLDS * N_TREES  # RNG ids of one batch of the job: step i uses [i * BATCH_IDS, (i + 1) * BATCH_IDS)
+
     def step(i):
-        # trees [i*T*world, (i+1)*T*world) of every fold; this rank builds its T per fold (lid % world == rank)
-        lo = (i * T * world) % N_TREES
-        hi = min(N_TREES, lo + T * world)
-        eng.fit_oof(y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=lo, t1=hi, votes=votes)
+        # trees t in [0, T*world) of every fold with the RNG ids of batch i; this rank builds exactly T per fold
+        # (lid = fold * 1000 + t, lid % world == rank; 1000 is a multiple of 1, 2, 4 and 8)
+        eng.fit_oof(y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, gid_base=i * BATCH_IDS, t0=0, t1=T * world, votes=votes)
         total = eng.allreduce_votes(votes)
         return eng.finalize(total, y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES)
 
@@ -278,8 +289,16 @@ def main():
     st = eng.stats()
     trees_per_rank = int(st["trees"])
     trees_total = trees_per_rank * world  # weak scaling: every rank builds the same count
+    assert trees_per_rank == K_FOLDS * T * args.steps, (trees_per_rank, K_FOLDS * T * args.steps)
     value = trees_total / (ms / 1e3)
     clocks = clk.summary()
+
+    # ---- world-invariant checksum: trees [0, 4) of every fold, all-reduced; the same bytes at N = 1, 2, 4, 8
+    import zlib
+    cv = eng.new_votes(N_CLASSES)
+    eng.fit_oof(y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=0, t1=4, votes=cv)
+    cv = eng.allreduce_votes(cv)
+    votes_crc = zlib.crc32(cv.cpu().numpy().tobytes())
 
     # ---- roofline of the dominant kernel: the three growth tiers share the (15 + m) bytes-per-visit accounting of
     # SURVEY 8(d); the one with the largest share of the step is reported, the other two ride along in `tiers`.
@@ -309,6 +328,7 @@ def main():
 
     # ---- e2e through the public API on host buffers
     e2e = None
+    job = None
     if not args.no_e2e:
         Xp = torch.from_numpy(X).pin_memory()
         yp = y
@@ -318,18 +338,30 @@ def main():
         tst.run_tst(Xp, yp, k=K_FOLDS, n_trees=N_TREES, seed=0, tree_range=(0, T * world), engine=eng)  # warm
         barrier()
         t0 = time.perf_counter()
+        e2e_trees = 0
         for i in range(e2e_steps):
-            lo = ((i + 1) * T * world) % N_TREES
-            res = tst.run_tst(Xp, yp, k=K_FOLDS, n_trees=N_TREES, seed=0, tree_range=(lo, min(N_TREES, lo + T * world)), engine=eng)
+            res = tst.run_tst(Xp, yp, k=K_FOLDS, n_trees=N_TREES, seed=i + 1, tree_range=(0, T * world), engine=eng)
+            e2e_trees += int(res.stats["trees"]) * world  # counted by the library, not assumed
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = dict(value=K_FOLDS * T * world * e2e_steps / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                   steps=e2e_steps, ms_per_step=1e3 * dt / e2e_steps,
+        e2e = dict(value=e2e_trees / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   steps=e2e_steps, ms_per_step=1e3 * dt / e2e_steps, trees=e2e_trees,
                    note="tst.run_tst on host arrays: pinned H2D of X/y, bin-edge selection + binning on the GPU, folds, fit, s(x), D2H of s/votes/folds")
+        # ---- strong scaling: the whole 10-fold x 1000-tree job, host arrays in -> s(x) on the host
+        if not args.no_job:
+            barrier()
+            t0 = time.perf_counter()
+            res = tst.run_tst(Xp, yp, k=K_FOLDS, n_trees=N_TREES, seed=0, engine=eng)
+            barrier()
+            dtj = max_over_ranks(time.perf_counter() - t0)
+            job = dict(wallclock_s=dtj, trees=K_FOLDS * N_TREES, trees_per_s=K_FOLDS * N_TREES / dtj, scaling="strong",
+                       trees_this_rank=int(res.stats["trees"]), blind_accuracy=float(np.nanmean(res.fold_accuracy)),
+                       s_crc32=zlib.crc32(res.s.tobytes()),
+                       note="whole BASELINE configs[4] job through tst.run_tst: H2D, binning, folds, 10,000 trees sharded over the ranks, vote all-gather, s(x), D2H")
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic", config=workload(T),
-                roofline=roofline, e2e=e2e, gpu_launches=gpu_launches, clocks=clocks,
+                roofline=roofline, e2e=e2e, gpu_launches=gpu_launches, clocks=clocks, job=job, votes_crc32=votes_crc,
                 trees_per_step=trees_total // max(1, args.steps), nodes_per_tree=st["nodes"] / max(1, trees_per_rank),
                 max_depth=int(st["max_depth"]))
 
@@ -337,8 +369,23 @@ def main():
         bins_cm, fold_h = (eng.get_bins(), fold_dev.cpu().numpy()) if not args.no_cpu else (None, None)
         if not args.no_secondary:  # before the CPU leg: idle OpenMP workers spin for a while and disturb millisecond latencies
             line["secondary"] = secondary_wallclock(tst, synth, eng)
+        if not args.no_cpu and not args.no_secondary:
+            line["secondary"]["cpu"] = secondary_cpu(synth)
         if not args.no_cpu:
-            line["cpu_baseline"], _ = cpu_baseline_port(X, yi, bins_cm, fold_h)
+            line["cpu_baseline"], ost, ovotes, per_fold = cpu_baseline_port(X, yi, bins_cm, fold_h)
+            # parity on the headline table itself: the GPU fit of the sample's trees against the oracle's votes and counters
+            gv = eng.new_votes(N_CLASSES)
+            eng.stats(reset=True)
+            eng.fit_oof(y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=0, t1=per_fold, votes=gv)
+            gst = eng.stats()
+            same_votes = bool(np.array_equal(gv.cpu().numpy().view(np.uint32), ovotes))
+            same_stats = all(int(gst[k]) == int(ost[k]) for k in ("nodes", "leaves", "searched", "fallback", "inbag_rows", "trees", "oof_steps", "max_depth")) \
+                and int(gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"]) == int(ost["row_visits"])
+            line["parity_1Mx64"] = same_votes and same_stats
+            line["parity_1Mx64_detail"] = dict(trees=K_FOLDS * per_fold, votes_equal=same_votes, counters_equal=same_stats,
+                                               nodes=int(ost["nodes"]), row_visits=int(ost["row_visits"]))
+            if per_fold == 4:
+                line["votes_crc32_oracle"] = zlib.crc32(ovotes.tobytes())
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -383,7 +430,52 @@ def secondary_wallclock(tst, synth, eng):
     out["regression_5k_x32_5fold_x100_ms"] = 1e3 * best
     ok = np.isfinite(rr.y_pred)
     out["regression_oof_r2"] = float(1.0 - ((rr.y_pred[ok] - yn[ok]) ** 2).sum() / ((yn[ok] - yn[ok].mean()) ** 2).sum())
+    # per-question-type batched forests (BASELINE.json configs[2]): one forest set per group, all groups in one call
+    for kind in ("cvbench", "mmmu", "videomme"):
+        Xg, yg, gg, ng = synth.grouped_table(kind)
+        tst.run_tst(Xg, yg, k=5, n_trees=100, seed=0, group=gg, engine=eng)
+        best = 1e9
+        for i in range(3):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            rg = tst.run_tst(Xg, yg, k=5, n_trees=100, seed=1 + i, group=gg, engine=eng)
+            best = min(best, time.perf_counter() - t)
+        out[f"grouped_{kind}_{ng}groups_5fold_x100_ms"] = 1e3 * best
+        out[f"grouped_{kind}_trees"] = int(rg.stats["trees"])
     out["note"] = "host arrays in, host arrays out; latency-bound (5k rows): reported as wall-clock, not bandwidth"
+    return out
+
+
+def secondary_cpu(synth):
+    """CPU timings beside the secondary metric (BASELINE.md CPU-baseline plan 2-3): sklearn and the C port of the same
+    histogram RF on the box's host cores, VSI-shaped TsT (full 5 x 100) and IBP (port: full 10 rounds; sklearn: 2 rounds,
+    extrapolated x5 and said so)."""
+    from oracle import hist_rf as H
+    from oracle import sklearn_tst
+
+    cores = len(os.sched_getaffinity(0))
+    X, y = synth.vsi_table()
+    out = dict(cores=cores)
+    r = sklearn_tst.run_tst(X, y, k=5, n_trees=100, seed=0, n_jobs=cores)
+    out["sklearn_tst_vsi_5fold_x100_ms"] = 1e3 * r["seconds"]
+    out["sklearn_version"] = r["sklearn_version"]
+    t = time.perf_counter()
+    edges, ne = H.find_edges(X)
+    bins = H.bin_table(X, edges, ne)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 5, 4)
+    t_bin = time.perf_counter() - t
+    t = time.perf_counter()
+    votes, _, _ = H.fit_oof(bins, y, fold, 5, 100, 4, H.make_params(X.shape[1]), seed=0, nthreads=cores)
+    H.finalize(votes, y, fold, 5, 100)
+    out["port_tst_vsi_5fold_x100_ms"] = 1e3 * (time.perf_counter() - t)
+    out["port_binning_ms"] = 1e3 * t_bin
+    t = time.perf_counter()
+    H.ibp(bins, y, 5, 200, 4, H.make_params(X.shape[1]), seed=0, rounds=10, tau=0.5, batch=250, nthreads=cores, want_s=False)
+    out["port_ibp_10rounds_5fold_x200_ms"] = 1e3 * (time.perf_counter() - t)
+    r2 = sklearn_tst.ibp(X, y, rounds=2, k=5, n_trees=200, tau=0.5, batch=250, seed=0, n_jobs=cores)
+    out["sklearn_ibp_2rounds_5fold_x200_ms"] = 1e3 * r2["seconds"]
+    out["sklearn_ibp_10rounds_extrapolated_ms"] = 5e3 * r2["seconds"]
+    out["note"] = f"host cores = {cores}; sklearn IBP is a 2-round sample extrapolated x5, everything else is the full workload"
     return out
 
 

@@ -180,6 +180,10 @@ int tst_predict(tst_handle* h, const float* X_dev, int64_t n, uint32_t* votes_de
 int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node* nodes_host, uint32_t* counts_host,
                     int64_t cap, int64_t* n_nodes);
 
+/* Tuning / diagnostic knobs of one handle (INTEGRATION.md "knobs").  Defaults come from the environment variables
+ * TST_<NAME>, read once in tst_create; names are case-insensitive, with or without the TST_ prefix. */
+int tst_set_option(tst_handle* h, const char* name, int64_t value);
+
 int tst_get_stats(tst_handle* h, tst_stats* out);
 int tst_reset_stats(tst_handle* h);
 

@@ -87,13 +87,17 @@ def ibp(X, y, rounds=10, k=5, n_trees=200, tau=0.5, batch=None, seed=0, n_jobs=N
 
 
 def time_fit_sample(X, y, train_mask, n_trees, seed=0, n_jobs=None, X_test=None):
-    """Time `n_trees` trees on one fold's training rows (+ OOF predict): the bounded CPU-baseline sample."""
+    """Time `n_trees` trees on one fold's training rows (+ OOF predict): the bounded CPU-baseline sample.
+    train_mask=None: X, y already are the training rows (the slicing copy then stays outside the timed region)."""
     from sklearn.ensemble import RandomForestClassifier
 
     n_jobs = usable_cores() if n_jobs is None else n_jobs
     t0 = time.perf_counter()
     rf = RandomForestClassifier(n_estimators=n_trees, random_state=seed, n_jobs=n_jobs)
-    rf.fit(X[train_mask], y[train_mask])
+    if train_mask is None:
+        rf.fit(X, y)
+    else:
+        rf.fit(X[train_mask], y[train_mask])
     if X_test is not None:
         rf.predict_proba(X_test)
     dt = time.perf_counter() - t0

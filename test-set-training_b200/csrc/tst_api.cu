@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -110,7 +111,18 @@ struct tst_handle {
     uint32_t* h_pinned = nullptr;  // 16 words
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
     cudaEvent_t ev_lvl[8][3] = {};  // per level of a group of blind levels: before big, between, after mid
-    size_t l2_carve_set = 0;
+    cudaEvent_t evi0 = nullptr, evi1 = nullptr;  // OOF inference
+    size_t l2_carve_set = 0, l2_carve_saved = 0;
+    bool l2_carve_touched = false;
+    // tuning / diagnostic knobs, read from the environment once in tst_create
+    struct Knobs {
+        bool trace = false, stash = false, big_packed = true;
+        int root_dense = -1;          // -1 = automatic, 0 = off, 2 = on for any table size
+        int tiny_max = -1, mid_max = -1, stash_max = -1;
+        int blind_levels = 4;
+        long thin_nodes = 2048;
+        int sub_rows = -1;            // row capacity of the CTA-per-subtree tier (0 = tier off)
+    } knobs;
     tst_stats stats;
     bool attrs_set = false;
 };
@@ -145,6 +157,50 @@ extern "C" int tst_nccl_unique_id(void* out128) {
     return TST_OK;
 }
 
+static int set_option(tst_handle* h, const std::string& nm, long v) {
+    tst_handle::Knobs& kn = h->knobs;
+    if (nm == "L2_PERSIST") h->l2_persist = v != 0;
+    else if (nm == "TRACE") kn.trace = v != 0;
+    else if (nm == "STASH") kn.stash = v != 0;
+    else if (nm == "BIG_PACKED") kn.big_packed = v != 0;
+    else if (nm == "ROOT_DENSE") kn.root_dense = (int)v;
+    else if (nm == "TINY_MAX") kn.tiny_max = (int)v;
+    else if (nm == "MID_MAX") kn.mid_max = (int)v;
+    else if (nm == "STASH_MAX") kn.stash_max = (int)v;
+    else if (nm == "BLIND_LEVELS") kn.blind_levels = (int)std::max(1l, std::min(8l, v));
+    else if (nm == "THIN_NODES") kn.thin_nodes = std::max(0l, v);
+    else if (nm == "SUB_ROWS") kn.sub_rows = (int)v;
+    else return -1;
+    return 0;
+}
+
+extern "C" int tst_set_option(tst_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return fail(TST_ERR_INVALID, "tst_set_option: null argument");
+    std::string nm(name);
+    for (auto& ch : nm) ch = (char)toupper((unsigned char)ch);
+    if (nm.rfind("TST_", 0) == 0) nm = nm.substr(4);
+    if (set_option(h, nm, (long)value)) return fail(TST_ERR_INVALID, std::string("tst_set_option: unknown option ") + name);
+    return TST_OK;
+}
+
+static int create_resources(tst_handle* h, int world, int rank, const void* nccl_unique_id) {
+    CK(cudaMallocHost((void**)&h->h_pinned, 256));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreate(&h->ev2));
+    CK(cudaEventCreate(&h->evm0)); CK(cudaEventCreate(&h->evm1)); CK(cudaEventCreate(&h->evs0)); CK(cudaEventCreate(&h->evs1));
+    CK(cudaEventCreate(&h->evi0)); CK(cudaEventCreate(&h->evi1));
+    for (auto& lv : h->ev_lvl) for (auto& e : lv) CK(cudaEventCreate(&e));
+    if (nccl_unique_id && world > 1) {
+        if (load_nccl()) return fail(TST_ERR_UNSUPPORTED, "tst_create: libnccl.so.2 not found");
+        tst_nccl_id id;
+        memcpy(&id, nccl_unique_id, sizeof(id));
+        int rc = g_nccl.CommInitRank(&h->comm, world, id, rank);
+        if (rc) { h->comm = nullptr; return fail(TST_ERR_CUDA, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); }
+    }
+    return 0;
+}
+
 extern "C" int tst_create(tst_handle** out, int device, int rank, int world, const void* nccl_unique_id) {
     if (!out || world < 1 || rank < 0 || rank >= world) return fail(TST_ERR_INVALID, "tst_create: bad arguments");
     int count = 0;
@@ -161,21 +217,15 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     tst_handle* h = new tst_handle();
     h->device = device; h->rank = rank; h->world = world; h->sm_count = prop.multiProcessorCount;
     h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize; h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-    if (const char* ev = getenv("TST_L2_PERSIST")) h->l2_persist = atoi(ev) != 0;
-    memset(&h->stats, 0, sizeof(h->stats));
-    CK(cudaMallocHost((void**)&h->h_pinned, 256));
-    CK(cudaEventCreate(&h->ev0));
-    CK(cudaEventCreate(&h->ev1));
-    CK(cudaEventCreate(&h->ev2));
-    CK(cudaEventCreate(&h->evm0)); CK(cudaEventCreate(&h->evm1)); CK(cudaEventCreate(&h->evs0)); CK(cudaEventCreate(&h->evs1));
-    for (auto& lv : h->ev_lvl) for (auto& e : lv) CK(cudaEventCreate(&e));
-    if (nccl_unique_id && world > 1) {
-        if (load_nccl()) { delete h; return fail(TST_ERR_UNSUPPORTED, "tst_create: libnccl.so.2 not found"); }
-        tst_nccl_id id;
-        memcpy(&id, nccl_unique_id, sizeof(id));
-        int rc = g_nccl.CommInitRank(&h->comm, world, id, rank);
-        if (rc) { delete h; return fail(TST_ERR_CUDA, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); }
+    // tuning / diagnostic knobs: defaults from the environment (TST_<NAME>), read once here; tst_set_option changes them later
+    for (const char* nm : {"L2_PERSIST", "TRACE", "STASH", "BIG_PACKED", "ROOT_DENSE", "TINY_MAX", "MID_MAX", "STASH_MAX", "BLIND_LEVELS",
+                           "THIN_NODES", "SUB_ROWS"}) {
+        const std::string env = std::string("TST_") + nm;
+        if (const char* v = getenv(env.c_str())) set_option(h, nm, atol(v));
     }
+    memset(&h->stats, 0, sizeof(h->stats));
+    int rc = create_resources(h, world, rank, nccl_unique_id);
+    if (rc) { tst_destroy(h); return rc; }  // frees whatever was created before the failure
     *out = h;
     return TST_OK;
 }
@@ -193,7 +243,9 @@ extern "C" int tst_destroy(tst_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
-    for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1, h->evi0, h->evi1}) if (e) cudaEventDestroy(e);
+    // cudaLimitPersistingL2CacheSize is device-wide: hand it back the way the host application (torch) had it
+    if (h->l2_carve_touched) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_carve_saved); cudaGetLastError(); }
     for (auto& lv : h->ev_lvl) for (auto& e : lv) if (e) cudaEventDestroy(e);
     delete h;
     return TST_OK;
@@ -350,7 +402,11 @@ static void set_l2_window(tst_handle* h, cudaStream_t st, bool on) {
     memset(&attr, 0, sizeof(attr));
     if (on) {
         const size_t carve = std::min(bytes, h->l2_persist_max);
-        if (h->l2_carve_set != carve) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve); h->l2_carve_set = carve; }  // device-wide and slow: only when it changes
+        if (h->l2_carve_set != carve) {  // device-wide and slow: only when it changes; the previous value is restored by tst_destroy
+            if (!h->l2_carve_touched) { cudaDeviceGetLimit(&h->l2_carve_saved, cudaLimitPersistingL2CacheSize); h->l2_carve_touched = true; }
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+            h->l2_carve_set = carve;
+        }
         attr.accessPolicyWindow.base_ptr = h->bins_rm.p;
         attr.accessPolicyWindow.num_bytes = std::min(bytes, h->l2_window_max);
         attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
@@ -399,7 +455,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     if ((uint64_t)n_groups * k * n_trees + gid_base > 0xFFFFFFFFull) return fail(TST_ERR_INVALID, "tst_fit_oof: tree id overflows 32 bits");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const bool trace = getenv("TST_TRACE") != nullptr;  // host wall-clock phases of every batch on stderr
+    const tst_handle::Knobs& kn = h->knobs;
+    const bool trace = kn.trace;  // host wall-clock phases of every batch on stderr
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     const auto t_entry = now();
@@ -461,9 +518,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint32_t n_chunks = (uint32_t)((n_pad + BOOT_CHUNK - 1) / BOOT_CHUNK);
     const uint64_t node_stride = 2 * n_cap;
     const uint64_t leafc_stride = (n_cap / 2 + 1) * (uint64_t)C;
-    const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / 8 + 2, qtiny_per = n_cap / 2 + 2;
+    // queue slots per tree.  With the thread-per-subtree tier on, qsmall only sees subtrees of >= 7 rows (<= n/7 of them); with it
+    // off (many classes, squared error, d > 64) every 2..32-row subtree lands there: up to n/2 tasks for a tree that peels rows off.
+    const uint64_t tiny_eff = (C <= 4 && prm->criterion == TST_GINI && d <= TINY_FY_MAX) ? (uint64_t)(kn.tiny_max >= 0 ? std::min(kn.tiny_max, TINY_MAX) : TINY_MAX) : 0;
+    const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / std::max<uint64_t>(2, tiny_eff + 1) + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
-    const bool want_stash = getenv("TST_STASH") && atoi(getenv("TST_STASH")) != 0;  // see use_stash below
+    const bool want_stash = kn.stash;  // see use_stash below
     const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (4 * qbig_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t free_b = 0, total_b = 0;
@@ -524,10 +584,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.MB = (int)std::min<size_t>(std::min<size_t>(32, (size_t)g.m), std::max<size_t>(1, BIG_SMEM_BUDGET / ((size_t)g.FS * 4)));
     g.big_tile = h->dstride <= 64 ? 1 : 0;  // cooperative whole-row fetch into a shared tile (rows of <= 64 bytes)
     const size_t big_tile_bytes = g.big_tile ? (size_t)BIG_THREADS * ((h->dstride >> 2) + 1) * 4 : 0;
-    g.big_tma = 1;
-    g.big_packed = 1;
-    if (const char* ev = getenv("TST_BIG_PACKED")) g.big_packed = atoi(ev) != 0;
-    if (const char* ev = getenv("TST_BIG_TMA")) g.big_tma = atoi(ev) != 0;
+    g.big_packed = kn.big_packed ? 1u : 0u;
     // Option (TST_STASH=1, off by default): the histogram pass of k_grow_big leaves the m sampled bins of every row in a
     // stash (8 bytes per row, coalesced) so that its partition pass does not gather the split feature's byte from the
     // table again.  Measured on B200 (1M x 64, 640 trees): 25 % fewer LSU wavefronts and -5 % kernel time on the full
@@ -538,11 +595,13 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         ENSURE(h->stash, B * n_cap * sizeof(uint2));
         g.stash = h->stash.as<uint2>();
         g.stash_max_rows = 0xFFFFFFFFu;
-        if (const char* ev = getenv("TST_STASH_MAX")) g.stash_max_rows = (uint32_t)std::max(0, atoi(ev));
+        if (kn.stash_max >= 0) g.stash_max_rows = (uint32_t)kn.stash_max;
     }
-    const size_t big_smem = (size_t)g.MB * g.FS * 4 + big_tile_bytes;
-    if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
     const bool packed_ok = C <= 4 && prm->criterion == TST_GINI;  // the packed 4-class kernels implement the Gini criterion only
+    // the packed 16-bit layout needs BIGP_FS = 640 words per feature, more than FS when C == 2 (544): size for the larger one
+    g.HFS_max = (packed_ok && g.big_packed && g.big_tile && g.MB <= 8) ? std::max<int>(g.FS, (int)BIGP_FS) : g.FS;
+    const size_t big_smem = (size_t)g.MB * g.HFS_max * 4 + big_tile_bytes;
+    if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
     const bool small_packed = packed_ok;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
     const uint32_t small_per_warp = small_packed ? ((64u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
@@ -550,10 +609,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     // dense root histograms (tst_root.cuh): big tables only; needs m <= 8 and the histogram + 2 TMA stages in shared memory
     const size_t root_smem = (size_t)g.m * g.FS * 4 + 2 * (size_t)(g.m + 2) * ROOT_TILE;
     bool root_dense = n >= 65536 && g.m <= 8 && root_smem <= 200 * 1024 && max_train > 32u * MID_R;
-    if (const char* ev = getenv("TST_ROOT_DENSE")) {  // 0 = off, 2 = on for any table size (tests)
-        if (atoi(ev) == 0) root_dense = false;
-        if (atoi(ev) == 2) root_dense = g.m <= 8 && root_smem <= 200 * 1024 && max_train > 32u * MID_R;
-    }
+    if (kn.root_dense == 0) root_dense = false;  // 0 = off, 2 = on for any table size (tests)
+    if (kn.root_dense == 2) root_dense = g.m <= 8 && root_smem <= 200 * 1024 && max_train > 32u * MID_R;
     if (root_dense) {
         ENSURE(h->ghist, B * (size_t)g.m * g.FS * 4);
         ENSURE(h->rsplit, B * sizeof(RootSplit));
@@ -565,7 +622,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.qsmall_count = counters + 4;
     g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
     g.tiny_max = (packed_ok && d <= TINY_FY_MAX && B <= 65535) ? TINY_MAX : 0;  // packed 4-class thread-per-subtree tier
-    if (const char* ev = getenv("TST_TINY_MAX")) g.tiny_max = std::min<uint32_t>(g.tiny_max, (uint32_t)atoi(ev));
+    if (kn.tiny_max >= 0) g.tiny_max = std::min<uint32_t>(g.tiny_max, (uint32_t)kn.tiny_max);
     const bool mid_packed = packed_ok;  // packed 16-bit class counts (k_grow_mid4)
     const uint32_t mid_per_warp = mid_packed ? ((MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                              : (uint32_t)g.FS + 2u * (uint32_t)C + (uint32_t)((d + 1) / 2);
@@ -575,7 +632,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const size_t mid_smem = (size_t)mid_warps * mid_per_warp * 4;
     g.mid_max = mid_smem <= 200 * 1024 ? 32u * MID_R : SMALL_MAX;
     g.mid_packed = mid_packed ? 1u : 0u;
-    if (const char* ev = getenv("TST_MID_MAX")) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)atoi(ev)));
+    if (kn.mid_max >= 0) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)kn.mid_max));
 
     if (trace) {
         cudaStreamSynchronize(st);
@@ -639,10 +696,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         int cur = 0;
         uint64_t level_guard = 0;
         bool small_started = false, tiny_timed = false;
-        int blind_levels = 4;
-        if (const char* ev = getenv("TST_BLIND_LEVELS")) blind_levels = std::max(1, std::min(8, atoi(ev)));
-        uint64_t thin_nodes = 2048;  // a level with at most this many nodes starts a group of blind levels
-        if (const char* ev = getenv("TST_THIN_NODES")) thin_nodes = (uint64_t)std::max(0, atoi(ev));
+        const int blind_levels = kn.blind_levels;
+        const uint64_t thin_nodes = (uint64_t)kn.thin_nodes;  // a level with at most this many nodes starts a group of blind levels
         uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1];
         double tr_gap = 0; int tr_groups = 0;
         while (nbig > 0 || nmid > 0) {
@@ -749,11 +804,11 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             }
             i = j;
         }
-        cudaEvent_t evi0 = nullptr, evi1 = nullptr;
+        bool infer_timed = false;
         if (votes_dev && !ips.empty()) {
             CK(cudaMemcpyAsync(h->infer_parts.p, ips.data(), ips.size() * sizeof(InferPart), cudaMemcpyHostToDevice, st));
-            CK(cudaEventCreate(&evi0)); CK(cudaEventCreate(&evi1));
-            CK(cudaEventRecord(evi0, st));
+            CK(cudaEventRecord(h->evi0, st));
+            infer_timed = true;
             // enough threads to fill the GPU: cut the trees of a partition into chunks when the held-out sets are small
             uint32_t max_trees = 0, rows_total = 0;
             for (auto& ip : ips) { max_trees = std::max(max_trees, ip.tree_hi - ip.tree_lo); rows_total += ip.fsz; }
@@ -766,16 +821,13 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             if (chunks > 1) k_oof_infer<true><<<grid, 256, 0, st>>>(g, h->infer_parts.as<InferPart>(), h->sorted.as<uint32_t>(), votes_dev, tpc);
             else k_oof_infer<false><<<grid, 256, 0, st>>>(g, h->infer_parts.as<InferPart>(), h->sorted.as<uint32_t>(), votes_dev, tpc);
             CKL();
-            CK(cudaEventRecord(evi1, st));
+            CK(cudaEventRecord(h->evi1, st));
             h->stats.kernel_launches++;
         }
         CK(cudaStreamSynchronize(st));
         if (small_started) { float ms = 0; cudaEventElapsedTime(&ms, h->evs0, h->evs1); h->stats.ms_grow_small += ms; }
         if (tiny_timed) { float ms = 0; cudaEventElapsedTime(&ms, h->evm0, h->evm1); h->stats.ms_grow_tiny += ms; }
-        if (evi0) {
-            float ms = 0; cudaEventElapsedTime(&ms, evi0, evi1); h->stats.ms_infer += ms;
-            cudaEventDestroy(evi0); cudaEventDestroy(evi1);
-        }
+        if (infer_timed) { float ms = 0; cudaEventElapsedTime(&ms, h->evi0, h->evi1); h->stats.ms_infer += ms; }
         if (keep) {
             std::vector<TreeDesc> back(nb);
             CK(cudaMemcpy(back.data(), h->trees.p, (size_t)nb * sizeof(TreeDesc), cudaMemcpyDeviceToHost));

@@ -158,7 +158,7 @@ struct GrowCtx {
     uint32_t stash_max_rows;  // nodes above this size gather instead: their stash would stream through HBM (the table itself is L2-resident)
     uint2* stash;             // non-null: [tree][n_cap] the m <= 8 sampled bins of each row, written by the histogram pass of k_grow_big for its partition pass
     int32_t big_tile; // k_grow_big stages whole rows in shared memory (dstride <= 128)
-    int32_t big_tma;  // ... and its row-index tiles arrive through TMA bulk copies
+    int32_t HFS_max;  // words per feature reserved in k_grow_big's histogram region: max(FS, packed layout) -- 2-class tables have FS = 544 < 640
     int32_t MB;       // features per shared-histogram batch
     int32_t FS;       // histogram words per feature = 32 * (8 * C + 1)
 };

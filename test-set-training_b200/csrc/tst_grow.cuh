@@ -267,21 +267,6 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
 #ifndef BIG_MINB
 #define BIG_MINB 3
 #endif
-#ifndef BIG_PART_SCAN
-#define BIG_PART_SCAN 1
-#endif
-#ifndef BIG_PART_PREFETCH
-#define BIG_PART_PREFETCH 0
-#endif
-// TMA ring for the row-index tiles of the histogram pass.  Measured on B200 (1M x 64, 320 trees in flight): the
-// ring adds mbarrier bookkeeping and registers to a kernel that sits at 80 registers / 3 CTAs per SM and is
-// issue-bound, k_grow_big 134 ms with it vs 112 ms without; it is therefore compiled out by default
-// (-DBIG_TMA_RING=1 builds it; TST_BIG_TMA=0 disables it at run time).  TMA is used where it pays: k_root_hist.
-#ifndef BIG_TMA_RING
-#define BIG_TMA_RING 0
-#endif
-#define ENT_STAGES 4  // 32-entry (256-byte) TMA tiles in flight per warp
-
 // ---------------------------------------------------------------------------------------------
 template <int THREADS, bool MSE = false>  // MSE: squared-error criterion on ordinal levels (its own instantiation: the Gini one keeps its registers)
 __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
@@ -294,17 +279,9 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     __shared__ double s_fgain[32];
     __shared__ uint32_t s_fbin[32];
     __shared__ uint32_t s_feat[32];
-#if BIG_PART_SCAN
     __shared__ uint32_t s_wl[2][4][NW];
-#else
-    __shared__ uint32_t s_wl[2][4][NW], s_wr[2][4][NW];
-#endif
     __shared__ double s_bgain;
     __shared__ uint32_t s_bkey, s_found, s_newj, s_N, s_stop, s_sj;  // s_sj: position of the best split's feature in the stash (or none)
-#if BIG_TMA_RING
-    __shared__ __align__(16) Entry s_ent[NW][ENT_STAGES][32];  // TMA-staged row-index tiles, one ring per warp
-    __shared__ __align__(8) uint64_t s_bar[NW][ENT_STAGES];
-#endif
 
     // thin levels are launched without a host round trip: the grid is an upper bound, the real count is on the device
     if (ntasks_dev) ntasks = min(ntasks, *ntasks_dev);
@@ -324,22 +301,10 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     const bool packed = !MSE && g.big_packed != 0u && use_tile && C <= 4 && g.MB <= 8 && t.pad1 != 0u && t.pad1 <= 65535u;
     const uint32_t HFS = packed ? BIGP_FS : (uint32_t)g.FS;  // histogram words per feature
     const uint32_t pitch = (dstride >> 2) + 1u;
-    uint32_t* s_tile = s_hist + g.MB * g.FS + wid * 32u * pitch;  // this warp's rows
+    uint32_t* s_tile = s_hist + g.MB * g.HFS_max + wid * 32u * pitch;  // this warp's rows (the histogram region holds either layout)
 
     for (int f = tid; f < d; f += THREADS) s_perm[f] = (uint16_t)f;
     if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; s_sj = 0xFFFFFFFFu; }
-#if BIG_TMA_RING
-    const bool use_tma = use_tile && g.big_tma != 0 && dstride <= 64;
-    if (use_tma && lane == 0) {
-        for (int sidx = 0; sidx < ENT_STAGES; ++sidx) mbar_init(&s_bar[wid][sidx], 1);
-        mbar_fence_init();
-    }
-    // this warp's 32-entry chunks: c = wid, wid + NW, ...; chunk starts are 16-byte aligned (a0 even)
-    const uint32_t a0 = t.begin & ~1u;
-    const uint32_t n_chunks = (t.end - a0 + 31u) >> 5;
-    const uint32_t n_my = n_chunks > wid ? (n_chunks - wid + NW - 1) / NW : 0u;
-    uint32_t tma_ph = 0;  // bit s = parity the next wait on stage s must see (uniform across the warp)
-#endif
     __syncthreads();
 
     // roots already split by the dense column-major kernels (tst_root.cuh) only need the partition below
@@ -377,41 +342,11 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 
         // ---- class histogram: hist[j][bin][class] += multiplicity (SK/.../histogram.pyx:336-425 pattern)
         if (use_tile && nb <= 8) {
-            uint2* stash_w = (!BIG_TMA_RING && g.stash != nullptr && pos == 0 && t.end - t.begin <= g.stash_max_rows) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
+            uint2* stash_w = (g.stash != nullptr && pos == 0 && t.end - t.begin <= g.stash_max_rows) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
             uint32_t featr[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) featr[jj] = jj < nb ? s_feat[jj] : 0u;
             const uint8_t* trow = (const uint8_t*)(s_tile + lane * pitch);
-#if BIG_TMA_RING
-            if (use_tma) {
-                // row-index tiles staged by TMA: a ring of ENT_STAGES 256-byte tiles per warp runs ahead of the gathers
-                if (lane == 0)
-                    for (uint32_t sidx = 0; sidx < ENT_STAGES && sidx < n_my; ++sidx) {
-                        mbar_expect_tx(&s_bar[wid][sidx], 256u);
-                        tma_load_1d(&s_ent[wid][sidx][0], ent_in + a0 + 32u * (wid + sidx * NW), 256u, &s_bar[wid][sidx]);
-                    }
-                for (uint32_t i = 0; i < n_my; ++i) {
-                    const uint32_t stage = i % ENT_STAGES;
-                    mbar_wait(&s_bar[wid][stage], (tma_ph >> stage) & 1u);
-                    tma_ph ^= 1u << stage;
-                    const uint32_t idx = a0 + 32u * (wid + i * NW) + lane;
-                    Entry e = s_ent[wid][stage][lane];
-                    if (idx < t.begin || idx >= t.end) e = make_uint2(0u, 0u);
-                    fetch_rows32(bins, dstride, e.x, e.y != 0u, s_tile, lane);
-                    if (lane == 0 && i + ENT_STAGES < n_my) {  // every lane consumed its entry (fetch ends with __syncwarp)
-                        mbar_expect_tx(&s_bar[wid][stage], 256u);
-                        tma_load_1d(&s_ent[wid][stage][0], ent_in + a0 + 32u * (wid + (i + ENT_STAGES) * NW), 256u, &s_bar[wid][stage]);
-                    }
-                    if (e.y) {
-                        const uint32_t cls = ent_cls(e), w = ent_w(e);
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj)
-                            if (jj < nb) atomicAdd(&s_hist[jj * g.FS + hist_index(trow[featr[jj]], cls, C)], w);
-                    }
-                    __syncwarp();
-                }
-            } else
-#endif
             // the entry of the NEXT tile is requested before this tile's rows: the two dependent latencies
             // (entry list from HBM, then the row gather from L2) overlap across iterations
             Entry e_next = t.begin + tid < t.end ? ent_load(ent_in + t.begin + tid) : make_uint2(0u, 0u);
@@ -504,7 +439,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                     uint32_t key = (s_feat[j] << 8) | s_fbin[j];  // ties: lowest feature, then lowest bin
                     if (s_fgain[j] > s_bgain || (s_fgain[j] == s_bgain && key < s_bkey)) {
                         s_bgain = s_fgain[j]; s_bkey = key; s_newj = j; s_found = 1;
-                        s_sj = (!BIG_TMA_RING && pos == 0 && g.stash != nullptr && use_tile && nb <= 8 && t.end - t.begin <= g.stash_max_rows) ? (uint32_t)j : 0xFFFFFFFFu;
+                        s_sj = (pos == 0 && g.stash != nullptr && use_tile && nb <= 8 && t.end - t.begin <= g.stash_max_rows) ? (uint32_t)j : 0xFFFFFFFFu;
                     }
                 }
             } else {
@@ -563,32 +498,15 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     uint32_t lbase = 0, rbase = 0;
     int par = 0;
     constexpr int PU = 4;  // chunks per barrier
-#if BIG_PART_PREFETCH
-    Entry e_nx[PU];  // entries of the next iteration, requested one iteration ahead
-#pragma unroll
-    for (int u = 0; u < PU; ++u) {
-        uint32_t idx = t.begin + u * THREADS + tid;
-        e_nx[u] = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
-    }
-#endif
     for (uint32_t c0 = t.begin; c0 < t.end; c0 += THREADS * PU, par ^= 1) {
         Entry e[PU];
         uint32_t balL[PU], balR[PU];
         bool goL[PU];
-#if BIG_PART_PREFETCH
-#pragma unroll
-        for (int u = 0; u < PU; ++u) {
-            e[u] = e_nx[u];
-            uint32_t idx = c0 + THREADS * PU + u * THREADS + tid;
-            e_nx[u] = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
-        }
-#else
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
             uint32_t idx = c0 + u * THREADS + tid;
             e[u] = idx < t.end ? ent_load(ent_in + idx) : make_uint2(0u, 0u);
         }
-#endif
         if (stash_r) {  // the split feature's bin of every row was left in the stash by the histogram pass
 #pragma unroll
             for (int u = 0; u < PU; ++u) {
@@ -601,7 +519,6 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 #pragma unroll
             for (int u = 0; u < PU; ++u) goL[u] = e[u].y && bins[(uint64_t)e[u].x * dstride + bf] <= bb;
         }
-#if BIG_PART_SCAN
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
             balL[u] = __ballot_sync(0xffffffffu, goL[u]);
@@ -627,28 +544,6 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
             }
             lbase += tot & 0xFFFFu; rbase += tot >> 16;
         }
-#else
-#pragma unroll
-        for (int u = 0; u < PU; ++u) {
-            balL[u] = __ballot_sync(0xffffffffu, goL[u]);
-            balR[u] = __ballot_sync(0xffffffffu, e[u].y && !goL[u]);
-            if (lane == 0) { s_wl[par][u][wid] = __popc(balL[u]); s_wr[par][u][wid] = __popc(balR[u]); }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < PU; ++u) {
-            uint32_t pl = 0, pr = 0, tl = 0, tr = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                uint32_t a = s_wl[par][u][w], b = s_wr[par][u][w];
-                if (w < (int)wid) { pl += a; pr += b; }
-                tl += a; tr += b;
-            }
-            if (goL[u]) ent_store(ent_out + t.begin + lbase + pl + __popc(balL[u] & lanemask_lt()), e[u]);
-            else if (e[u].y) ent_store(ent_out + t.end - 1u - (rbase + pr + __popc(balR[u] & lanemask_lt())), e[u]);
-            lbase += tl; rbase += tr;
-        }
-#endif
     }
     const uint32_t nLd = lbase;
     if (nLd == 0 || nLd == r) {  // cannot happen for a valid split; never loop on it

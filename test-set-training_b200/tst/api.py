@@ -130,6 +130,11 @@ class Engine:
         except Exception:
             pass
 
+    def set_option(self, name: str, value: int):
+        """Tuning / diagnostic knob of this handle (include/tst.h: tst_set_option)."""
+        check(_lib.lib().tst_set_option(self._h, name.encode(), C.c_int64(int(value))))
+        return self
+
     # ---- helpers
     def _stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.dev).cuda_stream)
@@ -554,4 +559,4 @@ class TsTForest:
         from .features import to_sklearn_arrays
 
         nodes, counts = self.export_tree(t)
-        return to_sklearn_arrays(nodes, counts, self._eng.edges)
+        return to_sklearn_arrays(nodes, counts, self._eng.edges, self._eng.n_edges)

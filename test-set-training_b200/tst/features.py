@@ -127,13 +127,16 @@ def gini_importances(nodes: np.ndarray, counts: np.ndarray, n_features: int) -> 
     return imp / s if s > 0 else imp
 
 
-def to_sklearn_arrays(nodes: np.ndarray, counts: np.ndarray, edges: np.ndarray | None = None) -> dict:
+def to_sklearn_arrays(nodes: np.ndarray, counts: np.ndarray, edges: np.ndarray | None = None, n_edges: np.ndarray | None = None) -> dict:
     """The field set of sklearn's Tree (SK/tree/_tree.pxd:15-25) from a canonical export; thresholds are
-    the raw-space bin edges when `edges` [d, 255] is given, else the bin index."""
+    the raw-space bin edges when `edges` [d, 255] is given, else the bin index.  A split at bin >= n_edges[feature]
+    separates every finite value from the NaN bin: its raw threshold is +inf (x <= inf goes left, NaN goes right)."""
     internal = nodes["feature"] >= 0
     thr = nodes["bin"].astype(np.float64)
     if edges is not None:
-        thr = np.where(internal, edges[np.maximum(nodes["feature"], 0), np.maximum(nodes["bin"], 0)], -2.0)
+        f, b = np.maximum(nodes["feature"], 0), np.maximum(nodes["bin"], 0)
+        ne = np.full(edges.shape[0], edges.shape[1], dtype=np.int64) if n_edges is None else np.asarray(n_edges, dtype=np.int64)
+        thr = np.where(b < ne[f], edges[f, np.minimum(b, edges.shape[1] - 1)], np.inf)
     c = counts.astype(np.float64)
     N = c.sum(1)
     return dict(children_left=nodes["left"].copy(), children_right=nodes["right"].copy(),

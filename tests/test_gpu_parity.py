@@ -246,9 +246,10 @@ def test_random_configurations_bit_exact(eng, seed):
 
 
 @pytest.mark.parametrize("n,d,C,k", [(3000, 16, 4, 3), (5001, 9, 3, 2), (2100, 40, 7, 4)])
-def test_dense_root_kernels_bit_exact(eng, monkeypatch, n, d, C, k):
+def test_dense_root_kernels_bit_exact(eng, request, n, d, C, k):
     """k_root_hist / k_root_split (TMA-streamed column-major histogram of the root) forced on small tables."""
-    monkeypatch.setenv("TST_ROOT_DENSE", "2")
+    eng.set_option("ROOT_DENSE", 2)
+    request.addfinalizer(lambda: eng.set_option("ROOT_DENSE", -1))
     rng = np.random.default_rng(n)
     bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
     y = ((bins[1].astype(int) * C) // 256).astype(np.uint8)
@@ -269,11 +270,12 @@ def test_dense_root_kernels_bit_exact(eng, monkeypatch, n, d, C, k):
     check_stats(gst, ost)
 
 
-def test_partition_stash_option_bit_exact(eng, monkeypatch):
+def test_partition_stash_option_bit_exact(eng, request):
     """TST_STASH=1: k_grow_big keeps the sampled bins of every row for its partition pass (off by default)."""
     from tst import synth
 
-    monkeypatch.setenv("TST_STASH", "1")
+    eng.set_option("STASH", 1)
+    request.addfinalizer(lambda: eng.set_option("STASH", 0))
     X, y = synth.vsi_table(30000, 24, 4, seed=8)
     edges, ne, bins = oracle_table(X)
     fold = H.assign_folds(y, np.ones(len(y), np.uint8), 2, 4)
@@ -300,6 +302,26 @@ def test_wide_tables_bit_exact(eng, d, C, mf):
     gn, gc = eng.export_tree(1, 1, C)
     ot = forest.tree(1, 1)
     compare_tree(gn, gc, ot.nodes, ot.counts, f"wide d={d}")
+
+
+@pytest.mark.parametrize("n,d,mf", [(6000, 20, "sqrt"), (20000, 64, "sqrt"), (4000, 9, None)])
+def test_two_class_packed_cta_tier_bit_exact(eng, n, d, mf):
+    """Binary labels, 256-valued bins, non-root nodes of > 256 rows that weigh < 2^16: k_grow_big's packed 16-bit
+    histogram (640 words per feature) is larger than the unpacked 2-class layout (544) -- the region must hold it."""
+    rng = np.random.default_rng(n + d)
+    bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
+    y = ((bins[0].astype(int) + bins[d - 1].astype(int)) > 255).astype(np.uint8)
+    flip = rng.random(n) < 0.25
+    y[flip] ^= 1
+    fold = H.assign_folds(y, np.ones(n, np.uint8), 3, 2)
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, 3, 6, 2, seed=9, keep=True, max_features=mf)
+    assert gst["row_visits_big"] > 0
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    for part, t in ((0, 0), (2, 5)):
+        gn, gc = eng.export_tree(part, t, 2)
+        ot = forest.tree(part, t)
+        compare_tree(gn, gc, ot.nodes, ot.counts, f"C=2 tree({part},{t})")
 
 
 def test_fewer_rows_than_folds(eng):
@@ -474,8 +496,9 @@ def test_squared_error_criterion_bit_exact(eng, n, d, L, k, mf, pk):
         compare_tree(gn, gc, ot.nodes, ot.counts, f"regression tree({part},{t})")
 
 
-def test_squared_error_dense_root_bit_exact(eng, monkeypatch):
-    monkeypatch.setenv("TST_ROOT_DENSE", "2")
+def test_squared_error_dense_root_bit_exact(eng, request):
+    eng.set_option("ROOT_DENSE", 2)
+    request.addfinalizer(lambda: eng.set_option("ROOT_DENSE", -1))
     from tst import quantise_target, synth
 
     X, y = synth.numeric_table(4000, 16, seed=9)
@@ -513,22 +536,65 @@ def test_regression_golden_and_public_api(eng):
 
 
 # --------------------------------------------------------------------------------------------- full size (BASELINE.json configs[4])
-def test_full_size_properties():
-    """1M x 64, 10 folds: too big for the CPU oracle in a unit test, so the checks are the size-independent properties
-    of the domain -- determinism, independence from batching / tree ranges / rank count (integer votes), Q0.16 vote
-    mass per held-out row, binary-tree counters, fully grown trees reproducing their in-bag labels."""
+@pytest.fixture(scope="module")
+def full_size():
+    """The headline table (BASELINE.json configs[4]): 1M x 64, 4 classes, 10 folds, binned and folded on the device."""
     import tst
     from tst import synth
 
     torch = _torch()
     n, d, C, k, T = 1_000_000, 64, 4, 10, 1000
     X, y = synth.scaleup_table(n, d, C, seed=0)
-    eng = tst.Engine(0)
-    eng.bin(X)
-    assert eng.n_edges.min() == 254  # continuous columns: all 255 bins used
-    y_dev = eng.to_dev(y, torch.uint8)
-    active = torch.ones(n, dtype=torch.uint8, device=eng.dev)
-    fold = eng.assign_folds(y_dev, active, k, C)
+    e = tst.Engine(0)
+    e.bin(X)
+    assert e.n_edges.min() == 254  # continuous columns: all 255 bins used
+    y_dev = e.to_dev(y, torch.uint8)
+    active = torch.ones(n, dtype=torch.uint8, device=e.dev)
+    fold = e.assign_folds(y_dev, active, k, C)
+    yield dict(eng=e, y=y, y_dev=y_dev, fold=fold, n=n, d=d, C=C, k=k, T=T)
+    e.close()
+
+
+def test_full_size_bit_exact_vs_oracle(full_size):
+    """1M x 64, 10 folds, trees t in [0, 2) of every fold (20 trees of ~295k nodes, root weight 900k > 2^16): GPU votes,
+    every work counter and one exported tree against the CPU oracle (OpenMP; ~1 s per tree per core)."""
+    import tst
+
+    fs = full_size
+    eng, d, C, k, T = fs["eng"], fs["d"], fs["C"], fs["k"], fs["T"]
+    bins = eng.get_bins()
+    fold_h = fs["fold"].cpu().numpy()
+    assert np.array_equal(fold_h, H.assign_folds(fs["y"], np.ones(fs["n"], np.uint8), k, C))
+    ov, ost, forest = H.fit_oof(bins, fs["y"], fold_h, k, T, C, H.make_params(d), seed=3, t0=0, t1=2, keep=True)
+    votes = eng.new_votes(C)
+    eng.stats(reset=True)
+    eng.fit_oof(fs["y_dev"], fs["fold"], k, T, C, tst.make_params(d), seed=3, t0=0, t1=2, votes=votes)
+    gst = eng.stats()
+    assert np.array_equal(votes.cpu().numpy().view(np.uint32), ov)
+    check_stats(gst, ost)
+    assert gst["max_depth"] == ost["max_depth"] and gst["trees"] == 20
+    # one whole tree, node by node (fold 7, tree 1), from a kept fit of the same (seed, gid)
+    e2 = tst.Engine(0)
+    try:
+        e2.set_bins(bins)
+        e2.fit_oof(fs["y_dev"], fs["fold"], k, T, C, tst.make_params(d, keep_forest=True, trees_in_flight=4), seed=3, t0=1, t1=2)
+        gn, gc = e2.export_tree(7, 1, C)
+    finally:
+        e2.close()
+    ot = forest.tree(7, 1)
+    compare_tree(gn, gc, ot.nodes, ot.counts, "1M x 64 tree (7, 1)")
+    assert int(ot.nodes["n_weighted"][0]) == 900_000
+
+
+def test_full_size_properties(full_size):
+    """1M x 64, 10 folds, beyond the oracle comparison above: the size-independent properties of the domain --
+    determinism, independence from batching / tree ranges / rank count (integer votes), Q0.16 vote
+    mass per held-out row, binary-tree counters, fully grown trees reproducing their in-bag labels."""
+    import tst
+
+    torch = _torch()
+    fs = full_size
+    eng, y_dev, fold, n, d, C, k, T = fs["eng"], fs["y_dev"], fs["fold"], fs["n"], fs["d"], fs["C"], fs["k"], fs["T"]
     sizes = torch.bincount(fold.long(), minlength=k)
     assert int(sizes.max() - sizes.min()) <= 1
     prm = tst.make_params(d)
@@ -568,4 +634,3 @@ def test_full_size_properties():
     s, cor, tot = eng.finalize(v_all, y_dev, fold, k, 2, C)
     acc = cor.double().sum() / tot.double().sum()
     assert 0.4 < float(acc) < 0.9 and float(s.min()) >= 0 and float(s.max()) <= 1
-    eng.close()
