@@ -367,20 +367,25 @@ def main():
 
     if rank == 0 and world == 1:
         bins_cm, fold_h = (eng.get_bins(), fold_dev.cpu().numpy()) if not args.no_cpu else (None, None)
+        per_fold = max(1, (2 * len(os.sched_getaffinity(0)) + K_FOLDS - 1) // K_FOLDS)  # the CPU sample's trees per fold
+        if not args.no_cpu:
+            # GPU side of the headline-table parity check, taken while the 1M x 64 table is still the engine's table
+            gv = eng.new_votes(N_CLASSES)
+            eng.stats(reset=True)
+            eng.fit_oof(y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=0, t1=per_fold, votes=gv)
+            gst = eng.stats()
+            gv_h = gv.cpu().numpy().view(np.uint32)
         if not args.no_secondary:  # before the CPU leg: idle OpenMP workers spin for a while and disturb millisecond latencies
             line["secondary"] = secondary_wallclock(tst, synth, eng)
         if not args.no_cpu and not args.no_secondary:
             line["secondary"]["cpu"] = secondary_cpu(synth)
         if not args.no_cpu:
-            line["cpu_baseline"], ost, ovotes, per_fold = cpu_baseline_port(X, yi, bins_cm, fold_h)
+            line["cpu_baseline"], ost, ovotes, per_fold_o = cpu_baseline_port(X, yi, bins_cm, fold_h)
+            assert per_fold_o == per_fold
             # parity on the headline table itself: the GPU fit of the sample's trees against the oracle's votes and counters
-            gv = eng.new_votes(N_CLASSES)
-            eng.stats(reset=True)
-            eng.fit_oof(y_dev, fold_dev, K_FOLDS, N_TREES, N_CLASSES, prm, seed=0, t0=0, t1=per_fold, votes=gv)
-            gst = eng.stats()
-            same_votes = bool(np.array_equal(gv.cpu().numpy().view(np.uint32), ovotes))
+            same_votes = bool(np.array_equal(gv_h, ovotes))
             same_stats = all(int(gst[k]) == int(ost[k]) for k in ("nodes", "leaves", "searched", "fallback", "inbag_rows", "trees", "oof_steps", "max_depth")) \
-                and int(gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"]) == int(ost["row_visits"])
+                and int(gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"] + gst.get("row_visits_sub", 0)) == int(ost["row_visits"])
             line["parity_1Mx64"] = same_votes and same_stats
             line["parity_1Mx64_detail"] = dict(trees=K_FOLDS * per_fold, votes_equal=same_votes, counters_equal=same_stats,
                                                nodes=int(ost["nodes"]), row_visits=int(ost["row_visits"]))

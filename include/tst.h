@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TST_ABI_VERSION 1
+#define TST_ABI_VERSION 2
 #define TST_MAX_EDGES 255        /* per feature; bins 0..254 + bin 255 for NaN */
 #define TST_MAX_CLASSES 32
 #define TST_MAX_FEATURES 1024
@@ -86,6 +86,9 @@ typedef struct {
     double ms_grow_tiny;        /* thread-per-subtree kernel (k_grow_tiny4); its visits are counted in row_visits_small */
     uint64_t launches_grow_tiny;
     uint64_t launches_root;     /* dense root kernels (k_root_hist + k_root_split), timed inside ms_prep */
+    uint64_t row_visits_sub;    /* ... by the CTA-per-subtree kernel (k_grow_sub: rows cached in shared memory) */
+    double ms_grow_sub;
+    uint64_t launches_grow_sub;
 } tst_stats;
 
 /* Canonical tree export: nodes in breadth-first order, i.e. sorted by (depth, begin). */
@@ -179,6 +182,15 @@ int tst_predict(tst_handle* h, const float* X_dev, int64_t n, uint32_t* votes_de
  * in which case TST_ERR_INVALID is returned and nothing is written). */
 int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node* nodes_host, uint32_t* counts_host,
                     int64_t cap, int64_t* n_nodes);
+
+/* (f3) "interpretable auditing" (REF/README.md:35): feature importances (mean decrease in impurity) of the trees this rank
+ * built in the LAST tst_fit_oof / tst_ibp round, accumulated on the device while the trees grew -- no kept forest needed, so
+ * they exist for the out-of-fold forests too.  Replaces SK/tree/_tree.pyx:1244-1280 + SK/ensemble/_forest.py feature_importances_.
+ * sums_host [d]: sum over those trees of floor(imp_t[f] * 2^32 / sum_f imp_t[f]) with imp_t in Q24 fixed point -- integers, so
+ * the sums of several ranks / calls add up in any order; forest importance = sums[f] / sum_f sums[f].  *n_counted = trees
+ * with at least one split.  raw_host (optional, [raw_cap_trees][d]): the per-tree Q24 impurity decreases, in the order the
+ * trees were enumerated (part-major, then t). */
+int tst_feature_importances(tst_handle* h, uint64_t* sums_host, int64_t* n_counted, uint64_t* raw_host, int64_t raw_cap_trees);
 
 /* Tuning / diagnostic knobs of one handle (INTEGRATION.md "knobs").  Defaults come from the environment variables
  * TST_<NAME>, read once in tst_create; names are case-insensitive, with or without the TST_ prefix. */

@@ -256,9 +256,18 @@ static inline double gain_mse(uint64_t SL, uint64_t NL, uint64_t SR, uint64_t NR
     return a + b;
 }
 
+/* Impurity decrease of one split in Q24 fixed point (feature importances, SK/tree/_tree.pyx:1244-1280):
+ * N*imp - N_L*imp_L - N_R*imp_R = gain - parent_term with the proxy the search maximised; floor(x * 2^24), negative -> 0. */
+static inline uint64_t imp_q24(double gain, double parent_term) {
+    volatile double c = gain - parent_term;
+    if (!(c > 0.0)) return 0;
+    volatile double scaled = c * 16777216.0;
+    return (uint64_t)floor(scaled);
+}
+
 static int grow_tree(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, int32_t C,
                      const orc_params* prm, uint32_t k0, uint32_t k1, uint32_t gid, entry_t* ent,
-                     entry_t* tmp, uint32_t n_inbag, node_store* S, orc_stats* st) {
+                     entry_t* tmp, uint32_t n_inbag, node_store* S, orc_stats* st, uint64_t* imp /* [d] or NULL */) {
     int32_t m = prm->max_features;
     uint32_t msl = (uint32_t)prm->min_samples_leaf, mss = (uint32_t)prm->min_samples_split;
     uint32_t* hist = (uint32_t*)calloc((size_t)ORC_NBINS * C, 4);
@@ -345,6 +354,19 @@ static int grow_tree(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t
             }
         }
         if (leaf || !found) { st->leaves++; continue; }
+        if (imp) {
+            uint64_t Sp = 0;
+            double parent;
+            if (prm->criterion == 1) {
+                for (int32_t c = 0; c < C; ++c) Sp += (uint64_t)c * tot[c];
+                volatile double sp = (double)Sp; volatile double sq = sp * sp;
+                parent = sq / (double)N;
+            } else {
+                for (int32_t c = 0; c < C; ++c) Sp += tot[c] * tot[c];
+                parent = (double)Sp / (double)N;
+            }
+            imp[bf] += imp_q24(bg, parent);
+        }
         /* stable partition: SK/tree/_partitioner.pyx:248-279 restated out-of-place */
         const uint8_t* col = bins_cm + (size_t)bf * n;
         uint32_t nl = 0, nr = 0;
@@ -372,7 +394,7 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
                 const int32_t* group, int32_t n_groups, int32_t k, int32_t n_trees, int32_t C,
                 const orc_params* prm, uint64_t seed, uint32_t gid_base, int32_t t0, int32_t t1,
                 int32_t rank, int32_t world, uint32_t* votes, orc_stats* stats, orc_forest** keep,
-                int32_t nthreads) {
+                int32_t nthreads, uint64_t* imp_sums /* [d + 1] or NULL: sum over trees of floor(imp_t[f] * 2^32 / sum_f imp_t[f]); [d] = trees with a split */) {
     if (n < 0 || n >= 0x7FFFFFF0LL || d < 1 || C < 1 || C > 256 || k < 1 || k > 250 || n_trees < 1 ||
         n_trees > 65535 || t0 < 0 || t1 > n_trees || t0 > t1 || world < 1 || rank < 0 || rank >= world ||
         prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2 ||
@@ -402,6 +424,8 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
         uint32_t* mult = (uint32_t*)calloc((size_t)(n > 0 ? n : 1), 4);
         entry_t* ent = (entry_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(entry_t));
         entry_t* tmp = (entry_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(entry_t));
+        uint64_t* imp = imp_sums ? (uint64_t*)malloc((size_t)d * 8) : NULL;
+        uint64_t* imp_loc = imp_sums ? (uint64_t*)calloc((size_t)d + 1, 8) : NULL;
 #pragma omp for schedule(dynamic, 1)
         for (int64_t task = 0; task < n_tasks; ++task) {
             int32_t part = (int32_t)(task / (t1 - t0));
@@ -437,8 +461,17 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
                 continue;
             }
             node_store S; memset(&S, 0, sizeof(S));
-            grow_tree(bins_cm, n, d, y, C, prm, k0, k1, gid, ent, tmp, ni, &S, &st);
+            if (imp) memset(imp, 0, (size_t)d * 8);
+            grow_tree(bins_cm, n, d, y, C, prm, k0, k1, gid, ent, tmp, ni, &S, &st, imp);
             st.trees++; st.inbag_rows += ni;
+            if (imp) {  /* per-tree normalisation in integers: the forest-level figure is a sum of these, in any order */
+                unsigned __int128 tsum = 0;
+                for (int32_t f2 = 0; f2 < d; ++f2) tsum += imp[f2];
+                if (tsum) {
+                    for (int32_t f2 = 0; f2 < d; ++f2) imp_loc[f2] += (uint64_t)((((unsigned __int128)imp[f2]) << 32) / tsum);
+                    imp_loc[d]++;
+                }
+            }
             /* OOF inference: SK/tree/_tree.pyx:954-996 on bins */
             if (votes) {
                 for (uint32_t q = fs; q < fe; ++q) {
@@ -473,8 +506,9 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
             total.searched += st.searched; total.fallback += st.fallback; total.inbag_rows += st.inbag_rows;
             total.trees += st.trees; total.oof_steps += st.oof_steps;
             if (st.max_depth > total.max_depth) total.max_depth = st.max_depth;
+            if (imp_sums) for (int32_t f2 = 0; f2 <= d; ++f2) imp_sums[f2] += imp_loc[f2];
         }
-        free(mult); free(ent); free(tmp);
+        free(mult); free(ent); free(tmp); free(imp); free(imp_loc);
     }
     if (stats) *stats = total;
     free(P.sorted); free(P.part_start);
@@ -608,7 +642,7 @@ int orc_ibp(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, uint
         if (rc) break;
         memset(votes, 0, (size_t)n * C * 4);
         rc = orc_fit_oof(bins_cm, n, d, y, fold, group, n_groups, k, n_trees, C, prm, seed,
-                         (uint32_t)r * per_round, 0, n_trees, 0, 1, votes, NULL, NULL, nthreads);
+                         (uint32_t)r * per_round, 0, n_trees, 0, 1, votes, NULL, NULL, nthreads, NULL);
         if (rc) break;
         if (s_per_round) orc_finalize(votes, y, fold, group, n, C, k, n_trees, s_per_round + (size_t)r * n, NULL, NULL);
         int64_t took = orc_ibp_select(votes, y, fold, n, C, k, vmin, batch, active);

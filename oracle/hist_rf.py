@@ -199,8 +199,9 @@ class Forest:
 
 
 def fit_oof(bins_cm, y, fold, k, n_trees, n_classes, params: OrcParams, seed=0, gid_base=0, t0=0, t1=None,
-            rank=0, world=1, group=None, n_groups=1, votes=None, keep=False, nthreads=0):
-    """-> (votes [n, C] uint32, stats dict, Forest | None)."""
+            rank=0, world=1, group=None, n_groups=1, votes=None, keep=False, nthreads=0, importances=None):
+    """-> (votes [n, C] uint32, stats dict, Forest | None).  importances: optional uint64 [d + 1] accumulator (zeroed by the
+    caller): sum over the trees built of floor(imp_t[f] * 2^32 / sum_f imp_t[f]); [d] counts the trees that split at all."""
     bins_cm = np.ascontiguousarray(bins_cm, dtype=np.uint8)
     d, n = bins_cm.shape
     y = np.ascontiguousarray(y, dtype=np.uint8)
@@ -215,11 +216,19 @@ def fit_oof(bins_cm, y, fold, k, n_trees, n_classes, params: OrcParams, seed=0, 
                            C.c_int32(k), C.c_int32(n_trees), C.c_int32(n_classes), C.byref(params),
                            C.c_uint64(seed), C.c_uint32(gid_base), C.c_int32(t0), C.c_int32(t1),
                            C.c_int32(rank), C.c_int32(world), _p(votes), C.byref(st),
-                           C.byref(fh) if keep else None, C.c_int32(nthreads))
+                           C.byref(fh) if keep else None, C.c_int32(nthreads), _p(importances))
     if rc:
         raise RuntimeError(f"orc_fit_oof rc={rc}")
     forest = Forest(fh, n_groups * k, n_trees, n_classes) if keep else None
     return votes, st.as_dict(), forest
+
+
+def importances_from_sums(sums) -> np.ndarray:
+    """Forest-level feature importances from the integer accumulator: mean over trees of the per-tree normalised importances,
+    normalised again (SK/ensemble/_forest.py feature_importances_)."""
+    s = np.asarray(sums[:-1], dtype=np.float64)
+    tot = s.sum()
+    return s / tot if tot > 0 else s
 
 
 def finalize(votes, y, fold, k, n_trees, group=None, n_groups=1):

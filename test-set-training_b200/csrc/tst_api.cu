@@ -16,6 +16,7 @@
 #include "tst_grow_small.cuh"
 #include "tst_grow_mid.cuh"
 #include "tst_grow_tiny.cuh"
+#include "tst_grow_sub.cuh"
 #include "tst_root.cuh"
 #include "tst_prep.cuh"
 #include "tst_quantile.cuh"
@@ -99,11 +100,13 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qmid0, qmid1, qsmall, qtiny, qtiny2, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
+        qmid0, qmid1, qsmall, qsub, qtiny, qtiny2, imp, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
     int32_t kept_C = 0, kept_n_trees = 0;
+    int64_t imp_trees = 0;  // trees of the last fit whose importances sit in `imp` ([imp_trees][d] uint64, Q24)
+    int32_t imp_d = 0;
     uint64_t kept_node_stride = 0, kept_leafc_stride = 0;
     // ibp / predict scratch
     DevBuf ibp_fold, ibp_votes, ibp_removed, pred_cm, pred_rm, sort_a, sort_b, sort_dk, gather;
@@ -112,6 +115,7 @@ struct tst_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
     cudaEvent_t ev_lvl[8][3] = {};  // per level of a group of blind levels: before big, between, after mid
     cudaEvent_t evi0 = nullptr, evi1 = nullptr;  // OOF inference
+    cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // CTA-per-subtree tier
     size_t l2_carve_set = 0, l2_carve_saved = 0;
     bool l2_carve_touched = false;
     // tuning / diagnostic knobs, read from the environment once in tst_create
@@ -121,7 +125,7 @@ struct tst_handle {
         int tiny_max = -1, mid_max = -1, stash_max = -1;
         int blind_levels = 4;
         long thin_nodes = 2048;
-        int sub_rows = -1;            // row capacity of the CTA-per-subtree tier (0 = tier off)
+        int sub_rows = -1;            // row capacity of the CTA-per-subtree tier (<= 0 = tier off, the default)
     } knobs;
     tst_stats stats;
     bool attrs_set = false;
@@ -189,7 +193,7 @@ static int create_resources(tst_handle* h, int world, int rank, const void* nccl
     CK(cudaEventCreate(&h->ev1));
     CK(cudaEventCreate(&h->ev2));
     CK(cudaEventCreate(&h->evm0)); CK(cudaEventCreate(&h->evm1)); CK(cudaEventCreate(&h->evs0)); CK(cudaEventCreate(&h->evs1));
-    CK(cudaEventCreate(&h->evi0)); CK(cudaEventCreate(&h->evi1));
+    CK(cudaEventCreate(&h->evi0)); CK(cudaEventCreate(&h->evi1)); CK(cudaEventCreate(&h->evk0)); CK(cudaEventCreate(&h->evk1));
     for (auto& lv : h->ev_lvl) for (auto& e : lv) CK(cudaEventCreate(&e));
     if (nccl_unique_id && world > 1) {
         if (load_nccl()) return fail(TST_ERR_UNSUPPORTED, "tst_create: libnccl.so.2 not found");
@@ -235,7 +239,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qsub, &h->imp, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk, &h->gather};
     for (DevBuf* b : bufs) b->release();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -243,7 +247,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
-    for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1, h->evi0, h->evi1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1, h->evi0, h->evi1, h->evk0, h->evk1}) if (e) cudaEventDestroy(e);
     // cudaLimitPersistingL2CacheSize is device-wide: hand it back the way the host application (torch) had it
     if (h->l2_carve_touched) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_carve_saved); cudaGetLastError(); }
     for (auto& lv : h->ev_lvl) for (auto& e : lv) if (e) cudaEventDestroy(e);
@@ -261,6 +265,8 @@ static int set_kernel_attrs(tst_handle* h) {
     CK(cudaFuncSetAttribute(k_grow_mid<4, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<2, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_sub<16, 2048, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sub_smem_bytes(16, 2048, 64)));
+    CK(cudaFuncSetAttribute(k_grow_sub<8, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sub_smem_bytes(8, 1024, 64)));
     CK(cudaFuncSetAttribute(k_root_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_root_split, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_bin_map, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -429,6 +435,12 @@ static int pull_stats(tst_handle* h, cudaStream_t st) {
     CK(cudaMemcpyAsync(&ds, h->dstats.p, sizeof(ds), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     h->stats.row_visits_big += ds.row_visits_big; h->stats.row_visits_mid += ds.row_visits_mid; h->stats.row_visits_small += ds.row_visits_small;
+    h->stats.row_visits_sub += ds.row_visits_sub;
+#ifdef SUB_PROFILE
+    fprintf(stderr, "[sub profile] CTAs %llu: cycles/CTA load %.0f wide %.0f phase2 %.0f | per CTA summed over warps: narrow %.0f small %.0f idle %.0f\n", ds.prof[6],
+            (double)ds.prof[0] / std::max(1ull, ds.prof[6]), (double)ds.prof[1] / std::max(1ull, ds.prof[6]), (double)ds.prof[2] / std::max(1ull, ds.prof[6]),
+            (double)ds.prof[3] / std::max(1ull, ds.prof[6]), (double)ds.prof[4] / std::max(1ull, ds.prof[6]), (double)ds.prof[5] / std::max(1ull, ds.prof[6]));
+#endif
     h->stats.nodes += ds.nodes; h->stats.leaves += ds.leaves; h->stats.searched += ds.searched; h->stats.fallback += ds.fallback;
     h->stats.inbag_rows += ds.inbag_rows; h->stats.oof_steps += ds.oof_steps;
     h->stats.max_depth = std::max(h->stats.max_depth, ds.max_depth);
@@ -507,6 +519,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     }
     const size_t total_trees = all.size();
     h->kept.clear();
+    h->imp_trees = 0; h->imp_d = d;
     if (total_trees == 0) return TST_OK;
     const double tr_parts = ms_since(t_entry);
     L2Window l2w(h, st);
@@ -524,12 +537,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / std::max<uint64_t>(2, tiny_eff + 1) + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
     const bool want_stash = kn.stash;  // see use_stash below
-    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (4 * qbig_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (5 * qbig_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
-                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qsmall.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
+                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qsmall.cap + h->qsub.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
     size_t budget = (size_t)((free_b + reclaim) * 0.6);
     if (keep) {
         size_t need = total_trees * arena_bytes;
@@ -552,6 +565,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->qmid0, B * qbig_per * sizeof(Task));
     ENSURE(h->qmid1, B * qbig_per * sizeof(Task));
     ENSURE(h->qsmall, B * qsmall_per * sizeof(Task));
+    ENSURE(h->qsub, B * qbig_per * sizeof(Task));
     // every warp of k_grow_small4 may leave up to TINY_RESERVE - 1 reserved slots unused
     const uint64_t qtiny_slack = (uint64_t)h->sm_count * 64u * SMALL_WARPS * TINY_RESERVE;
     ENSURE(h->qtiny, (B * qtiny_per + qtiny_slack) * 16);
@@ -569,8 +583,11 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         nodes_p = h->nodes.as<uint2>(); leafc_p = h->leafc.as<uint32_t>();
     }
 
+    ENSURE(h->imp, total_trees * (size_t)d * 8);
+    CK(cudaMemsetAsync(h->imp.p, 0, total_trees * (size_t)d * 8, st));
     GrowCtx g;
     memset(&g, 0, sizeof(g));
+    g.imp = h->imp.as<unsigned long long>();
     g.bins_rm = h->bins_rm.as<uint8_t>(); g.dstride = h->dstride; g.d = d; g.C = C; g.m = prm->max_features;
     g.max_depth = prm->max_depth; g.mss = (uint32_t)prm->min_samples_split; g.msl = (uint32_t)prm->min_samples_leaf;
     g.criterion = (uint32_t)prm->criterion;
@@ -606,18 +623,6 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint32_t small_per_warp = small_packed ? ((64u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
-    // dense root histograms (tst_root.cuh): big tables only; needs m <= 8 and the histogram + 2 TMA stages in shared memory
-    const size_t root_smem = (size_t)g.m * g.FS * 4 + 2 * (size_t)(g.m + 2) * ROOT_TILE;
-    bool root_dense = n >= 65536 && g.m <= 8 && root_smem <= 200 * 1024 && max_train > 32u * MID_R;
-    if (kn.root_dense == 0) root_dense = false;  // 0 = off, 2 = on for any table size (tests)
-    if (kn.root_dense == 2) root_dense = g.m <= 8 && root_smem <= 200 * 1024 && max_train > 32u * MID_R;
-    if (root_dense) {
-        ENSURE(h->ghist, B * (size_t)g.m * g.FS * 4);
-        ENSURE(h->rsplit, B * sizeof(RootSplit));
-        ENSURE(h->y_pad, (size_t)h->ld);
-        CK(cudaMemsetAsync(h->y_pad.p, 0, (size_t)h->ld, st));
-        CK(cudaMemcpyAsync(h->y_pad.p, y_dev, (size_t)n, cudaMemcpyDeviceToDevice, st));
-    }
     uint32_t* counters = h->counters.as<uint32_t>();  // [2p], [2p+1] big / mid queue counts of parity p, [4] small, [5] tiny, [6+r] tiny histogram
     g.qsmall_count = counters + 4;
     g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
@@ -633,6 +638,30 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.mid_max = mid_smem <= 200 * 1024 ? 32u * MID_R : SMALL_MAX;
     g.mid_packed = mid_packed ? 1u : 0u;
     if (kn.mid_max >= 0) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)kn.mid_max));
+    // CTA-per-subtree tier (tst_grow_sub.cuh): packed 4-class Gini, rows of <= 64 bytes.  It takes every node of 33 .. sub_max
+    // rows that weighs < 2^16 and finishes the whole subtree, so the warp-per-node tier is off and the warp-per-subtree kernel only
+    // sees the rare <= 32-row children of CTA-tier nodes.  SUB_ROWS: 2048 (16 warps, 1 CTA/SM, default), 1024 (8 warps, 2 CTAs/SM), 0 = off.
+    // Measured on B200 (profiles/r02_k_grow_sub.md): bit-exact but 3x slower than the level-synchronous tiers -- the row cache leaves
+    // 16 warps per SM for code that is a chain of dependent steps -- so it is OFF by default (SUB_ROWS=2048 / 1024 turns it on).
+    int sub_rows = 0;
+    if (kn.sub_rows > 0 && packed_ok && h->dstride <= 64 && B <= 65535) sub_rows = kn.sub_rows >= 2048 ? 2048 : (kn.sub_rows >= 1024 ? 1024 : 0);
+    g.sub_max = (uint32_t)sub_rows;
+    g.qsub = h->qsub.as<Task>(); g.qsub_count = counters + 20;
+    if (sub_rows) g.mid_max = SMALL_MAX;
+    g.big_min = sub_rows ? (uint32_t)sub_rows : g.mid_max;
+    const size_t sub_smem = sub_rows ? sub_smem_bytes(sub_rows == 2048 ? 16 : 8, sub_rows, h->dstride) : 0;
+    // dense root histograms (tst_root.cuh): big tables only; needs m <= 8 and the histogram + 2 TMA stages in shared memory
+    const size_t root_smem = (size_t)g.m * g.FS * 4 + 2 * (size_t)(g.m + 2) * ROOT_TILE;
+    bool root_dense = n >= 65536 && g.m <= 8 && root_smem <= 200 * 1024 && max_train > g.big_min;
+    if (kn.root_dense == 0) root_dense = false;  // 0 = off, 2 = on for any table size (tests)
+    if (kn.root_dense == 2) root_dense = g.m <= 8 && root_smem <= 200 * 1024 && max_train > g.big_min;
+    if (root_dense) {
+        ENSURE(h->ghist, B * (size_t)g.m * g.FS * 4);
+        ENSURE(h->rsplit, B * sizeof(RootSplit));
+        ENSURE(h->y_pad, (size_t)h->ld);
+        CK(cudaMemsetAsync(h->y_pad.p, 0, (size_t)h->ld, st));
+        CK(cudaMemcpyAsync(h->y_pad.p, y_dev, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    }
 
     if (trace) {
         cudaStreamSynchronize(st);
@@ -643,7 +672,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         const auto t_batch = now();
         double tr_boot = 0, tr_levels = 0, tr_tail = 0;
         const uint32_t nb = (uint32_t)std::min(B, total_trees - b0);
-        for (uint32_t i = 0; i < nb; ++i) all[b0 + i].arena = keep ? (uint32_t)(b0 + i) : i;
+        for (uint32_t i = 0; i < nb; ++i) { all[b0 + i].arena = keep ? (uint32_t)(b0 + i) : i; all[b0 + i].imp_row = (uint32_t)(b0 + i); }
         CK(cudaMemcpyAsync(h->trees.p, all.data() + b0, (size_t)nb * sizeof(TreeDesc), cudaMemcpyHostToDevice, st));
         g.qbig_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qbig_per);
         g.qsmall_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qsmall_per);
@@ -684,7 +713,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             h->stats.kernel_launches += 5;
         }
         CK(cudaEventRecord(h->ev1, st));
-        CK(cudaMemcpyAsync(h->h_pinned, counters, 32, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->h_pinned, counters, 128, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_prep += ms; }
         tr_boot = ms_since(t_batch);
@@ -695,7 +724,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         // upper bounds (children <= 2 x parents) and the kernels read the real counts on the device.
         int cur = 0;
         uint64_t level_guard = 0;
-        bool small_started = false, tiny_timed = false;
+        bool small_started = false, tiny_timed = false, sub_timed = false;
         const int blind_levels = kn.blind_levels;
         const uint64_t thin_nodes = (uint64_t)kn.thin_nodes;  // a level with at most this many nodes starts a group of blind levels
         uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1];
@@ -740,7 +769,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 ub_big = nb2; ub_mid = nm2;
                 if (++level_guard > n_cap + 8) return fail(TST_ERR_STATE, "tree growth did not terminate");
             }
-            CK(cudaMemcpyAsync(h->h_pinned, counters, 32, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h->h_pinned, counters, 128, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             {   // every level is timed, also the ones launched blind (the top levels of a small batch of trees are "thin" too)
                 float ms_b = 0, ms_m = 0;
@@ -757,6 +786,18 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             if (nbig > g.qbig_cap || nmid > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
         tr_levels = ms_since(t_batch);
+        // ---- subtrees of 33 .. sub_max rows: one CTA each, rows cached in shared memory, every level of the subtree in one launch
+        const uint32_t nsub = g.sub_max ? h->h_pinned[20] : 0u;
+        if (nsub > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "subtree queue overflowed");
+        if (nsub) {
+            CK(cudaEventRecord(h->evk0, st));
+            if (g.sub_max == 2048u) k_grow_sub<16, 2048, 1><<<nsub, 512, sub_smem, st>>>(g, g.qsub, nsub);
+            else k_grow_sub<8, 1024, 2><<<nsub, 256, sub_smem, st>>>(g, g.qsub, nsub);
+            CKL();
+            CK(cudaEventRecord(h->evk1, st));
+            sub_timed = true;
+            h->stats.kernel_launches++; h->stats.launches_grow_sub++;
+        }
         // ---- subtrees with 7..32 rows: one warp each
         const uint32_t nsmall = h->h_pinned[4];
         if (nsmall > g.qsmall_cap) return fail(TST_ERR_OVERFLOW, "small-node queue overflowed");
@@ -827,6 +868,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         CK(cudaStreamSynchronize(st));
         if (small_started) { float ms = 0; cudaEventElapsedTime(&ms, h->evs0, h->evs1); h->stats.ms_grow_small += ms; }
         if (tiny_timed) { float ms = 0; cudaEventElapsedTime(&ms, h->evm0, h->evm1); h->stats.ms_grow_tiny += ms; }
+        if (sub_timed) { float ms = 0; cudaEventElapsedTime(&ms, h->evk0, h->evk1); h->stats.ms_grow_sub += ms; }
         if (infer_timed) { float ms = 0; cudaEventElapsedTime(&ms, h->evi0, h->evi1); h->stats.ms_infer += ms; }
         if (keep) {
             std::vector<TreeDesc> back(nb);
@@ -835,6 +877,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 h->kept.push_back({(int32_t)all_id[b0 + i].part, (int32_t)all_id[b0 + i].t, back[i].arena, back[i].n_inbag});
         }
         h->stats.trees += nb;
+        h->imp_trees = (int64_t)(b0 + nb);
         if ((rc = pull_stats(h, st))) return rc;
         tr_tail = ms_since(t_batch);
         if (trace) fprintf(stderr, "[tst trace] batch of %u trees: boot+roots %.3f ms, levels %.3f ms (%d host round trips, %.3f ms outside the level kernels), small+tiny+infer+stats %.3f ms\n",
@@ -1034,6 +1077,33 @@ extern "C" int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node*
     if (!nodes_host || !counts_host || cap < (int64_t)out.size()) return fail(TST_ERR_INVALID, "tst_export_tree: capacity too small");
     memcpy(nodes_host, out.data(), out.size() * sizeof(tst_node));
     memcpy(counts_host, cnt.data(), out.size() * C * 4);
+    return TST_OK;
+}
+
+// --------------------------------------------------------------------------------------------- interpretability
+extern "C" int tst_feature_importances(tst_handle* h, uint64_t* sums_host, int64_t* n_counted, uint64_t* raw_host, int64_t raw_cap_trees) {
+    if (!h || !sums_host || !n_counted) return fail(TST_ERR_INVALID, "tst_feature_importances: null argument");
+    if (h->imp_d <= 0) return fail(TST_ERR_STATE, "tst_feature_importances: no fit yet");
+    CK(cudaSetDevice(h->device));
+    const int d = h->imp_d;
+    const int64_t T = h->imp_trees;
+    for (int f = 0; f < d; ++f) sums_host[f] = 0;
+    *n_counted = 0;
+    if (T == 0) return TST_OK;
+    std::vector<uint64_t> raw((size_t)T * d);
+    CK(cudaMemcpy(raw.data(), h->imp.p, (size_t)T * d * 8, cudaMemcpyDeviceToHost));
+    for (int64_t t = 0; t < T; ++t) {
+        const uint64_t* r = raw.data() + (size_t)t * d;
+        unsigned __int128 tsum = 0;
+        for (int f = 0; f < d; ++f) tsum += r[f];
+        if (!tsum) continue;  // a one-leaf tree has no importances (SK/ensemble/_forest.py: node_count > 1)
+        for (int f = 0; f < d; ++f) sums_host[f] += (uint64_t)((((unsigned __int128)r[f]) << 32) / tsum);
+        ++*n_counted;
+    }
+    if (raw_host) {
+        if (raw_cap_trees < T) return fail(TST_ERR_INVALID, "tst_feature_importances: raw buffer holds fewer trees than the last fit built");
+        memcpy(raw_host, raw.data(), (size_t)T * d * 8);
+    }
     return TST_OK;
 }
 

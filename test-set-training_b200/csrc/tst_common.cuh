@@ -104,11 +104,12 @@ struct TreeDesc {  // one tree of the batch in flight
     uint32_t fs;       // held-out rows are sorted[fs .. fs + fsz)
     uint32_t arena;    // node-arena slot (batch-local unless keep_forest)
     uint32_t n_inbag;  // distinct in-bag rows (written by k_boot_scan)
-    uint32_t pad;
+    uint32_t imp_row;  // row of the importance table: index of the tree among this call's trees
 };
 
 struct DevStats {
-    unsigned long long row_visits_big, row_visits_mid, row_visits_small, nodes, leaves, searched, fallback, oof_steps, inbag_rows;
+    unsigned long long row_visits_big, row_visits_mid, row_visits_small, nodes, leaves, searched, fallback, oof_steps, inbag_rows, row_visits_sub;
+    unsigned long long prof[8];  // -DSUB_PROFILE builds: clock cycles of k_grow_sub (load, wide, phase 2 per CTA; narrow, small, idle per warp)
     uint32_t max_depth;
     uint32_t error;  // sticky: 1 = multiplicity overflow, 2 = queue overflow, 3 = bootstrap weight mismatch
 };
@@ -143,6 +144,10 @@ struct GrowCtx {
     uint32_t qbig_cap;
     Task* qmid_next;  // warp-per-node queue for the next level (SMALL_MAX < rows <= mid_max)
     uint32_t* qmid_next_count;
+    Task* qsub;       // CTA-per-subtree queue (k_grow_sub): SMALL_MAX < rows <= sub_max and weight < 2^16; filled by every level, drained once
+    uint32_t* qsub_count;
+    uint32_t sub_max; // 0 disables the tier
+    uint32_t big_min; // a tree root with more distinct rows than this is a "big root" (dense root kernels + k_grow_big)
     uint32_t mid_max; // == SMALL_MAX disables the mid tier
     uint32_t mid_packed; // k_grow_mid4: 16-bit packed class counts, nodes must weigh <= 65535
     Task* qsmall;
@@ -153,6 +158,7 @@ struct GrowCtx {
     uint32_t qtiny_cap;
     uint32_t tiny_max; // 0 disables the tier
     DevStats* stats;
+    unsigned long long* imp;  // [call's trees][d] impurity decrease per feature in Q24 fixed point (nullptr: not collected)
     const RootSplit* rsplit;  // non-null: big roots were split by the dense root kernels (Task.pad0 == 1)
     uint32_t big_packed;  // k_grow_big: packed 16-bit histogram + scan for nodes that weigh < 2^16 (<= 4 classes, m <= 8)
     uint32_t stash_max_rows;  // nodes above this size gather instead: their stash would stream through HBM (the table itself is L2-resident)
@@ -235,10 +241,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-__device__ __forceinline__ void tiny_push(const GrowCtx& g, uint32_t tree, uint32_t begin, uint32_t rows, uint32_t depth, uint32_t slot) {
-    // TinyTask = (begin, slot, depth, tree | rows << 16)
+// Mean decrease in impurity (SK/tree/_tree.pyx:1244-1280) accumulated while the tree grows: a split adds
+// N*imp - N_L*imp_L - N_R*imp_R = gain - parent_term to its feature, with gain the proxy the split search maximised
+// (S_L/N_L + S_R/N_R for Gini, S_L^2/N_L + S_R^2/N_R for squared error) and parent_term the same expression of the unsplit
+// node (S/N resp. S^2/N).  Stored as floor(x * 2^24) in uint64: integer sums are independent of the order the nodes finish in.
+__device__ __forceinline__ void imp_add(const GrowCtx& g, uint32_t imp_row, uint32_t f, double gain, double parent_term) {
+    if (g.imp == nullptr) return;
+    const double c = __dadd_rn(gain, -parent_term);
+    if (c > 0.0) atomicAdd(&g.imp[(uint64_t)imp_row * (uint32_t)g.d + f], __double2ull_rd(__dmul_rn(c, 16777216.0)));
+}
+__device__ __forceinline__ double imp_parent_gini(unsigned long long S, uint32_t N) { return __ddiv_rn(__ull2double_rn(S), __uint2double_rn(N)); }
+__device__ __forceinline__ double imp_parent_mse(unsigned long long S, uint32_t N) {
+    const double s = __ull2double_rn(S);
+    return __ddiv_rn(__dmul_rn(s, s), __uint2double_rn(N));
+}
+
+__device__ __forceinline__ void tiny_push(const GrowCtx& g, uint32_t tree, uint32_t begin, uint32_t rows, uint32_t depth, uint32_t slot, uint32_t buf) {
+    // TinyTask = (begin, slot, depth | buf << 31, tree | rows << 16); buf = the entry buffer holding the rows (0 = entA, 1 = entB)
     uint32_t i = atomicAdd(g.qtiny_count, 1u);  // (the size histogram for the sort is taken by k_tiny_hist, not here)
-    if (i < g.qtiny_cap) ((uint4*)g.qtiny)[i] = make_uint4(begin, slot, depth, tree | (rows << 16));
+    if (i < g.qtiny_cap) ((uint4*)g.qtiny)[i] = make_uint4(begin, slot, depth | (buf << 31), tree | (rows << 16));
     else g.stats->error = 2;
 }
 

@@ -34,7 +34,7 @@ __device__ __forceinline__ bool stop_rule(const GrowCtx& g, uint32_t N, uint32_t
 // routed by size to the CTA-per-node queue, the warp-per-node queue or the warp-per-subtree queue.
 __device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint2* nodes, uint32_t* leafc,
                                            const uint32_t* tot, const uint32_t* bestL, uint32_t N, uint32_t nLd,
-                                           uint32_t bf, uint32_t bb) {
+                                           uint32_t bf, uint32_t bb, double gain /* the split's exact gain; < 0: recompute it from the counts */) {
     const int C = g.C;
     uint32_t NL = 0;
     for (int c = 0; c < C; ++c) NL += bestL[c];
@@ -64,16 +64,27 @@ __device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint
             ct.pad0 = ct.pad2 = 0;
             ct.pad1 = Nc;  // the node's weight: k_grow_big picks its packed path from it
             const uint32_t cr = ce - cb;
-            if (cr <= g.tiny_max) tiny_push(g, t.tree, cb, cr, t.depth + 1u, cslot);
+            if (cr <= g.tiny_max) tiny_push(g, t.tree, cb, cr, t.depth + 1u, cslot, (t.depth + 1u) & 1u);  // the children sit in the buffer of their depth
+            else if (cr <= SMALL_MAX) queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
+            else if (cr <= g.sub_max && Nc <= 65535u) queue_push(g.qsub, g.qsub_count, g.qbig_cap, g.stats, ct);  // whole subtree in one CTA
             else if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
-            else if (cr > SMALL_MAX && (Nc <= 65535u || !g.mid_packed)) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
-            else if (cr > SMALL_MAX) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);  // too heavy for 16-bit packed counts
-            else queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
+            else if (Nc <= 65535u || !g.mid_packed) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
+            else queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);  // too heavy for 16-bit packed counts
         }
     }
     atomicAdd(&g.stats->nodes, 1ull + new_leaves);
     if (new_leaves) { atomicAdd(&g.stats->leaves, new_leaves); atomicMax(&g.stats->max_depth, t.depth + 1u); }
     atomicAdd(&g.stats->searched, 1ull);
+    if (g.imp != nullptr) {  // the split's impurity decrease (the same doubles as the split search)
+        unsigned long long SL = 0, SR = 0, S = 0;
+        const bool mse = g.criterion == 1u;
+        for (int c = 0; c < C; ++c) {
+            const unsigned long long l = bestL[c], r = tot[c] - bestL[c], a = tot[c];
+            SL += mse ? l * (unsigned)c : l * l; SR += mse ? r * (unsigned)c : r * r; S += mse ? a * (unsigned)c : a * a;
+        }
+        if (gain < 0.0) gain = mse ? mse_gain(SL, NL, SR, NR) : gini_gain(SL, NL, SR, NR);  // roots split by the dense root kernels
+        imp_add(g, g.trees[t.tree].imp_row, bf, gain, mse ? imp_parent_mse(S, N) : imp_parent_gini(S, N));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -553,7 +564,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 
     // ---- node record + children (leaf children are finished here, the rest are queued)
     if (tid == 0) {
-        emit_split(g, t, nodes, leafc, s_tot, s_bestL, s_N, nLd, bf, bb);
+        emit_split(g, t, nodes, leafc, s_tot, s_bestL, s_N, nLd, bf, bb, presplit ? -1.0 : s_bgain);
         atomicAdd(&g.stats->row_visits_big, (unsigned long long)r);
     }
 }
@@ -702,6 +713,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task
             const uint32_t right_slot = slot + 2u * nLd;
             if (lane == 0) {
                 write_internal(nodes, slot, right_slot, bf, bb);
+                if (g.imp != nullptr) {
+                    unsigned long long S = 0;
+                    for (int c = 0; c < C; ++c) S += (unsigned long long)s_tot[c] * (g.criterion == 1u ? (uint32_t)c : s_tot[c]);
+                    imp_add(g, td.imp_row, bf, best_gain, g.criterion == 1u ? imp_parent_mse(S, N) : imp_parent_gini(S, N));
+                }
                 s_stack[sp * 3] = (lo + nLd) | (hi << 8);
                 s_stack[sp * 3 + 1] = depth + 1u;
                 s_stack[sp * 3 + 2] = right_slot;

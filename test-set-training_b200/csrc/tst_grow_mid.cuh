@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
         rbase += __popc(balR);
     }
     if (lane == 0) {
-        emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nLd, bf, bbin);
+        emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nLd, bf, bbin, best_gain);
         atomicAdd(&g.stats->row_visits_mid, (unsigned long long)r);
     }
 }
@@ -401,7 +401,8 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         rbase += __popc(balR);
     }
     if (lane == 0) {
-        emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nLd, bf, bbin);
+        emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nLd, bf, bbin, best_gain);
         atomicAdd(&g.stats->row_visits_mid, (unsigned long long)r);
     }
 }
+

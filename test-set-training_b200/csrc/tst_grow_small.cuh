@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                 if (active) ent_store(eb + t.begin + lane, e);
                 if (lane == 0) {
                     if (res_i == res_end) { res_i = atomicAdd(g.qtiny_count, TINY_RESERVE); res_end = res_i + TINY_RESERVE; }
-                    if (res_i < g.qtiny_cap) ((uint4*)g.qtiny)[res_i] = make_uint4(abs_begin, slot, depth, t.tree | (rr << 16));
+                    if (res_i < g.qtiny_cap) ((uint4*)g.qtiny)[res_i] = make_uint4(abs_begin, slot, depth | ((depth & 1u) << 31), t.tree | (rr << 16));
                     else g.stats->error = 2;
                     ++res_i;
                 }
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
             const uint32_t right_slot = slot + 2u * nLd;
             if (lane == 0) {
                 write_internal(nodes, slot, right_slot, bf, bb);
+                imp_add(g, td.imp_row, bf, best_gain, imp_parent_gini((unsigned long long)(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3), N));
                 s_stack[sp * 3] = (lo + nLd) | (hi << 8);
                 s_stack[sp * 3 + 1] = depth + 1u;
                 s_stack[sp * 3 + 2] = right_slot;

@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
     if (live) tk = tasks[ti];
     if (live && (tk.w >> 16) != 0u) {  // 0 rows: an unused slot of a warp's reservation in k_grow_small4
         const uint32_t tree = tk.w & 0xFFFFu, r = tk.w >> 16;
-        const uint32_t gid = g.trees[tree].gid, arena = g.trees[tree].arena;
-        const Entry* __restrict__ ent = ((tk.z & 1u) ? g.entB : g.entA) + (uint64_t)tree * g.n_cap + tk.x;
+        const uint32_t gid = g.trees[tree].gid, arena = g.trees[tree].arena, imp_row = g.trees[tree].imp_row;
+        const Entry* __restrict__ ent = ((tk.z >> 31) ? g.entB : g.entA) + (uint64_t)tree * g.n_cap + tk.x;  // bit 31: which buffer the producer parked the rows in
         uint2* nodes = g.nodes + (uint64_t)arena * g.node_stride;
         uint32_t* leafc = g.leafc + (uint64_t)arena * g.leafc_stride;
         uint32_t row[TMAX];
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
         uint32_t st_mask[TMAX], st_begin[TMAX], st_slot[TMAX], st_depth[TMAX];
         unsigned long long st_tot[TMAX];
         int sp = 0;
-        uint32_t mask = (1u << r) - 1u, begin = tk.x, slot = tk.y, depth = tk.z;
+        uint32_t mask = (1u << r) - 1u, begin = tk.x, slot = tk.y, depth = tk.z & 0x7FFFFFFFu;
         unsigned long long tot = 0;
 #pragma unroll
         for (int k = 0; k < TMAX; ++k) tot += cw[k];
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
                 if (nLd == 0 || mL == mask) { g.stats->error = 4; break; }
                 const uint32_t right_slot = slot + 2u * nLd;
                 write_internal(nodes, slot, right_slot, bf, bb);
+                imp_add(g, imp_row, bf, best_gain, imp_parent_gini((unsigned long long)(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3), N));
                 // children: leaves are finished here, the others are stacked (right first, so the left one is next)
 #pragma unroll
                 for (int side = 1; side >= 0; --side) {

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_root_hist(GrowCtx g, const uint8_t* __r
     const uint32_t tid = threadIdx.x;
     const int C = g.C, d = g.d, m = g.m;
     const TreeDesc td = g.trees[blockIdx.y];
-    if (td.n_inbag <= g.mid_max) return;  // not a big root
+    if (td.n_inbag <= g.big_min) return;  // not a big root
     uint32_t* s_hist = (uint32_t*)s_raw;
     uint8_t* s_stage = s_raw + (size_t)m * g.FS * 4;
     const uint32_t stage_bytes = (uint32_t)(m + 2) * ROOT_TILE;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) k_root_split(GrowCtx g, const uint32_t* _
     const int C = g.C, d = g.d, m = g.m;
     const TreeDesc td = g.trees[blockIdx.x];
     RootSplit* rs = out + blockIdx.x;
-    if (td.n_inbag <= g.mid_max) { if (tid == 0) rs->state = 0; return; }
+    if (td.n_inbag <= g.big_min) { if (tid == 0) rs->state = 0; return; }
     const uint32_t* gh = ghist + (uint64_t)blockIdx.x * (uint64_t)(m * g.FS);
     for (int i = tid; i < m * g.FS; i += 256) s_hist[i] = gh[i];
     if (tid == 0) root_features(g, td.gid, d, m, s_perm, s_feat);

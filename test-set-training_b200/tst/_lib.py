@@ -41,7 +41,8 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("levels", C.c_uint64), ("max_depth", C.c_uint32),
                 ("pad", C.c_uint32), ("ms_grow_big", C.c_double), ("ms_grow_small", C.c_double),
                 ("ms_prep", C.c_double), ("ms_infer", C.c_double), ("launches_grow_big", C.c_uint64),
-                ("launches_grow_small", C.c_uint64), ("ms_grow_mid", C.c_double), ("launches_grow_mid", C.c_uint64), ("row_visits_mid", C.c_uint64), ("ms_grow_tiny", C.c_double), ("launches_grow_tiny", C.c_uint64), ("launches_root", C.c_uint64)]
+                ("launches_grow_small", C.c_uint64), ("ms_grow_mid", C.c_double), ("launches_grow_mid", C.c_uint64), ("row_visits_mid", C.c_uint64), ("ms_grow_tiny", C.c_double), ("launches_grow_tiny", C.c_uint64), ("launches_root", C.c_uint64),
+                ("row_visits_sub", C.c_uint64), ("ms_grow_sub", C.c_double), ("launches_grow_sub", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}
@@ -79,7 +80,7 @@ def lib():
         L.tst_last_error.restype = C.c_char_p
         for name in ("tst_create", "tst_destroy", "tst_bin", "tst_bin_auto", "tst_set_bins", "tst_get_bins", "tst_assign_folds",
                      "tst_fit_oof", "tst_reduce_votes", "tst_allreduce_votes", "tst_nccl_unique_id", "tst_finalize", "tst_ibp_select", "tst_ibp", "tst_predict",
-                     "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_abi_version", "tst_set_option"):
+                     "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_abi_version", "tst_set_option", "tst_feature_importances"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -87,7 +88,7 @@ def lib():
 
 EXPORTS = ["tst_abi_version", "tst_last_error", "tst_create", "tst_destroy", "tst_bin", "tst_bin_auto", "tst_set_bins", "tst_get_bins",
            "tst_assign_folds", "tst_fit_oof", "tst_reduce_votes", "tst_allreduce_votes", "tst_nccl_unique_id", "tst_finalize", "tst_ibp_select", "tst_ibp",
-           "tst_predict", "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_set_option"]
+           "tst_predict", "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_set_option", "tst_feature_importances"]
 
 
 def check(rc: int):

@@ -276,6 +276,34 @@ class Engine:
                                          counts.ctypes.data_as(C.c_void_p), C.c_int64(n_nodes.value), C.byref(n_nodes)))
         return nodes, counts
 
+    def importance_sums(self, raw: bool = False):
+        """Integer feature-importance accumulator of the trees THIS rank built in the last fit (include/tst.h:
+        tst_feature_importances): -> (sums uint64 [d], trees counted[, raw Q24 uint64 [trees, d]])."""
+        sums = np.zeros(self.d, dtype=np.uint64)
+        n_counted = C.c_int64(0)
+        raw_arr, cap = None, 0
+        if raw:
+            cap = int(self.stats()["trees"])
+            raw_arr = np.zeros((max(cap, 1), self.d), dtype=np.uint64)
+        check(_lib.lib().tst_feature_importances(self._h, sums.ctypes.data_as(C.c_void_p), C.byref(n_counted),
+                                                 None if raw_arr is None else raw_arr.ctypes.data_as(C.c_void_p), C.c_int64(cap)))
+        return (sums, int(n_counted.value), raw_arr[:cap]) if raw else (sums, int(n_counted.value))
+
+    def feature_importances(self) -> np.ndarray:
+        """Mean decrease in impurity per feature over all trees of the last fit (all ranks), normalised to sum 1
+        (SK/ensemble/_forest.py feature_importances_): accumulated on the device while the trees grew."""
+        sums, _ = self.importance_sums()
+        if self.world > 1:
+            torch = _torch()
+            import torch.distributed as dist
+
+            t = torch.from_numpy(sums.view(np.int64).copy()).to(self.dev)
+            dist.all_reduce(t)  # integer sums: any order
+            sums = t.cpu().numpy().view(np.uint64)
+        s = sums.astype(np.float64)
+        tot = s.sum()
+        return s / tot if tot > 0 else s
+
     def stats(self, reset=False) -> dict:
         st = Stats()
         check(_lib.lib().tst_get_stats(self._h, C.byref(st)))
@@ -311,6 +339,7 @@ class TsTResult:
     fold_accuracy: np.ndarray   # [n_groups * k] blind accuracy per (group, fold)
     classes: np.ndarray
     stats: dict = field(default_factory=dict)
+    feature_importances: np.ndarray | None = None  # [d] mean decrease in Gini impurity over the k x n_trees out-of-fold forests
 
 
 def run_tst(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, max_depth=None, min_samples_split=2,
@@ -348,7 +377,7 @@ def run_tst(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, max_depth=No
     votes_h = votes.cpu().numpy().view(np.uint32)
     tot = total.cpu().numpy().astype(np.float64)
     acc = np.divide(correct.cpu().numpy().astype(np.float64), tot, out=np.full_like(tot, np.nan), where=tot > 0)
-    return TsTResult(s_h, votes_h, fold_dev.cpu().numpy(), acc, classes, eng.stats())
+    return TsTResult(s_h, votes_h, fold_dev.cpu().numpy(), acc, classes, eng.stats(), eng.feature_importances())
 
 
 # ------------------------------------------------------------------------------------------------- numeric answers
@@ -504,6 +533,7 @@ class TsTForest:
         prm = make_params(self._eng.d, self.max_depth, self.min_samples_split, self.min_samples_leaf, self.max_features,
                           keep_forest=True, criterion=self.criterion)
         self._eng.fit_oof(y_dev, fold, 1, self.n_estimators, self.n_classes_, prm, seed=int(self.random_state or 0))
+        self._importances = self._eng.feature_importances()
         return self
 
     def predict_votes(self, X) -> np.ndarray:
@@ -523,8 +553,13 @@ class TsTForest:
 
     @property
     def feature_importances_(self) -> np.ndarray:
-        """Gini importances (mean over trees, normalised), computed on the host from the exported trees --
-        the "interpretable auditing" output of REF/README.md:35 (SK/ensemble/_forest.py feature_importances_)."""
+        """Gini importances (mean over trees of the per-tree normalised decrease in impurity, normalised) -- the
+        "interpretable auditing" output of REF/README.md:35 (SK/ensemble/_forest.py feature_importances_).  Accumulated on
+        the device while the trees grew (integer fixed point: independent of batching and rank count)."""
+        return self._importances
+
+    def feature_importances_from_trees(self) -> np.ndarray:
+        """The same quantity recomputed on the host from the exported trees (cross-check of the device accumulation)."""
         from .features import gini_importances
 
         imp = np.zeros(self.n_features_in_, dtype=np.float64)

@@ -54,12 +54,17 @@ def run_both(eng, bins, y, fold, k, T, C, seed=0, keep=False, group=None, n_grou
     eng.fit_oof(y_dev, fold_dev, k, T, C, prm, seed=seed, group_dev=g_dev, n_groups=n_groups, votes=votes)
     gst = eng.stats()
     oprm = H.make_params(d, **pk)
-    ov, ost, forest = H.fit_oof(bins, y, fold, k, T, C, oprm, seed=seed, keep=keep, group=group, n_groups=n_groups)
+    oimp = np.zeros(d + 1, np.uint64)
+    ov, ost, forest = H.fit_oof(bins, y, fold, k, T, C, oprm, seed=seed, keep=keep, group=group, n_groups=n_groups, importances=oimp)
+    # feature importances accumulated on the device while the trees grew: the integer sums equal the oracle's in every test
+    gimp, gcnt = eng.importance_sums()
+    assert gcnt == int(oimp[d]), f"trees with a split: gpu {gcnt} oracle {int(oimp[d])}"
+    assert np.array_equal(gimp, oimp[:d]), f"importance sums differ: gpu {gimp} oracle {oimp[:d]}"
     return votes.cpu().numpy().view(np.uint32), ov, gst, ost, forest
 
 
 def check_stats(gst, ost):
-    assert gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"] == ost["row_visits"]
+    assert gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"] + gst["row_visits_sub"] == ost["row_visits"]
     for key in ("nodes", "leaves", "searched", "fallback", "inbag_rows", "trees", "oof_steps", "max_depth"):
         assert gst[key] == ost[key], f"stat {key}: gpu {gst[key]} oracle {ost[key]}"
 
@@ -305,9 +310,11 @@ def test_wide_tables_bit_exact(eng, d, C, mf):
 
 
 @pytest.mark.parametrize("n,d,mf", [(6000, 20, "sqrt"), (20000, 64, "sqrt"), (4000, 9, None)])
-def test_two_class_packed_cta_tier_bit_exact(eng, n, d, mf):
+def test_two_class_packed_cta_tier_bit_exact(eng, request, n, d, mf):
     """Binary labels, 256-valued bins, non-root nodes of > 256 rows that weigh < 2^16: k_grow_big's packed 16-bit
     histogram (640 words per feature) is larger than the unpacked 2-class layout (544) -- the region must hold it."""
+    eng.set_option("SUB_ROWS", 0)  # keep the 257 .. 2048-row nodes on k_grow_big
+    request.addfinalizer(lambda: eng.set_option("SUB_ROWS", -1))
     rng = np.random.default_rng(n + d)
     bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
     y = ((bins[0].astype(int) + bins[d - 1].astype(int)) > 255).astype(np.uint8)
@@ -322,6 +329,58 @@ def test_two_class_packed_cta_tier_bit_exact(eng, n, d, mf):
         gn, gc = eng.export_tree(part, t, 2)
         ot = forest.tree(part, t)
         compare_tree(gn, gc, ot.nodes, ot.counts, f"C=2 tree({part},{t})")
+
+
+@pytest.mark.parametrize("sub_rows", [2048, 1024, 0])
+@pytest.mark.parametrize("shape", [(20000, 24, 4, 3, "sqrt"), (5000, 32, 4, 5, "sqrt"), (3100, 9, 3, 2, None), (2500, 64, 2, 2, 20), (900, 5, 4, 3, 1)])
+def test_subtree_tier_bit_exact(eng, request, sub_rows, shape):
+    """k_grow_sub (one CTA finishes a subtree of <= 2048 / 1024 rows from shared memory) against the oracle, and the
+    level-synchronous warp tiers it replaces (SUB_ROWS=0) on the same tables: votes, counters, whole trees."""
+    from tst import synth
+
+    n, d, C, k, mf = shape
+    eng.set_option("SUB_ROWS", sub_rows)
+    request.addfinalizer(lambda: eng.set_option("SUB_ROWS", -1))
+    X, y = synth.vsi_table(n, d, C, seed=n + d)
+    X[:, 0] = np.round(X[:, 0] * 2)  # a low-cardinality column: many ties
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(y, np.ones(n, np.uint8), k, C)
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, 5, C, seed=sub_rows + n, keep=True, max_features=mf)
+    if sub_rows and d <= 64:
+        assert gst["row_visits_sub"] > 0 and gst["row_visits_mid"] == 0 and gst["launches_grow_sub"] > 0
+    else:
+        assert gst["row_visits_sub"] == 0
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    for part, t in ((0, 0), (k - 1, 4)):
+        gn, gc = eng.export_tree(part, t, C)
+        ot = forest.tree(part, t)
+        compare_tree(gn, gc, ot.nodes, ot.counts, f"sub_rows={sub_rows} tree({part},{t})")
+
+
+@pytest.mark.parametrize("pk", [dict(max_depth=6), dict(min_samples_leaf=5, min_samples_split=12), dict(max_features=None)])
+def test_subtree_tier_growth_parameters(eng, request, pk):
+    """Stop rules and the fallback draw inside the CTA-per-subtree kernel: depth limit, leaf / split minima on weighted counts,
+    constant and duplicated columns (features that cannot split)."""
+    eng.set_option("SUB_ROWS", 2048)
+    request.addfinalizer(lambda: eng.set_option("SUB_ROWS", -1))
+    rng = np.random.default_rng(17)
+    n, d, C = 6000, 12, 4
+    bins = rng.integers(0, 200, (d, n)).astype(np.uint8)
+    bins[3] = 7                       # constant column
+    bins[4] = bins[5]                 # duplicated column
+    bins[6] = (bins[6] > 100) * 3     # two-valued column
+    y = ((bins[0].astype(int) // 50) % C).astype(np.uint8)
+    flip = rng.random(n) < 0.3
+    y[flip] = rng.integers(0, C, int(flip.sum()))
+    fold = H.assign_folds(y, np.ones(n, np.uint8), 3, C)
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, 3, 4, C, seed=2, keep=True, **pk)
+    assert gst["row_visits_sub"] > 0
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    gn, gc = eng.export_tree(1, 3, C)
+    ot = forest.tree(1, 3)
+    compare_tree(gn, gc, ot.nodes, ot.counts, f"params {pk}")
 
 
 def test_fewer_rows_than_folds(eng):
@@ -466,6 +525,14 @@ def test_public_api_run_tst_and_forest(vsi_small):
     assert (clf.predict(v["X"]) == v["y"]).mean() > 0.9  # fully grown trees memorise the training set
     imp = clf.feature_importances_
     assert imp.shape == (16,) and abs(imp.sum() - 1.0) < 1e-9 and (imp >= 0).all()
+    assert np.allclose(imp, clf.feature_importances_from_trees(), atol=1e-6)  # device accumulation == host recomputation from the trees
+    oimp = np.zeros(17, np.uint64)
+    H.fit_oof(v["bins"], v["y"], fold, 1, 10, 4, H.make_params(16), seed=3, importances=oimp)
+    assert np.allclose(imp, H.importances_from_sums(oimp), atol=1e-12)
+    # the out-of-fold forests of run_tst carry importances too (no kept forest needed)
+    oimp = np.zeros(17, np.uint64)
+    H.fit_oof(v["bins"], v["y"], v["fold"], 5, 12, 4, H.make_params(16), seed=1, importances=oimp)
+    assert np.allclose(res.feature_importances, H.importances_from_sums(oimp), atol=1e-12)
     sk = clf.sklearn_tree(0)
     assert sk["threshold"].shape == sk["feature"].shape and np.isfinite(sk["threshold"]).all()
     # per-feature attribution of the blind prediction: telescopes to the forest's probability of the true class

@@ -1,16 +1,10 @@
 #!/bin/bash
-# A/B of build variants on one box: tools/variant_bench.sh name[:ENV=VAL,...] ...   (libs in build/variants/libtst_<name>.so; "base" = the in-tree library)
-for spec in "$@"; do
-  name=${spec%%:*}; envs=""
-  if [[ "$spec" == *:* ]]; then envs=$(echo "${spec#*:}" | tr ',' ' '); fi
-  lib=""; [[ "$name" != base ]] && lib="TST_LIB=$PWD/build/variants/libtst_$name.so"
-  out=$(env $lib $envs timeout 200 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-secondary 2>&1 | tail -1)
-  python - "$spec" <<PY "$out"
-import json,sys
-try:
-    d=json.loads(sys.argv[2]); t=d["roofline"]["tiers"]; w=d["roofline"]["whole_tree"]
-    print(sys.argv[1], "value %.1f ms %.1f |"%(d["value"], d["ms_per_step"]), {k[7:]:round(v["ms"]/d["steps"],1) for k,v in t.items()}, "tiny %.1f prep %.1f infer %.1f rest %.1f"%(w.get("ms_tiny",0)/d["steps"], w["ms_prep"]/d["steps"], w["ms_infer"]/d["steps"], d["ms_per_step"]-(sum(v["ms"] for v in t.values())+w.get("ms_tiny",0)+w["ms_prep"]+w["ms_infer"])/d["steps"]), flush=True)
-except Exception as e:
-    print(sys.argv[1], "FAILED", sys.argv[2][-300:])
-PY
+# A/B of build variants (TST_LIB) and knobs on the headline step; prints value + per-tier ms/step.  Usage: tools/variant_bench.sh "VAR=.. VAR=.." ...
+for v in "$@"; do
+  env $v python bench.py --steps 3 --warmup 3 --no-cpu --no-secondary --no-job --no-e2e 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+t = d['roofline']['tiers']; w = d['roofline']['whole_tree']; s = d['steps']
+print('$v', '| trees/s %.0f ms/step %.1f |' % (d['value'], d['ms_per_step']), ' '.join('%s %.1f' % (k.replace('k_grow_', ''), x['ms'] / s) for k, x in t.items()), 'tiny %.1f prep %.1f infer %.1f' % (w['ms_tiny'] / s, w['ms_prep'] / s, w['ms_infer'] / s))
+"
 done
