@@ -447,8 +447,8 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
             if (primary) {
                 for (int j = 0; j < nb; ++j) {
                     if (s_fbin[j] == 0xFFFFFFFFu) continue;
-                    uint32_t key = (s_feat[j] << 8) | s_fbin[j];  // ties: lowest feature, then lowest bin
-                    if (s_fgain[j] > s_bgain || (s_fgain[j] == s_bgain && key < s_bkey)) {
+                    uint32_t key = (s_feat[j] << 8) | s_fbin[j];  // ties: the feature drawn first (positions are visited in order), then lowest bin
+                    if (s_fgain[j] > s_bgain) {
                         s_bgain = s_fgain[j]; s_bkey = key; s_newj = j; s_found = 1;
                         s_sj = (pos == 0 && g.stash != nullptr && use_tile && nb <= 8 && t.end - t.begin <= g.stash_max_rows) ? (uint32_t)j : 0xFFFFFFFFu;
                     }
@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_small(GrowCtx g, const Task
                     if (gb != 0xFFFFFFFFu) {
                         uint32_t key = (f << 8) | gb;
                         if (i < m) {
-                            if (gn > best_gain || (gn == best_gain && key < best_key)) { best_gain = gn; best_key = key; found = true; }
+                            if (gn > best_gain) { best_gain = gn; best_key = key; found = true; }  // ties: the feature drawn first
                         } else {
                             best_gain = gn; best_key = key; found = true;
                         }

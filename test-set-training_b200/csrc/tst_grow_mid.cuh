@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
         if (bb != 0xFFFFFFFFu) {
             uint32_t key = (f << 8) | bb;
             if (i < m) {
-                if (bg > best_gain || (bg == best_gain && key < best_key)) newbest = true;
+                if (bg > best_gain) newbest = true;  // ties: the feature drawn first
             } else {
                 newbest = true;
             }
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         if (wb != 0xFFFFFFFFu) {
             const uint32_t key = (f << 8) | wb;
             bool newbest;
-            if (i < m) newbest = wg > best_gain || (wg == best_gain && key < best_key);
+            if (i < m) newbest = wg > best_gain;  // ties: the feature drawn first
             else newbest = true;
             if (newbest) {
                 const uint32_t winner = __ffs(__ballot_sync(0xffffffffu, bb == wb && bg == wg)) - 1;

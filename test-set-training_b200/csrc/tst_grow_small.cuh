@@ -167,11 +167,11 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                         thr *= TST_EST_MARGIN;
                         if (ok && ge >= thr) {
                             gn = gini_gain(SL, NL, SR, NR);
-                            key = (f << 8) | b;
+                            key = (pos << 8) | b;  // ties among the positions evaluated side by side: the feature drawn first, then lowest bin
                         }
                         warp_argmax_redux(gn, key);
-                        if (key != 0xFFFFFFFFu && (gn > best_gain || (gn == best_gain && key < best_key))) {
-                            best_gain = gn; best_key = key; found = true;
+                        if (key != 0xFFFFFFFFu && gn > best_gain) {  // ... and an earlier pass keeps a tie
+                            best_gain = gn; best_key = ((uint32_t)s_perm[key >> 8] << 8) | (key & 0xFFu); found = true;
                         }
                     } else {
                         // fallback: the first position in draw order that has any valid split

@@ -236,7 +236,7 @@ __device__ __forceinline__ bool sub_narrow_node(const GrowCtx& g, uint32_t lane,
         if (wb != 0xFFFFFFFFu) {
             const uint32_t key = (f << 8) | wb;
             bool newbest;
-            if (i < m) newbest = wg > best_gain || (wg == best_gain && key < best_key);
+            if (i < m) newbest = wg > best_gain;  // ties: the feature drawn first
             else newbest = true;
             if (newbest) {
                 const uint32_t winner = __ffs(__ballot_sync(0xffffffffu, bb == wb && bg == wg)) - 1;
@@ -395,11 +395,11 @@ __device__ __forceinline__ void sub_small_subtree(const GrowCtx& g, uint32_t lan
                     thr *= TST_EST_MARGIN;
                     if (ok && ge >= thr) {
                         gn = gini_gain(SL, NL, SR, NR);
-                        key = (f << 8) | b;
+                        key = (pos << 8) | b;  // ties among the positions evaluated side by side: the feature drawn first, then lowest bin
                     }
                     warp_argmax_redux(gn, key);
-                    if (key != 0xFFFFFFFFu && (gn > best_gain || (gn == best_gain && key < best_key))) {
-                        best_gain = gn; best_key = key; found = true;
+                    if (key != 0xFFFFFFFFu && gn > best_gain) {
+                        best_gain = gn; best_key = ((uint32_t)s_perm[key >> 8] << 8) | (key & 0xFFu); found = true;
                     }
                 } else {
                     if (ok) {
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_grow_sub(GrowCtx g, const 
                 for (int j = 0; j < NF; ++j) {
                     if (s_fbin[j] == 0xFFFFFFFFu) continue;
                     const uint32_t key = ((uint32_t)perm0[pos + j] << 8) | s_fbin[j];
-                    if (!primary || s_fgain[j] > s_bgain || (s_fgain[j] == s_bgain && key < s_bkey)) {
+                    if (!primary || s_fgain[j] > s_bgain) {  // ties: the feature drawn first
                         s_bgain = s_fgain[j]; s_bkey = key; s_bP0 = s_fP0[j]; s_bP1 = s_fP1[j]; s_found = 1;
                         if (!primary) break;
                     }

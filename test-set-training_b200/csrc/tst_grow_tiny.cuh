@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
                     }
                     if (fkey != 0xFFFFFFFFu) {
                         if (i < m) {
-                            if (fg > best_gain || (fg == best_gain && fkey < best_key)) { best_gain = fg; best_key = fkey; found = true; }
+                            if (fg > best_gain) { best_gain = fg; best_key = fkey; found = true; }  // ties: the feature drawn first
                         } else {
                             best_gain = fg; best_key = fkey; found = true;  // fallback: first feature in draw order that separates
                         }

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_root_split(GrowCtx g, const uint32_t* _
             for (int j = 0; j < m; ++j) {
                 if (s_fbin[j] == 0xFFFFFFFFu) continue;
                 const uint32_t k2 = (s_feat[j] << 8) | s_fbin[j];
-                if (s_fgain[j] > best || (s_fgain[j] == best && k2 < key)) { best = s_fgain[j]; key = k2; bj = j; state = 1; }
+                if (s_fgain[j] > best) { best = s_fgain[j]; key = k2; bj = j; state = 1; }  // ties: the feature drawn first
             }
         rs->state = state; rs->key = key; rs->N = s_N;
         for (int c = 0; c < C; ++c) rs->tot[c] = s_tot[c];

@@ -4,3 +4,4 @@ from .api import (Engine, IBPResult, TsTForest, TsTRegressionResult, TsTResult, 
                   make_params, quantise_target, resolve_max_features, run_tst, run_tst_regression, shard_trees,
                   votes_to_value)
 from .features import extract_features, gini_importances, path_contributions, to_sklearn_arrays  # noqa: F401,E402
+from .interop import ExportedForest, load_forest  # noqa: F401,E402

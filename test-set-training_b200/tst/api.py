@@ -595,3 +595,18 @@ class TsTForest:
 
         nodes, counts = self.export_tree(t)
         return to_sklearn_arrays(nodes, counts, self._eng.edges, self._eng.n_edges)
+
+    def export(self):
+        """The whole kept forest on the host (interop.ExportedForest): .save(path), .to_sklearn() -> a genuine
+        sklearn RandomForestClassifier, .predict_votes(X)."""
+        from .interop import ExportedForest
+
+        trees = [self.export_tree(t) for t in range(self.n_estimators)]
+        return ExportedForest([n for n, _ in trees], [c for _, c in trees], self._eng.edges.copy(), self._eng.n_edges.copy(),
+                              np.asarray(self.classes_), int(self.n_features_in_), self.criterion)
+
+    def save(self, path: str) -> None:
+        self.export().save(path)
+
+    def to_sklearn(self):
+        return self.export().to_sklearn()

@@ -76,7 +76,41 @@ def spec_regression_vectors():
                         stats=np.array([st[k] for k in ("row_visits", "nodes", "leaves", "searched", "fallback", "inbag_rows", "max_depth")]))
 
 
+def sklearn_seed_averaged(n_seeds=8, n_seeds_binned=4, T=500):
+    """The statistical oracle, seed-averaged (python tests/golden/make_golden.py sklearn_rf; ~6 min on 8 cores).
+    sklearn's RandomForestClassifier on the VSI-shaped table with the oracle's fold assignment: per-seed per-fold accuracy
+    and s(x) at T trees per fold -- on the raw floats, and on the uint8-binned table (same candidate splits as the
+    histogram RF: differs only in RNG and tie-breaks; SURVEY 8(c) third tier) where the impurity-based feature
+    importances are recorded as well.  Seed-averaging is what makes the +-1 point per-fold tolerance testable: two
+    sklearn seeds alone differ by 0.8 .. 1.3 points per fold at 500 .. 2000 trees."""
+    import sklearn
+    from sklearn.ensemble import RandomForestClassifier
+
+    from oracle import hist_rf as H
+    from oracle import sklearn_tst as S
+    from tst import synth
+
+    X, y = synth.vsi_table()
+    edges, ne = H.find_edges(X)
+    bins = H.bin_table(X, edges, ne)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 5, 4)
+    raw = [S.run_tst(X, y, 5, T, seed=sd, fold=fold) for sd in range(n_seeds)]
+    Xb = bins.T.astype(np.float32)
+    binned = [S.run_tst(Xb, y, 5, T, seed=100 + sd, fold=fold) for sd in range(n_seeds_binned)]
+    imp = np.zeros(X.shape[1])
+    for f in range(5):  # importances of the same 5 training sets on the binned table
+        rf = RandomForestClassifier(n_estimators=T, random_state=7 + f, n_jobs=-1).fit(Xb[fold != f], y[fold != f])
+        imp += rf.feature_importances_ / 5
+    np.savez_compressed(os.path.join(HERE, "sklearn_rf_vsi.npz"), sklearn_version=np.array(sklearn.__version__), n_trees=T, fold=fold,
+                        acc_raw=np.stack([r["fold_accuracy"] for r in raw]), s_raw=np.stack([r["s"] for r in raw]).astype(np.float32),
+                        acc_binned=np.stack([r["fold_accuracy"] for r in binned]), s_binned=np.stack([r["s"] for r in binned]).astype(np.float32),
+                        importances_binned=imp)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sklearn_rf":
+        sklearn_seed_averaged()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "regression":
         spec_regression_vectors()
         sys.exit(0)
