@@ -57,13 +57,17 @@ typedef struct {
     int32_t max_features;       /* m in [1, d]; host resolves "sqrt" -> max(1, floor(sqrt(d))) */
     int32_t trees_in_flight;    /* <= 0: sized from free HBM */
     int32_t keep_forest;        /* != 0: node arrays stay resident for tst_export_tree / tst_predict */
-    int32_t criterion;          /* TST_GINI (0) or TST_SQUARED_ERROR (1): the labels 0..C-1 are then the ordinal levels of a
+    int32_t criterion;          /* TST_GINI (0); TST_SQUARED_ERROR_LEVELS (1): the labels 0..C-1 are the ordinal levels of a
                                    uniformly quantised numeric target and splits maximise S_L^2/N_L + S_R^2/N_R with
-                                   S = sum_c c * count_c (SK/tree/_criterion.pyx:707-1000, MSE.proxy_impurity_improvement) */
+                                   S = sum_c c * count_c; TST_SQUARED_ERROR (2): the same proxy (SK/tree/_criterion.pyx:1074-1096,
+                                   MSE.proxy_impurity_improvement) on a CONTINUOUS target in 16-bit fixed point (tst_set_target):
+                                   per-bin (weight, sum y) histograms with exact integer sums, leaves hold (N, sum y), n_classes
+                                   must be 2 and votes_dev [n, 2] collects the low / high 16-bit halves of the Q16.16 leaf means
+                                   (prediction = (votes[1] * 65536 + votes[0]) / (n_trees * 65536)); y_dev then only stratifies folds */
     int32_t reserved;
 } tst_params;
 
-enum { TST_GINI = 0, TST_SQUARED_ERROR = 1 };
+enum { TST_GINI = 0, TST_SQUARED_ERROR_LEVELS = 1, TST_SQUARED_ERROR = 2 };
 
 typedef struct {
     uint64_t row_visits_big;    /* distinct in-bag rows summed over nodes searched by the per-node CTA kernel */
@@ -130,6 +134,11 @@ int tst_bin_auto(tst_handle* h, const float* X_dev, int64_t n, int32_t d, int32_
 int tst_set_bins(tst_handle* h, const uint8_t* bins_cm_dev, int64_t n, int32_t d, void* stream);
 /* Copy the column-major table out: out_dev [d][n]. */
 int tst_get_bins(tst_handle* h, uint8_t* out_dev, void* stream);
+
+/* Numeric answers: the continuous target of criterion TST_SQUARED_ERROR, yq_dev [n] uint16 =
+ * round((y - min) / (max - min) * 65535), copied into the handle; valid until the table is re-binned.  Replaces the float64 y
+ * of RandomForestRegressor.fit (SK/ensemble/_forest.py:303-522, SK/tree/_criterion.pyx:707-1000). */
+int tst_set_target(tst_handle* h, const uint16_t* yq_dev, int64_t n, void* stream);
 
 /* (A3) Stratified k-fold assignment on the device -- "k-fold cross-validation" (REF/README.md:35);
  * replaces SK/model_selection/_split.py:774-840.  group_dev may be NULL (one group). */

@@ -45,7 +45,9 @@ typedef struct {
     int32_t min_samples_leaf;  /* >= 1 */
     int32_t max_features;      /* m in [1, d]; "sqrt" resolved by the caller (SK/tree/_classes.py:330-345) */
     int32_t criterion;         /* 0 = Gini (classification); 1 = squared error on ordinal levels: the labels 0..C-1 are
-                                  the levels of a uniformly quantised numeric target (SK/tree/_criterion.pyx:707-1000) */
+                                  the levels of a uniformly quantised numeric target (SK/tree/_criterion.pyx:707-1000);
+                                  2 = squared error on a continuous target in 16-bit fixed point (orc_set_target): per-bin
+                                  (count, sum y) histograms, leaves hold (N, sum y), votes are Q16.16 leaf means */
 } orc_params;
 
 typedef struct {
@@ -211,6 +213,11 @@ static int build_parts(const uint8_t* fold, const int32_t* group, int32_t n_grou
     free(cur);
     return 0;
 }
+
+/* Continuous target of criterion 2: yq[i] in [0, 65535] (host: round((y - lo) / (hi - lo) * 65535)).  Set before orc_fit_oof;
+ * the uint8 labels passed to orc_fit_oof are then only the stratification levels of the fold assignment. */
+static const uint16_t* g_target16 = NULL;
+void orc_set_target(const uint16_t* yq) { g_target16 = yq; }
 
 /* ---------------------------------------------------------------- one tree */
 typedef struct { uint32_t row; uint32_t w; } entry_t;
@@ -386,6 +393,102 @@ static int grow_tree(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t
     return 0;
 }
 
+/* Criterion 2: the same growth loop on (count, sum y) histograms.  A node is a leaf when all its targets are
+ * equal (sklearn: impurity <= EPSILON, SK/tree/_tree.pyx:236), N < min_samples_split, N < 2 * min_samples_leaf, depth limit,
+ * or no valid split.  gain = S_L^2 / N_L + S_R^2 / N_R (MSE.proxy_impurity_improvement, SK/tree/_criterion.pyx:1074-1096) with
+ * S = sum of w * yq exact in uint64.  counts[node] = (S low 32 bits, S high 32 bits); n_weighted = N. */
+static int grow_tree_reg(const uint8_t* bins_cm, int64_t n, int32_t d, const uint16_t* yq, const orc_params* prm, uint32_t k0,
+                         uint32_t k1, uint32_t gid, entry_t* ent, entry_t* tmp, uint32_t n_inbag, node_store* S, orc_stats* st,
+                         uint64_t* imp) {
+    int32_t m = prm->max_features;
+    uint32_t msl = (uint32_t)prm->min_samples_leaf, mss = (uint32_t)prm->min_samples_split;
+    uint64_t* hcnt = (uint64_t*)calloc(ORC_NBINS, 8);
+    uint64_t* hsum = (uint64_t*)calloc(ORC_NBINS, 8);
+    int32_t* perm = (int32_t*)malloc((size_t)d * 4);
+    size_t scap = 64, sp = 0;
+    stack_item* stk = (stack_item*)malloc(scap * sizeof(stack_item));
+    stk[sp++] = (stack_item){0, n_inbag, 0, -1, 0};
+    while (sp) {
+        stack_item it = stk[--sp];
+        int64_t id = store_push(S, 2);
+        orc_node* nd = &S->nodes[id];
+        if (it.parent >= 0) {
+            if (it.is_right) S->nodes[it.parent].right = (int32_t)id; else S->nodes[it.parent].left = (int32_t)id;
+        }
+        uint64_t N = 0, Sy = 0;
+        uint32_t ymin = 0xFFFFFFFFu, ymax = 0;
+        for (uint32_t i = it.begin; i < it.end; ++i) {
+            uint32_t v = yq[ent[i].row];
+            N += ent[i].w; Sy += (uint64_t)ent[i].w * v;
+            if (v < ymin) ymin = v;
+            if (v > ymax) ymax = v;
+        }
+        S->counts[(size_t)id * 2] = (uint32_t)Sy; S->counts[(size_t)id * 2 + 1] = (uint32_t)(Sy >> 32);
+        nd->left = nd->right = -1; nd->feature = -1; nd->bin = -1;
+        nd->begin = it.begin; nd->end = it.end; nd->depth = it.depth; nd->n_weighted = (uint32_t)N;
+        st->nodes++;
+        if (it.depth > st->max_depth) st->max_depth = it.depth;
+        int pure = ymin == ymax;
+        int leaf = (prm->max_depth > 0 && it.depth >= (uint32_t)prm->max_depth) || N < mss || N < 2ull * msl || pure;
+        int found = 0; int32_t bf = 0, bb = 0; double bg = 0.0;
+        if (!leaf) {
+            st->searched++;
+            st->row_visits += it.end - it.begin;
+            for (int32_t f = 0; f < d; ++f) perm[f] = f;
+            uint32_t rnd[4] = {0, 0, 0, 0};
+            for (int32_t i = 0; i < d; ++i) {
+                if (i >= m && found) break;
+                if ((i & 3) == 0)
+                    philox4x32_10(it.begin, it.depth, gid, ORC_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), k0, k1, rnd);
+                int32_t j = i + (int32_t)mulhi32(rnd[i & 3], (uint32_t)(d - i));
+                int32_t f = perm[j]; perm[j] = perm[i]; perm[i] = f;
+                if (i == m) st->fallback++;
+                const uint8_t* col = bins_cm + (size_t)f * n;
+                int32_t lo = 255, hi = 0;
+                for (uint32_t r = it.begin; r < it.end; ++r) {
+                    uint8_t b = col[ent[r].row];
+                    hcnt[b] += ent[r].w; hsum[b] += (uint64_t)ent[r].w * yq[ent[r].row];
+                    if (b < lo) lo = b;
+                    if (b > hi) hi = b;
+                }
+                uint64_t NL = 0, SL = 0;
+                int f_found = 0; int32_t f_bin = 0; double f_gain = 0.0;
+                for (int32_t b = lo; b < hi; ++b) {
+                    if (!hcnt[b]) continue;
+                    NL += hcnt[b]; SL += hsum[b];
+                    uint64_t NR = N - NL;
+                    if (NL < msl || NR < msl) continue;
+                    double g = gain_mse(SL, NL, Sy - SL, NR);
+                    if (!f_found || g > f_gain) { f_found = 1; f_gain = g; f_bin = b; }
+                }
+                for (int32_t b = lo; b <= hi; ++b) { hcnt[b] = 0; hsum[b] = 0; }
+                if (f_found) {
+                    if (i < m) { if (!found || f_gain > bg) { found = 1; bg = f_gain; bf = f; bb = f_bin; } }
+                    else { found = 1; bg = f_gain; bf = f; bb = f_bin; }
+                }
+            }
+        }
+        if (leaf || !found) { st->leaves++; continue; }
+        if (imp) {
+            volatile double sp2 = (double)Sy; volatile double sq = sp2 * sp2;
+            imp[bf] += imp_q24(bg, sq / (double)N);
+        }
+        const uint8_t* col = bins_cm + (size_t)bf * n;
+        uint32_t nl = 0, nr = 0;
+        for (uint32_t r = it.begin; r < it.end; ++r) {
+            if (col[ent[r].row] <= bb) ent[it.begin + nl++] = ent[r]; else tmp[nr++] = ent[r];
+        }
+        memcpy(ent + it.begin + nl, tmp, (size_t)nr * sizeof(entry_t));
+        nd = &S->nodes[id];
+        nd->feature = bf; nd->bin = bb;
+        if (sp + 2 > scap) { scap *= 2; stk = (stack_item*)realloc(stk, scap * sizeof(stack_item)); }
+        stk[sp++] = (stack_item){it.begin + nl, it.end, it.depth + 1, (int32_t)id, 1};
+        stk[sp++] = (stack_item){it.begin, it.begin + nl, it.depth + 1, (int32_t)id, 0};
+    }
+    free(hcnt); free(hsum); free(perm); free(stk);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- fit + OOF votes
  * Trees are identified by (part = group*k + fold, t).  RNG id gid = gid_base +
  * part*n_trees + t.  This rank builds trees with (part*n_trees + t) % world == rank,
@@ -400,7 +503,7 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
     if (n < 0 || n >= 0x7FFFFFF0LL || d < 1 || C < 1 || C > 256 || k < 1 || k > 250 || n_trees < 1 ||
         n_trees > 65535 || t0 < 0 || t1 > n_trees || t0 > t1 || world < 1 || rank < 0 || rank >= world ||
         prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2 ||
-        prm->criterion < 0 || prm->criterion > 1)
+        prm->criterion < 0 || prm->criterion > 2 || (prm->criterion == 2 && (!g_target16 || C != 2)))
         return -1;
     orc_parts P;
     int rc = build_parts(fold, group, n_groups, n, k, &P);
@@ -464,7 +567,8 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
             }
             node_store S; memset(&S, 0, sizeof(S));
             if (imp) memset(imp, 0, (size_t)d * 8);
-            grow_tree(bins_cm, n, d, y, C, prm, k0, k1, gid, ent, tmp, ni, &S, &st, imp);
+            if (prm->criterion == 2) grow_tree_reg(bins_cm, n, d, g_target16, prm, k0, k1, gid, ent, tmp, ni, &S, &st, imp);
+            else grow_tree(bins_cm, n, d, y, C, prm, k0, k1, gid, ent, tmp, ni, &S, &st, imp);
             st.trees++; st.inbag_rows += ni;
             if (imp) {  /* per-tree normalisation in integers: the forest-level figure is a sum of these, in any order */
                 unsigned __int128 tsum = 0;
@@ -486,6 +590,15 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
                     }
                     uint64_t N = S.nodes[nd].n_weighted;
                     if (!N) continue;
+                    if (prm->criterion == 2) {  /* Q16.16 leaf mean, added as two 16-bit halves: no carries between the words */
+                        uint64_t Sy = (uint64_t)S.counts[(size_t)nd * 2] | ((uint64_t)S.counts[(size_t)nd * 2 + 1] << 32);
+                        uint32_t v = (uint32_t)((Sy << 16) / N);
+#pragma omp atomic
+                        votes[(size_t)row * 2] += v & 0xFFFFu;
+#pragma omp atomic
+                        votes[(size_t)row * 2 + 1] += v >> 16;
+                        continue;
+                    }
                     for (int32_t c = 0; c < C; ++c) {
                         uint32_t v = (uint32_t)(((uint64_t)S.counts[(size_t)nd * C + c] << 16) / N);
                         if (v) {

@@ -153,7 +153,7 @@ def resolve_max_features(max_features, d: int) -> int:
     return int(max_features)
 
 
-CRITERIA = {"gini": 0, "squared_error": 1}
+CRITERIA = {"gini": 0, "squared_error_levels": 1, "squared_error": 2}
 
 
 def make_params(d, max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt", criterion="gini"):
@@ -229,6 +229,16 @@ def importances_from_sums(sums) -> np.ndarray:
     s = np.asarray(sums[:-1], dtype=np.float64)
     tot = s.sum()
     return s / tot if tot > 0 else s
+
+
+def set_target(yq):
+    """Continuous target of criterion 'squared_error' (uint16 fixed point); keep the array alive while fitting."""
+    global _TARGET
+    _TARGET = None if yq is None else np.ascontiguousarray(yq, dtype=np.uint16)
+    lib().orc_set_target(_p(_TARGET))
+
+
+_TARGET = None
 
 
 def finalize(votes, y, fold, k, n_trees, group=None, n_groups=1):

@@ -104,7 +104,9 @@ struct tst_handle {
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
-    int32_t kept_C = 0, kept_n_trees = 0;
+    int32_t kept_C = 0, kept_n_trees = 0, kept_criterion = 0;
+    DevBuf target16;          // criterion 2: the 16-bit fixed-point target (tst_set_target)
+    int64_t target_n = 0;
     int64_t imp_trees = 0;  // trees of the last fit whose importances sit in `imp` ([imp_trees][d] uint64, Q24)
     int32_t imp_d = 0;
     uint64_t kept_node_stride = 0, kept_leafc_stride = 0;
@@ -239,7 +241,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qsub, &h->imp, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qsub, &h->imp, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk, &h->gather};
     for (DevBuf* b : bufs) b->release();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -258,9 +260,12 @@ extern "C" int tst_destroy(tst_handle* h) {
 static int set_kernel_attrs(tst_handle* h) {
     if (h->attrs_set) return 0;
     CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
-    CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, MID_R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<4, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<2, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -280,6 +285,7 @@ static int alloc_table(tst_handle* h, int64_t n, int32_t d) {
     if (n < 1 || n >= TST_MAX_ROWS) return fail(TST_ERR_INVALID, "table: need 1 <= n < 2^31 - 16 rows");
     if (d < 1 || d > TST_MAX_FEATURES) return fail(TST_ERR_INVALID, "table: need 1 <= d <= 1024 features");
     h->n = n; h->d = d;
+    h->target_n = 0;  // a target belongs to one table
     h->ld = (n + 15) / 16 * 16;
     // rows of <= 128 bytes are padded to a power of two so the cooperative row fetch can shift instead of divide
     h->dstride = (uint32_t)((d + 15) / 16 * 16);
@@ -380,6 +386,16 @@ extern "C" int tst_get_bins(tst_handle* h, uint8_t* out_dev, void* stream) {
     return TST_OK;
 }
 
+extern "C" int tst_set_target(tst_handle* h, const uint16_t* yq_dev, int64_t n, void* stream) {
+    if (!h || !yq_dev) return fail(TST_ERR_INVALID, "tst_set_target: null argument");
+    if (!h->n || n != h->n) return fail(TST_ERR_STATE, "tst_set_target: bin the table first; the target must have one value per row");
+    CK(cudaSetDevice(h->device));
+    ENSURE(h->target16, (size_t)n * 2);
+    CK(cudaMemcpyAsync(h->target16.p, yq_dev, (size_t)n * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    h->target_n = n;
+    return TST_OK;
+}
+
 // --------------------------------------------------------------------------------------------- folds
 extern "C" int tst_assign_folds(tst_handle* h, const uint8_t* y_dev, const uint8_t* active_dev, const int32_t* group_dev,
                                 int32_t n_groups, int32_t k, int32_t C, uint8_t* fold_dev, void* stream) {
@@ -463,7 +479,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         return fail(TST_ERR_INVALID, "tst_fit_oof: bad k / n_trees / classes / tree range");
     if (prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2)
         return fail(TST_ERR_INVALID, "tst_fit_oof: bad growth parameters");
-    if (prm->criterion != TST_GINI && prm->criterion != TST_SQUARED_ERROR) return fail(TST_ERR_INVALID, "tst_fit_oof: unknown criterion");
+    if (prm->criterion != TST_GINI && prm->criterion != TST_SQUARED_ERROR_LEVELS && prm->criterion != TST_SQUARED_ERROR)
+        return fail(TST_ERR_INVALID, "tst_fit_oof: unknown criterion");
+    const bool reg = prm->criterion == TST_SQUARED_ERROR;
+    if (reg && C != 2) return fail(TST_ERR_INVALID, "tst_fit_oof: the squared-error criterion takes n_classes = 2 (votes are the two 16-bit halves of the Q16.16 leaf means)");
+    if (reg && h->target_n != n) return fail(TST_ERR_STATE, "tst_fit_oof: the squared-error criterion needs the 16-bit target of this table (tst_set_target)");
+    if (reg && n >= (1ll << 24) / 255) return fail(TST_ERR_UNSUPPORTED, "tst_fit_oof: squared-error criterion: a node must weigh < 2^24");
     if ((uint64_t)n_groups * k * n_trees + gid_base > 0xFFFFFFFFull) return fail(TST_ERR_INVALID, "tst_fit_oof: tree id overflows 32 bits");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -533,7 +554,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint64_t leafc_stride = (n_cap / 2 + 1) * (uint64_t)C;
     // queue slots per tree.  With the thread-per-subtree tier on, qsmall only sees subtrees of >= 7 rows (<= n/7 of them); with it
     // off (many classes, squared error, d > 64) every 2..32-row subtree lands there: up to n/2 tasks for a tree that peels rows off.
-    const uint64_t tiny_eff = (C <= 4 && prm->criterion == TST_GINI && d <= TINY_FY_MAX) ? (uint64_t)(kn.tiny_max >= 0 ? std::min(kn.tiny_max, TINY_MAX) : TINY_MAX) : 0;
+    const uint64_t tiny_eff = (((C <= 4 && prm->criterion == TST_GINI) || reg) && d <= TINY_FY_MAX) ? (uint64_t)(kn.tiny_max >= 0 ? std::min(kn.tiny_max, TINY_MAX) : TINY_MAX) : 0;
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / std::max<uint64_t>(2, tiny_eff + 1) + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
     const bool want_stash = kn.stash;  // see use_stash below
@@ -576,7 +597,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         ENSURE(h->keep_nodes, total_trees * node_stride * sizeof(uint2));
         ENSURE(h->keep_leafc, total_trees * leafc_stride * 4);
         nodes_p = h->keep_nodes.as<uint2>(); leafc_p = h->keep_leafc.as<uint32_t>();
-        h->kept_C = C; h->kept_n_trees = n_trees; h->kept_node_stride = node_stride; h->kept_leafc_stride = leafc_stride;
+        h->kept_C = C; h->kept_criterion = prm->criterion; h->kept_n_trees = n_trees; h->kept_node_stride = node_stride; h->kept_leafc_stride = leafc_stride;
     } else {
         ENSURE(h->nodes, B * node_stride * sizeof(uint2));
         ENSURE(h->leafc, B * leafc_stride * 4);
@@ -598,7 +619,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.qsmall = h->qsmall.as<Task>();
     g.stats = h->dstats.as<DevStats>();
     g.FS = 32 * (8 * C + 1);
-    g.MB = (int)std::min<size_t>(std::min<size_t>(32, (size_t)g.m), std::max<size_t>(1, BIG_SMEM_BUDGET / ((size_t)g.FS * 4)));
+    g.MB = (int)std::min<size_t>(std::min<size_t>(32, (size_t)g.m), std::max<size_t>(1, BIG_SMEM_BUDGET / ((size_t)(reg ? BIGP_FS : g.FS) * 4)));
     g.big_tile = h->dstride <= 64 ? 1 : 0;  // cooperative whole-row fetch into a shared tile (rows of <= 64 bytes)
     const size_t big_tile_bytes = g.big_tile ? (size_t)BIG_THREADS * ((h->dstride >> 2) + 1) * 4 : 0;
     g.big_packed = kn.big_packed ? 1u : 0u;
@@ -614,9 +635,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         g.stash_max_rows = 0xFFFFFFFFu;
         if (kn.stash_max >= 0) g.stash_max_rows = (uint32_t)kn.stash_max;
     }
-    const bool packed_ok = C <= 4 && prm->criterion == TST_GINI;  // the packed 4-class kernels implement the Gini criterion only
+    // the packed kernels: <= 4 classes with the Gini criterion, or the continuous squared-error criterion (64-bit (weight, sum) cells)
+    const bool packed_ok = (C <= 4 && prm->criterion == TST_GINI) || reg;
     // the packed 16-bit layout needs BIGP_FS = 640 words per feature, more than FS when C == 2 (544): size for the larger one
-    g.HFS_max = (packed_ok && g.big_packed && g.big_tile && g.MB <= 8) ? std::max<int>(g.FS, (int)BIGP_FS) : g.FS;
+    g.HFS_max = (reg || (packed_ok && g.big_packed && g.big_tile && g.MB <= 8)) ? std::max<int>(g.FS, (int)BIGP_FS) : g.FS;
     const size_t big_smem = (size_t)g.MB * g.HFS_max * 4 + big_tile_bytes;
     if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
     const bool small_packed = packed_ok;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
@@ -644,7 +666,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     // Measured on B200 (profiles/r02_k_grow_sub.md): bit-exact but 3x slower than the level-synchronous tiers -- the row cache leaves
     // 16 warps per SM for code that is a chain of dependent steps -- so it is OFF by default (SUB_ROWS=2048 / 1024 turns it on).
     int sub_rows = 0;
-    if (kn.sub_rows > 0 && packed_ok && h->dstride <= 64 && B <= 65535) sub_rows = kn.sub_rows >= 2048 ? 2048 : (kn.sub_rows >= 1024 ? 1024 : 0);
+    if (kn.sub_rows > 0 && packed_ok && !reg && h->dstride <= 64 && B <= 65535) sub_rows = kn.sub_rows >= 2048 ? 2048 : (kn.sub_rows >= 1024 ? 1024 : 0);
     g.sub_max = (uint32_t)sub_rows;
     g.qsub = h->qsub.as<Task>(); g.qsub_count = counters + 20;
     if (sub_rows) g.mid_max = SMALL_MAX;
@@ -655,6 +677,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     bool root_dense = n >= 65536 && g.m <= 8 && root_smem <= 200 * 1024 && max_train > g.big_min;
     if (kn.root_dense == 0) root_dense = false;  // 0 = off, 2 = on for any table size (tests)
     if (kn.root_dense == 2) root_dense = g.m <= 8 && root_smem <= 200 * 1024 && max_train > g.big_min;
+    if (reg) root_dense = false;  // the dense root kernels histogram class counts
     if (root_dense) {
         ENSURE(h->ghist, B * (size_t)g.m * g.FS * 4);
         ENSURE(h->rsplit, B * sizeof(RootSplit));
@@ -692,7 +715,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             CKL();
             k_boot_scan<<<nb, 256, 0, st>>>(g.trees, n_chunks, h->chunk_cnt.as<uint32_t>(), h->chunk_sum.as<uint32_t>(), g.stats);
             CKL();
-            k_boot_scatter<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), y_dev, g.entA, n_cap);
+            k_boot_scatter<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), y_dev, reg ? h->target16.as<uint16_t>() : nullptr, g.entA, n_cap);
             CKL();
             g.rsplit = nullptr;
             if (root_dense) {
@@ -748,14 +771,16 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 const uint32_t* cm = j ? counters + 2 * cur + 1 : nullptr;
                 CK(cudaEventRecord(h->ev_lvl[j][0], st));
                 if (gb) {
-                    if (g.criterion == 1u) k_grow_big<BIG_THREADS, true><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
+                    if (g.criterion == 1u) k_grow_big<BIG_THREADS, 1><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
+                    else if (reg) k_grow_big<BIG_THREADS, 2><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
                     else k_grow_big<BIG_THREADS><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
                     CKL();
                     h->stats.kernel_launches++; h->stats.launches_grow_big++;
                 }
                 CK(cudaEventRecord(h->ev_lvl[j][1], st));
                 if (gm) {
-                    if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
+                    if (reg) k_grow_mid4<MID_WARPS, MID_R, true><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
+                    else if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
                     else if (mid_warps == 8) k_grow_mid<8, MID_R><<<(gm + 7) / 8, 256, mid_smem, st>>>(g, qmcur, gm, cm);
                     else if (mid_warps == 4) k_grow_mid<4, MID_R><<<(gm + 3) / 4, 128, mid_smem, st>>>(g, qmcur, gm, cm);
                     else k_grow_mid<2, MID_R><<<(gm + 1) / 2, 64, mid_smem, st>>>(g, qmcur, gm, cm);
@@ -805,7 +830,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             uint32_t blocks = std::min<uint32_t>((nsmall + SMALL_WARPS - 1) / SMALL_WARPS, (uint32_t)h->sm_count * 64u);
             CK(cudaEventRecord(h->evs0, st));
             small_started = true;
-            if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            if (reg) k_grow_small4<SMALL_WARPS, true><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            else if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
             else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
             CKL();
             CK(cudaEventRecord(h->evs1, st));
@@ -826,7 +852,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 CKL();
                 k_tiny_sort<<<(ntiny + 255) / 256, 256, 0, st>>>((const uint4*)h->qtiny.p, ntiny, counters + 32, (uint4*)h->qtiny2.p);
                 CKL();
-                k_grow_tiny4<TINY_MAX><<<(ntiny + 127) / 128, 128, 0, st>>>(g, (const uint4*)h->qtiny2.p, ntiny);
+                if (reg) k_grow_tiny4<TINY_MAX, true><<<(ntiny + 127) / 128, 128, 0, st>>>(g, (const uint4*)h->qtiny2.p, ntiny);
+                else k_grow_tiny4<TINY_MAX><<<(ntiny + 127) / 128, 128, 0, st>>>(g, (const uint4*)h->qtiny2.p, ntiny);
                 CKL();
                 CK(cudaEventRecord(h->evm1, st));
                 tiny_timed = true;
@@ -957,6 +984,7 @@ extern "C" int tst_ibp(tst_handle* h, const uint8_t* y_dev, uint8_t* active_dev,
                        int64_t batch, int64_t* removed_host, float* s_per_round_dev, void* stream) {
     if (!h || !y_dev || !active_dev || !prm || !removed_host || rounds < 1) return fail(TST_ERR_INVALID, "tst_ibp: bad argument");
     if (!h->n) return fail(TST_ERR_STATE, "tst_ibp: bin the table first");
+    if (prm->criterion == TST_SQUARED_ERROR) return fail(TST_ERR_UNSUPPORTED, "tst_ibp: pruning is defined on class votes; the squared-error criterion has none");
     if (h->world != 1 && !h->comm) return fail(TST_ERR_STATE, "tst_ibp: world > 1 needs a handle created with an NCCL unique id (or drive the rounds from the host, INTEGRATION.md)");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -1015,7 +1043,7 @@ extern "C" int tst_predict(tst_handle* h, const float* X_dev, int64_t n, uint32_
     CK(cudaMemcpyAsync(h->keep_arenas.p, arenas.data(), arenas.size() * 4, cudaMemcpyHostToDevice, st));
     k_predict<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->pred_rm.as<uint8_t>(), h->dstride, n, h->kept_C, h->keep_nodes.as<uint2>(),
                                                          h->kept_node_stride, h->keep_leafc.as<uint32_t>(), h->kept_leafc_stride,
-                                                         h->keep_arenas.as<uint32_t>(), (uint32_t)arenas.size(), votes_dev);
+                                                         h->keep_arenas.as<uint32_t>(), (uint32_t)arenas.size(), votes_dev, h->kept_criterion == TST_SQUARED_ERROR);
     CKL();
     CK(cudaStreamSynchronize(st));  // `arenas` is a stack-owned staging buffer
     h->stats.kernel_launches += 2;
@@ -1030,6 +1058,7 @@ extern "C" int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node*
     if (!kt) return fail(TST_ERR_STATE, "tst_export_tree: tree not kept (keep_forest = 0, other rank, or out of range)");
     CK(cudaSetDevice(h->device));
     const int C = h->kept_C;
+    const bool regx = h->kept_criterion == TST_SQUARED_ERROR;
     const uint64_t nslots = std::max<uint64_t>(1, 2ull * kt->n_inbag);
     const uint64_t nleafc = ((uint64_t)kt->n_inbag / 2 + 1) * C;
     std::vector<uint2> nodes(nslots);
@@ -1058,6 +1087,11 @@ extern "C" int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node*
             nd.left = (int32_t)q.size(); nd.right = (int32_t)q.size() + 1;
             q.push_back({it.slot + 1, it.begin, it.begin + nl, it.depth + 1});
             q.push_back({rec.x, it.begin + nl, it.end, it.depth + 1});
+        } else if (kind == KIND_PURE && regx) {  // criterion 2: counts = (S low, S high), S = sum of w * yq
+            const uint64_t S = (uint64_t)rec.x * (rec.y & 0xFFFFu);
+            c[0] = (uint32_t)S; c[1] = (uint32_t)(S >> 32); nd.n_weighted = rec.x;
+        } else if (kind == KIND_MIXED && regx) {
+            c[0] = leafc[(uint64_t)rec.x * 2]; c[1] = leafc[(uint64_t)rec.x * 2 + 1]; nd.n_weighted = rec.y & 0x3FFFFFFFu;
         } else if (kind == KIND_PURE) {
             c[rec.y & 0xFFu] = rec.x; nd.n_weighted = rec.x;
         } else if (kind == KIND_MIXED) {
@@ -1068,7 +1102,12 @@ extern "C" int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node*
         out.push_back(nd);
     }
     for (size_t i = out.size(); i-- > 0;) {
-        if (out[i].left >= 0) {
+        if (out[i].left >= 0 && regx) {  // 64-bit sums in two words
+            const size_t l = (size_t)out[i].left * 2, r2 = (size_t)out[i].right * 2;
+            const uint64_t S = ((uint64_t)cnt[l] | ((uint64_t)cnt[l + 1] << 32)) + ((uint64_t)cnt[r2] | ((uint64_t)cnt[r2 + 1] << 32));
+            cnt[i * 2] = (uint32_t)S; cnt[i * 2 + 1] = (uint32_t)(S >> 32);
+            out[i].n_weighted = out[out[i].left].n_weighted + out[out[i].right].n_weighted;
+        } else if (out[i].left >= 0) {
             for (int k2 = 0; k2 < C; ++k2) cnt[i * C + k2] = cnt[(size_t)out[i].left * C + k2] + cnt[(size_t)out[i].right * C + k2];
             out[i].n_weighted = out[out[i].left].n_weighted + out[out[i].right].n_weighted;
         }

@@ -74,6 +74,17 @@ __device__ __forceinline__ void warp_argmax_redux(double& gn, uint32_t& key) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Criterion 2 (squared error on a continuous target): the target is 16-bit fixed point and travels in the
+// entry where the class does (y = multiplicity | yq << 8); a histogram cell is ONE 64-bit word, weight in the low 24 bits
+// and the sum of w * yq in the upper 40 (a node weighs < 2^24, so neither field overflows) -- one 64-bit shared atomic per
+// (row, feature), one 64-bit shuffle chain for the prefix scan, in every tier.
+#define TST_REG 2u
+#define REG_NBITS 24u
+__device__ __forceinline__ unsigned long long reg_cell(uint32_t w, uint32_t yq) { return (unsigned long long)w | ((unsigned long long)(w * yq) << REG_NBITS); }
+__device__ __forceinline__ uint32_t reg_N(unsigned long long P) { return (uint32_t)P & 0xFFFFFFu; }
+__device__ __forceinline__ unsigned long long reg_S(unsigned long long P) { return P >> REG_NBITS; }
+
+// ---------------------------------------------------------------------------------------------
 // One in-bag row of one tree: x = row id, y = bootstrap multiplicity | class << 8.  Real entries have
 // multiplicity >= 1, so y == 0 marks padding.  64-bit entries keep the class next to the row id
 // (no label gather in the hot loops) and leave the full 32 bits to the row id.

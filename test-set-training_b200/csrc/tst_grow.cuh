@@ -88,6 +88,116 @@ __device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// Criterion 2 (continuous squared error): leaves hold (N, S = sum of w * yq).  A leaf whose targets are all equal is a
+// "pure" record (N, yq); any other leaf keeps N in the record and S in the leaf table (two words).
+__device__ __forceinline__ void reg_write_leaf(uint2* nodes, uint32_t* leafc, uint32_t slot, uint32_t begin, uint32_t N, unsigned long long S,
+                                               bool single_value, uint32_t yq) {
+    if (single_value) nodes[slot] = make_uint2(N, (KIND_PURE << 30) | yq);
+    else {
+        leafc[(uint64_t)(begin >> 1) * 2] = (uint32_t)S;
+        leafc[(uint64_t)(begin >> 1) * 2 + 1] = (uint32_t)(S >> 32);
+        nodes[slot] = make_uint2(begin >> 1, (KIND_MIXED << 30) | N);
+    }
+}
+
+// emit_split for criterion 2.  A child of one distinct row is a leaf (its target is trivially constant); whether a larger
+// child is constant is found out when that child is processed (every tier starts a node with the min / max of its targets).
+__device__ __forceinline__ void emit_split_reg(const GrowCtx& g, const Task& t, uint2* nodes, uint32_t* leafc, uint32_t N, unsigned long long S,
+                                               uint32_t NL, unsigned long long SL, uint32_t nLd, uint32_t bf, uint32_t bb, double gain) {
+    const uint32_t right_slot = t.slot + 2u * nLd;
+    write_internal(nodes, t.slot, right_slot, bf, bb);
+    unsigned long long new_leaves = 0;
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t cb = side ? t.begin + nLd : t.begin, ce = side ? t.end : t.begin + nLd;
+        const uint32_t cslot = side ? right_slot : t.slot + 1u;
+        const uint32_t Nc = side ? N - NL : NL;
+        const unsigned long long Sc = side ? S - SL : SL;
+        const uint32_t cr = ce - cb;
+        if (stop_rule(g, Nc, t.depth + 1u, cr == 1u)) {
+            reg_write_leaf(nodes, leafc, cslot, cb, Nc, Sc, cr == 1u, cr == 1u ? (uint32_t)(Sc / Nc) : 0u);
+            new_leaves++;
+        } else {
+            Task ct;
+            ct.tree = t.tree; ct.begin = cb; ct.end = ce; ct.depth = t.depth + 1u; ct.slot = cslot;
+            ct.pad0 = ct.pad2 = 0;
+            ct.pad1 = Nc;
+            if (cr <= g.tiny_max) tiny_push(g, t.tree, cb, cr, t.depth + 1u, cslot, (t.depth + 1u) & 1u);
+            else if (cr <= SMALL_MAX) queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
+            else if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
+            else queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
+        }
+    }
+    atomicAdd(&g.stats->nodes, 1ull + new_leaves);
+    if (new_leaves) { atomicAdd(&g.stats->leaves, new_leaves); atomicMax(&g.stats->max_depth, t.depth + 1u); }
+    atomicAdd(&g.stats->searched, 1ull);
+    imp_add(g, g.trees[t.tree].imp_row, bf, gain, imp_parent_mse(S, N));
+}
+
+// Split scan of one feature for criterion 2: cells are 64-bit (weight | sum << 24), lane l owns bins [8l, 8l+8) of the
+// packed layout (80-byte lane segments).  Same structure as scan_feature_packed4: one 64-bit shuffle chain, fp32 estimate,
+// fp64 gain S_L^2/N_L + S_R^2/N_R of the contenders, ties -> lowest bin.
+__device__ __forceinline__ void scan_feature_reg(const uint32_t* __restrict__ hf, uint32_t msl, uint32_t lane, double& best_gain, uint32_t& best_bin,
+                                                 unsigned long long& bestP, unsigned long long& tot_out) {
+    const ulonglong2* hl = (const ulonglong2*)(hf + lane * 20u);
+    unsigned long long p[8], run = 0;
+    uint32_t occ = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const ulonglong2 hq = hl[q >> 1];
+        const unsigned long long h = (q & 1) ? hq.y : hq.x;
+        occ |= (h ? 1u : 0u) << q;
+        run += h;
+        p[q] = run;
+    }
+    unsigned long long incl = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long a = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= (uint32_t)off) incl += a;
+    }
+    const unsigned long long excl = incl - run, tot = __shfl_sync(0xffffffffu, incl, 31);
+    tot_out = tot;
+    const uint32_t N = reg_N(tot);
+    const unsigned long long S = reg_S(tot);
+    float ge[8], lmax = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        ge[q] = -1.0f;
+        if ((occ >> q) & 1u) {
+            const unsigned long long P = excl + p[q];
+            const uint32_t NL = reg_N(P), NR = N - NL;
+            if (NL >= msl && NR >= msl) {
+                const unsigned long long SL = reg_S(P);
+                ge[q] = mse_gain_estimate(__ull2float_rn(SL), __uint2float_rn(NL), __ull2float_rn(S - SL), __uint2float_rn(NR));
+                lmax = fmaxf(lmax, ge[q]);
+            }
+        }
+    }
+    const float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lmax))) * TST_EST_MARGIN;
+    double bg = -1.0;
+    uint32_t bb = 0xFFFFFFFFu;
+    unsigned long long bP = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (ge[q] >= thr) {
+            const unsigned long long P = excl + p[q];
+            const uint32_t NL = reg_N(P);
+            const double gn = mse_gain(reg_S(P), NL, S - reg_S(P), N - NL);
+            if (gn > bg) { bg = gn; bb = lane * 8u + q; bP = P; }
+        }
+    }
+    double wg = bg;
+    uint32_t wb = bb;
+    warp_argmax_redux(wg, wb);
+    if (wb != 0xFFFFFFFFu) {
+        const uint32_t winner = __ffs(__ballot_sync(0xffffffffu, bb == wb && bg == wg)) - 1;
+        bestP = __shfl_sync(0xffffffffu, bP, winner);
+    }
+    best_gain = wg;
+    best_bin = wb;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Split scan of one feature histogram by one warp.  Lane l owns bins [8l, 8l+8).  Per class: local
 // inclusive prefix, warp-shuffle exclusive scan of the lane totals, then L/R sums of squares are
 // accumulated exactly in uint64.  Returns the warp-wide best (gain, bin) with ties -> lowest bin.
@@ -279,9 +389,12 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
 #define BIG_MINB 3
 #endif
 // ---------------------------------------------------------------------------------------------
-template <int THREADS, bool MSE = false>  // MSE: squared-error criterion on ordinal levels (its own instantiation: the Gini one keeps its registers)
+template <int THREADS, int CRIT = 0>  // CRIT: 0 Gini, 1 squared error on ordinal levels, 2 squared error on the 16-bit target (own instantiations: the Gini one keeps its registers)
 __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     constexpr int NW = THREADS / 32;
+    constexpr bool MSE = CRIT == 1, REG = CRIT == 2;
+    __shared__ unsigned long long s_fP[32], s_totP, s_bestP;  // criterion 2: left cell of each feature's best split, node total, best split's left cell
+    __shared__ uint32_t s_ymin, s_ymax;
     extern __shared__ __align__(16) uint32_t s_hist[];  // [MB][FS] histogram, then (row tile) [THREADS][dstride/4 + 1]
     __shared__ uint32_t s_fL[8][4];  // packed nodes: left class counts of each feature's best split
     __shared__ uint16_t s_perm[TST_MAX_FEATURES];
@@ -309,13 +422,13 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     const uint32_t dstride = g.dstride;
     const bool use_tile = g.big_tile != 0;
     // a node that weighs < 2^16 (its parent wrote the weight into the task) uses the packed histogram and scan
-    const bool packed = !MSE && g.big_packed != 0u && use_tile && C <= 4 && g.MB <= 8 && t.pad1 != 0u && t.pad1 <= 65535u;
+    const bool packed = REG || (!MSE && g.big_packed != 0u && use_tile && C <= 4 && g.MB <= 8 && t.pad1 != 0u && t.pad1 <= 65535u);
     const uint32_t HFS = packed ? BIGP_FS : (uint32_t)g.FS;  // histogram words per feature
     const uint32_t pitch = (dstride >> 2) + 1u;
     uint32_t* s_tile = s_hist + g.MB * g.HFS_max + wid * 32u * pitch;  // this warp's rows (the histogram region holds either layout)
 
     for (int f = tid; f < d; f += THREADS) s_perm[f] = (uint16_t)f;
-    if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; s_sj = 0xFFFFFFFFu; }
+    if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; s_sj = 0xFFFFFFFFu; s_ymin = 0xFFFFFFFFu; s_ymax = 0u; s_totP = 0ull; }
     __syncthreads();
 
     // roots already split by the dense column-major kernels (tst_root.cuh) only need the partition below
@@ -360,6 +473,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
             const uint8_t* trow = (const uint8_t*)(s_tile + lane * pitch);
             // the entry of the NEXT tile is requested before this tile's rows: the two dependent latencies
             // (entry list from HBM, then the row gather from L2) overlap across iterations
+            uint32_t ymn = 0xFFFFFFFFu, ymx = 0u;
             Entry e_next = t.begin + tid < t.end ? ent_load(ent_in + t.begin + tid) : make_uint2(0u, 0u);
             for (uint32_t base = t.begin; base < t.end; base += THREADS) {
                 const Entry e = e_next;
@@ -371,7 +485,17 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                 if (e.y) {
                     const uint32_t cls = ent_cls(e), w = ent_w(e);
                     uint32_t sb0 = 0, sb1 = 0;  // the row's sampled bins, byte jj = feature jj of the draw
-                    if (packed) {
+                    if (REG) {
+                        const unsigned long long val = reg_cell(w, cls);  // `cls` is the 16-bit target here
+                        ymn = min(ymn, cls); ymx = max(ymx, cls);
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj)
+                            if (jj < nb) {
+                                const uint32_t bj = trow[featr[jj]];
+                                if (jj < 4) sb0 |= bj << (8 * jj); else sb1 |= bj << (8 * (jj - 4));
+                                atomicAdd((unsigned long long*)&s_hist[jj * BIGP_FS + (bj >> 3) * 20u + (bj & 7u) * 2u], val);
+                            }
+                    } else if (packed) {
                         const uint32_t coff = cls >> 1, val = w << (16u * (cls & 1u));
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj)
@@ -393,7 +517,12 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                 }
                 __syncwarp();
             }
+            if (REG && pos == 0) {  // is the node's target constant?  (its parent could not know)
+                ymn = __reduce_min_sync(0xffffffffu, ymn); ymx = __reduce_max_sync(0xffffffffu, ymx);
+                if (lane == 0) { atomicMin(&s_ymin, ymn); atomicMax(&s_ymax, ymx); }
+            }
         } else {
+            uint32_t ymn = 0xFFFFFFFFu, ymx = 0u;
             constexpr int U = 4;
             for (uint32_t base = t.begin + tid; base < t.end; base += THREADS * U) {
                 Entry e[U];
@@ -412,8 +541,18 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                     for (int u = 0; u < U; ++u) b[u] = e[u].y ? (uint32_t)bins[(uint64_t)e[u].x * dstride + f] : 0u;
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (e[u].y) atomicAdd(&s_hist[j * g.FS + hist_index(b[u], ent_cls(e[u]), C)], ent_w(e[u]));
+                        if (e[u].y) {
+                            if (REG) atomicAdd((unsigned long long*)&s_hist[j * BIGP_FS + (b[u] >> 3) * 20u + (b[u] & 7u) * 2u], reg_cell(ent_w(e[u]), ent_cls(e[u])));
+                            else atomicAdd(&s_hist[j * g.FS + hist_index(b[u], ent_cls(e[u]), C)], ent_w(e[u]));
+                        }
                 }
+                if (REG)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (e[u].y) { ymn = min(ymn, ent_cls(e[u])); ymx = max(ymx, ent_cls(e[u])); }
+            }
+            if (REG && pos == 0) {
+                ymn = __reduce_min_sync(0xffffffffu, ymn); ymx = __reduce_max_sync(0xffffffffu, ymx);
+                if (lane == 0) { atomicMin(&s_ymin, ymn); atomicMax(&s_ymax, ymx); }
             }
         }
         __syncthreads();
@@ -422,7 +561,14 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
         for (int j = wid; j < nb; j += NW) {
             double bg; uint32_t bb;
             bool want_tot = (pos == 0 && j == 0);
-            if (packed) {
+            if (REG) {
+                unsigned long long P = 0, tot;
+                scan_feature_reg(s_hist + j * BIGP_FS, g.msl, lane, bg, bb, P, tot);
+                if (lane == 0) {
+                    s_fP[j] = P;
+                    if (want_tot) { s_totP = tot; s_N = reg_N(tot); }
+                }
+            } else if (packed) {
                 uint32_t P0 = 0, P1 = 0, T0, T1;
                 scan_feature_packed4(s_hist + j * BIGP_FS, g.msl, lane, bg, bb, P0, P1, T0, T1);
                 if (lane == 0) {
@@ -441,7 +587,8 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
         if (tid == 0) {
             if (pos == 0) {
                 bool pure = false;
-                for (int c = 0; c < C; ++c) pure |= (s_tot[c] == s_N);
+                if (REG) pure = s_ymin == s_ymax;
+                else for (int c = 0; c < C; ++c) pure |= (s_tot[c] == s_N);
                 if (stop_rule(g, s_N, t.depth, pure)) s_stop = 1;
             }
             if (primary) {
@@ -461,8 +608,10 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                 }
             }
         }
-        if (tid == 0 && packed && s_newj != 0xFFFFFFFFu)
-            for (int c = 0; c < C; ++c) s_bestL[c] = s_fL[s_newj][c];
+        if (tid == 0 && packed && s_newj != 0xFFFFFFFFu) {
+            if (REG) s_bestP = s_fP[s_newj];
+            else for (int c = 0; c < C; ++c) s_bestL[c] = s_fL[s_newj][c];
+        }
         __syncthreads();
         if (s_stop) break;
         if (s_newj != 0xFFFFFFFFu && !packed) {
@@ -486,12 +635,15 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     if (s_stop || !s_found) {
         // leaf: root that needs no split, or no feature separates the rows
         if (tid == 0) {
-            int pc = -1;
-            for (int c = 0; c < C; ++c) if (s_tot[c] == s_N) pc = c;
-            if (pc >= 0) write_pure_leaf(nodes, t.slot, s_N, (uint32_t)pc);
+            if (REG) reg_write_leaf(nodes, leafc, t.slot, t.begin, s_N, reg_S(s_totP), s_ymin == s_ymax, s_ymin);
             else {
-                for (int c = 0; c < C; ++c) leafc[(uint64_t)(t.begin >> 1) * C + c] = s_tot[c];
-                write_mixed_leaf(nodes, t.slot, t.begin);
+                int pc = -1;
+                for (int c = 0; c < C; ++c) if (s_tot[c] == s_N) pc = c;
+                if (pc >= 0) write_pure_leaf(nodes, t.slot, s_N, (uint32_t)pc);
+                else {
+                    for (int c = 0; c < C; ++c) leafc[(uint64_t)(t.begin >> 1) * C + c] = s_tot[c];
+                    write_mixed_leaf(nodes, t.slot, t.begin);
+                }
             }
             atomicAdd(&g.stats->nodes, 1ull);
             atomicAdd(&g.stats->leaves, 1ull);
@@ -564,7 +716,8 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 
     // ---- node record + children (leaf children are finished here, the rest are queued)
     if (tid == 0) {
-        emit_split(g, t, nodes, leafc, s_tot, s_bestL, s_N, nLd, bf, bb, presplit ? -1.0 : s_bgain);
+        if (REG) emit_split_reg(g, t, nodes, leafc, s_N, reg_S(s_totP), reg_N(s_bestP), reg_S(s_bestP), nLd, bf, bb, s_bgain);
+        else emit_split(g, t, nodes, leafc, s_tot, s_bestL, s_N, nLd, bf, bb, presplit ? -1.0 : s_bgain);
         atomicAdd(&g.stats->row_visits_big, (unsigned long long)r);
     }
 }

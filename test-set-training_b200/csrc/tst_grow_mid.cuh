@@ -176,9 +176,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 #ifndef MID_MINB
 #define MID_MINB 5
 #endif
-template <int WARPS, int R>
+template <int WARPS, int R, bool REG = false>  // REG: criterion 2 -- a cell is (weight | sum of w * yq << 24) instead of four 16-bit class counts
 __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
-    static_assert(32 * R * 255 < 65536, "packed 16-bit class counts need <= 256 rows per node");
+    static_assert(REG || 32 * R * 255 < 65536, "packed 16-bit class counts need <= 256 rows per node");
     extern __shared__ __align__(16) uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int C = g.C, d = g.d, m = g.m;
@@ -217,6 +217,12 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
     double best_gain = -1.0;
     uint32_t best_key = 0xFFFFFFFFu, bestP0 = 0, bestP1 = 0;
     uint32_t N = 0, T0 = 0, T1 = 0;
+    uint32_t ymn = 0xFFFFFFFFu, ymx = 0u;  // criterion 2: is the node's target constant?
+    if (REG) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) if (e[k].y) { ymn = min(ymn, ent_cls(e[k])); ymx = max(ymx, ent_cls(e[k])); }
+        ymn = __reduce_min_sync(0xffffffffu, ymn); ymx = __reduce_max_sync(0xffffffffu, ymx);
+    }
     uint32_t bnext[R];
     {
         const uint32_t f0 = s_perm[0];
@@ -259,7 +265,10 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < R; ++k)
-            if (e[k].y) atomicAdd(&s_hist[(b[k] >> 3) * 20u + (b[k] & 7u) * 2u + (ent_cls(e[k]) >> 1)], ent_w(e[k]) << (16u * (ent_cls(e[k]) & 1u)));
+            if (e[k].y) {
+                if (REG) atomicAdd((unsigned long long*)&s_hist[(b[k] >> 3) * 20u + (b[k] & 7u) * 2u], reg_cell(ent_w(e[k]), ent_cls(e[k])));
+                else atomicAdd(&s_hist[(b[k] >> 3) * 20u + (b[k] & 7u) * 2u + (ent_cls(e[k]) >> 1)], ent_w(e[k]) << (16u * (ent_cls(e[k]) & 1u)));
+            }
         __syncwarp();
         // packed prefix scan over bins
         const uint4* hl = (const uint4*)(s_hist + lane * 20u);
@@ -269,7 +278,10 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
             const uint4 hq = hl[q >> 1];  // two bins per 128-bit load (the compiler keeps one load per pair)
             const uint32_t h0 = (q & 1) ? hq.z : hq.x, h1 = (q & 1) ? hq.w : hq.y;
             occ |= ((h0 | h1) ? 1u : 0u) << q;
-            run0 += h0; run1 += h1;
+            if (REG) {  // one 64-bit field pair: the sum straddles the word boundary, so the carry must propagate
+                const unsigned long long acc = ((unsigned long long)run0 | ((unsigned long long)run1 << 32)) + ((unsigned long long)h0 | ((unsigned long long)h1 << 32));
+                run0 = (uint32_t)acc; run1 = (uint32_t)(acc >> 32);
+            } else { run0 += h0; run1 += h1; }
             p0[q] = run0; p1[q] = run1;
         }
         unsigned long long run = (unsigned long long)run0 | ((unsigned long long)run1 << 32), incl = run;
@@ -286,8 +298,8 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         if (i == 0) {
             T0 = (uint32_t)tot; T1 = (uint32_t)(tot >> 32);
             const uint32_t t0 = T0 & 0xFFFFu, t1 = T0 >> 16, t2 = T1 & 0xFFFFu, t3 = T1 >> 16;
-            N = t0 + t1 + t2 + t3;
-            const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
+            N = REG ? reg_N(tot) : t0 + t1 + t2 + t3;
+            const bool pure = REG ? ymn == ymx : (t0 == N || t1 == N || t2 == N || t3 == N);
             if (stop_rule(g, N, t.depth, pure)) { stop = true; break; }
         }
         // candidate list = occupied bins in ascending order: left counts packed | bin | fp32 gain estimate (SoA)
@@ -296,6 +308,10 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
 #pragma unroll
             for (int q = 0; q < 8; ++q)
                 if ((occ >> q) & 1u) {
+                    if (REG) {
+                        const unsigned long long P = excl + ((unsigned long long)p0[q] | ((unsigned long long)p1[q] << 32));
+                        ((uint2*)s_cand)[j] = make_uint2((uint32_t)P, (uint32_t)(P >> 32));
+                    } else
                     ((uint2*)s_cand)[j] = make_uint2(e0 + p0[q], e1 + p1[q]);  // one 64-bit store for both packed words
                     s_cand[512u + j] = lane * 8u + q;
                     ++j;
@@ -303,14 +319,22 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         }
         __syncwarp();
         const uint32_t t0 = T0 & 0xFFFFu, t1 = T0 >> 16, t2 = T1 & 0xFFFFu, t3 = T1 >> 16;
+        const unsigned long long Stot = reg_S((unsigned long long)T0 | ((unsigned long long)T1 << 32));  // criterion 2
         // pass 1: fp32 estimates (a node here weighs < 2^16, so the sums of squares fit 32 bits)
         float lmax = 0.0f;
         for (uint32_t j = lane; j < n_cand; j += 32) {
             const uint2 PP = ((const uint2*)s_cand)[j];
             const uint32_t P0 = PP.x, P1 = PP.y;
             const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
-            const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+            const unsigned long long P = (unsigned long long)P0 | ((unsigned long long)P1 << 32);
+            const uint32_t NL = REG ? reg_N(P) : L0 + L1 + L2 + L3, NR = N - NL;
             float ge = -1.0f;
+            if (REG) {
+                if (NL >= g.msl && NR >= g.msl) {
+                    ge = mse_gain_estimate(__ull2float_rn(reg_S(P)), __uint2float_rn(NL), __ull2float_rn(Stot - reg_S(P)), __uint2float_rn(NR));
+                    lmax = fmaxf(lmax, ge);
+                }
+            } else
             if (NL >= g.msl && NR >= g.msl) {
                 const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
                 const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
@@ -330,10 +354,11 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
                 const uint2 PP = ((const uint2*)s_cand)[j];
                 const uint32_t P0 = PP.x, P1 = PP.y, bin = s_cand[512u + j];
                 const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
-                const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+                const unsigned long long P = (unsigned long long)P0 | ((unsigned long long)P1 << 32);
+                const uint32_t NL = REG ? reg_N(P) : L0 + L1 + L2 + L3, NR = N - NL;
                 const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
                 const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
-                const double gn = gini_gain(SL, NL, SR, NR);
+                const double gn = REG ? mse_gain(reg_S(P), NL, Stot - reg_S(P), NR) : gini_gain(SL, NL, SR, NR);
                 if (gn > bg) { bg = gn; bb = bin; bP0 = P0; bP1 = P1; }  // ascending bins: strict > keeps the lowest
             }
         }
@@ -360,14 +385,18 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         s_bestL[0] = bestP0 & 0xFFFFu; s_bestL[1] = bestP0 >> 16; s_bestL[2] = bestP1 & 0xFFFFu; s_bestL[3] = bestP1 >> 16;
     }
     __syncwarp();
+    const unsigned long long Ptot = (unsigned long long)T0 | ((unsigned long long)T1 << 32), Pbest = (unsigned long long)bestP0 | ((unsigned long long)bestP1 << 32);
     if (stop || !found) {
         if (lane == 0) {
             int pc = -1;
+            if (REG) reg_write_leaf(nodes, leafc, t.slot, t.begin, N, reg_S(Ptot), ymn == ymx, ymn);
+            else {
             for (int c = 0; c < C; ++c) if (s_tot[c] == N) pc = c;
             if (pc >= 0) write_pure_leaf(nodes, t.slot, N, (uint32_t)pc);
             else {
                 for (int c = 0; c < C; ++c) leafc[(uint64_t)(t.begin >> 1) * C + c] = s_tot[c];
                 write_mixed_leaf(nodes, t.slot, t.begin);
+            }
             }
             atomicAdd(&g.stats->nodes, 1ull);
             atomicAdd(&g.stats->leaves, 1ull);
@@ -401,7 +430,8 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         rbase += __popc(balR);
     }
     if (lane == 0) {
-        emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nLd, bf, bbin, best_gain);
+        if (REG) emit_split_reg(g, t, nodes, leafc, N, reg_S(Ptot), reg_N(Pbest), reg_S(Pbest), nLd, bf, bbin, best_gain);
+        else emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nLd, bf, bbin, best_gain);
         atomicAdd(&g.stats->row_visits_mid, (unsigned long long)r);
     }
 }

@@ -28,12 +28,14 @@ __device__ __forceinline__ void warp_argmax(double& gn, uint32_t& key) {
 }
 
 #define F13(x, c) ((uint32_t)((x) >> (13 * (c))) & 0x1FFFu)
+// criterion 2: the 64-bit word of a row is weight (13 bits) | w * yq (39 bits) [| bin << 52 while comparing]
+#define REG13_S(x) (((x) >> 13) & 0x7FFFFFFFFFull)
 
 #ifndef SMALL_MINB
 #define SMALL_MINB 7  // 72 registers: measured 117.4 ms per 640 trees vs 121.8 (8 CTAs, 64 registers, spills), 120 (6), 122.6 (5)
 #endif
 #define TINY_RESERVE 8u  // tiny-queue slots a warp of k_grow_small4 reserves per atomic
-template <int WARPS>
+template <int WARPS, bool REG = false>  // REG: criterion 2 (continuous squared error), same register-only scheme on (weight, sum) words
 __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     extern __shared__ __align__(16) uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -65,11 +67,18 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
             const bool active = lane >= lo && lane < hi;
             const uint32_t rr = hi - lo;
             const uint32_t abs_begin = t.begin + lo;
-            const unsigned long long cw = active ? ((unsigned long long)ent_w(e) << (13u * ent_cls(e))) : 0ull;
+            const unsigned long long cw = !active ? 0ull : REG ? ((unsigned long long)ent_w(e) | ((unsigned long long)(ent_w(e) * ent_cls(e)) << 13))
+                                                               : ((unsigned long long)ent_w(e) << (13u * ent_cls(e)));
             const unsigned long long tot = warp_sum64(cw);
             const uint32_t t0 = F13(tot, 0), t1 = F13(tot, 1), t2 = F13(tot, 2), t3 = F13(tot, 3);
-            const uint32_t N = t0 + t1 + t2 + t3;
-            const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
+            const uint32_t N = REG ? t0 : t0 + t1 + t2 + t3;
+            const unsigned long long Stot = REG13_S(tot);
+            uint32_t ymn = 0, ymx = 0;
+            if (REG) {
+                ymn = __reduce_min_sync(0xffffffffu, active ? ent_cls(e) : 0xFFFFFFFFu);
+                ymx = __reduce_max_sync(0xffffffffu, active ? ent_cls(e) : 0u);
+            }
+            const bool pure = REG ? ymn == ymx : (t0 == N || t1 == N || t2 == N || t3 == N);
             const bool stop = stop_rule(g, N, depth, pure);
             if (!stop && rr <= g.tiny_max) {
                 // hand the node to the thread-per-subtree tier: park its rows in the entry buffer of its depth
@@ -105,7 +114,8 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                 Entry e_g;
                 e_g.x = __shfl_sync(0xffffffffu, e.x, srcl);
                 e_g.y = __shfl_sync(0xffffffffu, e.y, srcl);
-                const unsigned long long cw_g = gvalid ? ((unsigned long long)ent_w(e_g) << (13u * ent_cls(e_g))) : 0ull;
+                const unsigned long long cw_g = !gvalid ? 0ull : REG ? ((unsigned long long)ent_w(e_g) | ((unsigned long long)(ent_w(e_g) * ent_cls(e_g)) << 13))
+                                                                     : ((unsigned long long)ent_w(e_g) << (13u * ent_cls(e_g)));
                 const uint8_t* __restrict__ rowp = bins + (uint64_t)e_g.x * dstride;
                 for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
                 __syncwarp();
@@ -152,21 +162,23 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                         if ((uint32_t)(c.y >> 32) <= cmp) acc += c.y;
                     }
                     const uint32_t L0 = F13(acc, 0), L1 = F13(acc, 1), L2 = F13(acc, 2), L3 = F13(acc, 3);
-                    const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+                    const uint32_t NL = REG ? L0 : L0 + L1 + L2 + L3, NR = N - NL;
                     const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
                     const bool ok = lv && NL >= g.msl && NR >= g.msl;
                     // a node here weighs < 2^13: the sums of squares fit 32 bits
                     const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+                    const unsigned long long SLr = REG13_S(acc), SRr = Stot - SLr;  // criterion 2
                     double gn = -1.0;
                     uint32_t key = 0xFFFFFFFFu;
                     if (pos0 < m) {
                         // fp32 estimate first; the exact fp64 gain only where it can still win (tst_common.cuh: gain_estimate)
-                        const float ge = ok ? gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR)) : 0.0f;
+                        const float ge = !ok ? 0.0f : REG ? mse_gain_estimate(__ull2float_rn(SLr), __uint2float_rn(NL), __ull2float_rn(SRr), __uint2float_rn(NR))
+                                                          : gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR));
                         float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ge)));
                         if (found) thr = fmaxf(thr, __double2float_rd(best_gain));
                         thr *= TST_EST_MARGIN;
                         if (ok && ge >= thr) {
-                            gn = gini_gain(SL, NL, SR, NR);
+                            gn = REG ? mse_gain(SLr, NL, SRr, NR) : gini_gain(SL, NL, SR, NR);
                             key = (pos << 8) | b;  // ties among the positions evaluated side by side: the feature drawn first, then lowest bin
                         }
                         warp_argmax_redux(gn, key);
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                     } else {
                         // fallback: the first position in draw order that has any valid split
                         if (ok) {
-                            gn = gini_gain(SL, NL, SR, NR);
+                            gn = REG ? mse_gain(SLr, NL, SRr, NR) : gini_gain(SL, NL, SR, NR);
                             key = (f << 8) | b;
                         }
                         uint32_t mp = ok ? pos : 0xFFFFFFFFu;
@@ -193,7 +205,9 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
             }
             if (!found) {
                 n_leaves++;
-                if (pure) {
+                if (REG) {
+                    if (lane == 0) reg_write_leaf(nodes, leafc, slot, abs_begin, N, Stot, pure, ymn);
+                } else if (pure) {
                     const uint32_t pc = t0 == N ? 0u : (t1 == N ? 1u : (t2 == N ? 2u : 3u));
                     if (lane == 0) write_pure_leaf(nodes, slot, N, pc);
                 } else {
@@ -229,7 +243,7 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
             const uint32_t right_slot = slot + 2u * nLd;
             if (lane == 0) {
                 write_internal(nodes, slot, right_slot, bf, bb);
-                imp_add(g, td.imp_row, bf, best_gain, imp_parent_gini((unsigned long long)(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3), N));
+                imp_add(g, td.imp_row, bf, best_gain, REG ? imp_parent_mse(Stot, N) : imp_parent_gini((unsigned long long)(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3), N));
                 s_stack[sp * 3] = (lo + nLd) | (hi << 8);
                 s_stack[sp * 3 + 1] = depth + 1u;
                 s_stack[sp * 3 + 2] = right_slot;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_tiny_sort(const uint4* __restrict__ in,
 #ifndef TINY_MINB
 #define TINY_MINB 1
 #endif
-template <int TMAX>
+template <int TMAX, bool REG = false>  // REG: criterion 2, words are weight (13 bits) | w * yq (39 bits)
 __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const uint4* __restrict__ tasks, uint32_t ntasks) {
     const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = ti < ntasks;
@@ -64,17 +64,26 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
         const Entry* __restrict__ ent = ((tk.z >> 31) ? g.entB : g.entA) + (uint64_t)tree * g.n_cap + tk.x;  // bit 31: which buffer the producer parked the rows in
         uint2* nodes = g.nodes + (uint64_t)arena * g.node_stride;
         uint32_t* leafc = g.leafc + (uint64_t)arena * g.leafc_stride;
-        uint32_t row[TMAX];
+        uint32_t row[TMAX], yv[TMAX];
         unsigned long long cw[TMAX];
 #pragma unroll
         for (int k = 0; k < TMAX; ++k) {
-            row[k] = 0; cw[k] = 0;
+            row[k] = 0; cw[k] = 0; yv[k] = 0;
             if (k < (int)r) {
                 const Entry e = ent_load(ent + k);
                 row[k] = e.x;
-                cw[k] = (unsigned long long)ent_w(e) << (13u * ent_cls(e));
+                yv[k] = ent_cls(e);
+                cw[k] = REG ? ((unsigned long long)ent_w(e) | ((unsigned long long)(ent_w(e) * ent_cls(e)) << 13)) : ((unsigned long long)ent_w(e) << (13u * ent_cls(e)));
             }
         }
+        // criterion 2: a node (bit mask over the slots) is constant when its targets' min equals their max
+        auto reg_const = [&](uint32_t msk, uint32_t& y_any) {
+            uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+            for (int k = 0; k < TMAX; ++k) if ((msk >> k) & 1u) { mn = min(mn, yv[k]); mx = max(mx, yv[k]); }
+            y_any = mn;
+            return mn == mx;
+        };
         // Every loop iteration is one split search: leaf children are written at split time and never come back
         // through the loop, so the lanes of a warp do the same kind of work (tasks are sorted by row count).
         uint32_t st_mask[TMAX], st_begin[TMAX], st_slot[TMAX], st_depth[TMAX];
@@ -85,12 +94,14 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
 #pragma unroll
         for (int k = 0; k < TMAX; ++k) tot += cw[k];
         bool have = true;
-        {   // the task's root was checked by its producer, except tree roots: check once
-            const uint32_t t0 = F13(tot, 0), t1 = F13(tot, 1), t2 = F13(tot, 2), t3 = F13(tot, 3), N = t0 + t1 + t2 + t3;
-            const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
+        {   // the task's root was checked by its producer, except tree roots (and, for criterion 2, constant targets): check once
+            const uint32_t t0 = F13(tot, 0), t1 = F13(tot, 1), t2 = F13(tot, 2), t3 = F13(tot, 3), N = REG ? t0 : t0 + t1 + t2 + t3;
+            uint32_t yc = 0;
+            const bool pure = REG ? reg_const(mask, yc) : (t0 == N || t1 == N || t2 == N || t3 == N);
             if (stop_rule(g, N, depth, pure)) {
                 n_nodes++; n_leaves++; maxd = max(maxd, depth);
-                if (pure) write_pure_leaf(nodes, slot, N, t0 == N ? 0u : (t1 == N ? 1u : (t2 == N ? 2u : 3u)));
+                if (REG) reg_write_leaf(nodes, leafc, slot, begin, N, REG13_S(tot), pure, yc);
+                else if (pure) write_pure_leaf(nodes, slot, N, t0 == N ? 0u : (t1 == N ? 1u : (t2 == N ? 2u : 3u)));
                 else {
                     for (int c = 0; c < C; ++c) leafc[(uint64_t)(begin >> 1) * C + c] = F13(tot, c);
                     write_mixed_leaf(nodes, slot, begin);
@@ -100,7 +111,8 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
         }
         while (have) {
             const uint32_t t0 = F13(tot, 0), t1 = F13(tot, 1), t2 = F13(tot, 2), t3 = F13(tot, 3);
-            const uint32_t N = t0 + t1 + t2 + t3;
+            const uint32_t N = REG ? t0 : t0 + t1 + t2 + t3;
+            const unsigned long long Stot = REG13_S(tot);
             n_nodes++;
             maxd = max(maxd, depth);
             visits += __popc(mask);
@@ -136,12 +148,12 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
 #pragma unroll
                         for (int k = 0; k < TMAX; ++k) if (b[k] <= b[c]) acc += cw[k] & (((mask >> k) & 1u) ? ~0ull : 0ull);
                         const uint32_t L0 = F13(acc, 0), L1 = F13(acc, 1), L2 = F13(acc, 2), L3 = F13(acc, 3);
-                        const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+                        const uint32_t NL = REG ? L0 : L0 + L1 + L2 + L3, NR = N - NL;
                         if (((mask >> c) & 1u) && NL >= g.msl && NR >= g.msl) {
                             const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
                             unsigned long long SL = (unsigned long long)L0 * L0 + (unsigned long long)L1 * L1 + (unsigned long long)L2 * L2 + (unsigned long long)L3 * L3;
                             unsigned long long SR = (unsigned long long)R0 * R0 + (unsigned long long)R1 * R1 + (unsigned long long)R2 * R2 + (unsigned long long)R3 * R3;
-                            const double gn = gini_gain(SL, NL, SR, NR);
+                            const double gn = REG ? mse_gain(REG13_S(acc), NL, Stot - REG13_S(acc), NR) : gini_gain(SL, NL, SR, NR);
                             const uint32_t key = (f << 8) | b[c];
                             if (gn > fg || (gn == fg && key < fkey)) { fg = gn; fkey = key; }
                         }
@@ -157,8 +169,11 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
             }
             if (!found) {  // no feature separates the rows: a mixed leaf
                 n_leaves++;
-                for (int c = 0; c < C; ++c) leafc[(uint64_t)(begin >> 1) * C + c] = F13(tot, c);
-                write_mixed_leaf(nodes, slot, begin);
+                if (REG) reg_write_leaf(nodes, leafc, slot, begin, N, Stot, false, 0u);
+                else {
+                    for (int c = 0; c < C; ++c) leafc[(uint64_t)(begin >> 1) * C + c] = F13(tot, c);
+                    write_mixed_leaf(nodes, slot, begin);
+                }
             } else {
                 const uint32_t bf = best_key >> 8, bb = best_key & 0xFFu;
                 uint32_t mL = 0;
@@ -170,17 +185,19 @@ __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const 
                 if (nLd == 0 || mL == mask) { g.stats->error = 4; break; }
                 const uint32_t right_slot = slot + 2u * nLd;
                 write_internal(nodes, slot, right_slot, bf, bb);
-                imp_add(g, imp_row, bf, best_gain, imp_parent_gini((unsigned long long)(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3), N));
+                imp_add(g, imp_row, bf, best_gain, REG ? imp_parent_mse(Stot, N) : imp_parent_gini((unsigned long long)(t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3), N));
                 // children: leaves are finished here, the others are stacked (right first, so the left one is next)
 #pragma unroll
                 for (int side = 1; side >= 0; --side) {
                     const unsigned long long ct = side ? tot - totL : totL;
                     const uint32_t cm = side ? (mask & ~mL) : mL, cb = side ? begin + nLd : begin, cs = side ? right_slot : slot + 1u;
-                    const uint32_t c0 = F13(ct, 0), c1 = F13(ct, 1), c2 = F13(ct, 2), c3 = F13(ct, 3), Nc = c0 + c1 + c2 + c3;
-                    const bool cpure = c0 == Nc || c1 == Nc || c2 == Nc || c3 == Nc;
+                    const uint32_t c0 = F13(ct, 0), c1 = F13(ct, 1), c2 = F13(ct, 2), c3 = F13(ct, 3), Nc = REG ? c0 : c0 + c1 + c2 + c3;
+                    uint32_t yc = 0;
+                    const bool cpure = REG ? reg_const(cm, yc) : (c0 == Nc || c1 == Nc || c2 == Nc || c3 == Nc);
                     if (stop_rule(g, Nc, depth + 1u, cpure)) {
                         n_nodes++; n_leaves++; maxd = max(maxd, depth + 1u);
-                        if (cpure) write_pure_leaf(nodes, cs, Nc, c0 == Nc ? 0u : (c1 == Nc ? 1u : (c2 == Nc ? 2u : 3u)));
+                        if (REG) reg_write_leaf(nodes, leafc, cs, cb, Nc, REG13_S(ct), cpure, yc);
+                        else if (cpure) write_pure_leaf(nodes, cs, Nc, c0 == Nc ? 0u : (c1 == Nc ? 1u : (c2 == Nc ? 2u : 3u)));
                         else {
                             for (int c = 0; c < C; ++c) leafc[(uint64_t)(cb >> 1) * C + c] = F13(ct, c);
                             write_mixed_leaf(nodes, cs, cb);

@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(256) k_boot_scan(TreeDesc* __restrict__ trees,
 
 __global__ void __launch_bounds__(256) k_boot_scatter(const uint32_t* __restrict__ counts8, uint64_t n_pad, uint32_t n_chunks,
                                                       const uint32_t* __restrict__ chunk_off, const uint8_t* __restrict__ y,
+                                                      const uint16_t* __restrict__ yq /* criterion 2: the 16-bit target rides where the class does */,
                                                       Entry* __restrict__ entA, uint64_t n_cap) {
     __shared__ uint32_t s_w[8];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(256) k_boot_scatter(const uint32_t* __restrict
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             uint32_t m = (ws[i] >> (8 * b)) & 0xFFu;
-            if (m) { uint32_t rw = row + i * 4 + b; out[pos++] = make_uint2(rw, m | ((uint32_t)y[rw] << 8)); }
+            if (m) { uint32_t rw = row + i * 4 + b; out[pos++] = make_uint2(rw, m | ((yq ? (uint32_t)yq[rw] : (uint32_t)y[rw]) << 8)); }
         }
 }
 
@@ -321,7 +322,7 @@ __global__ void k_init_roots(GrowCtx g, uint32_t n_trees) {
     else if (td.n_inbag <= SMALL_MAX) queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, k);
     else if (td.n_inbag <= g.sub_max && td.n_train <= 65535u) queue_push(g.qsub, g.qsub_count, g.qbig_cap, g.stats, k);  // tree per CTA
     else if (td.n_inbag > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, k);
-    else if (td.n_train <= 65535u || !g.mid_packed) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, k);
+    else if (td.n_train <= 65535u || !g.mid_packed || g.criterion == TST_REG) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, k);
     else queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, k);
 }
 
@@ -332,8 +333,20 @@ __global__ void k_init_roots(GrowCtx g, uint32_t n_trees) {
 struct InferPart { uint32_t fs, fsz, tree_lo, tree_hi; };
 
 template <bool ATOMIC>
-__device__ __forceinline__ void add_leaf_votes(uint2 rec, const uint32_t* __restrict__ leafc, int C, uint32_t* __restrict__ vrow) {
+__device__ __forceinline__ void add_leaf_votes(uint2 rec, const uint32_t* __restrict__ leafc, int C, uint32_t* __restrict__ vrow, bool reg) {
     uint32_t kind = rec.y >> 30;
+    if (reg) {
+        // criterion 2: the leaf mean in Q16.16, floor((S << 16) / N), added as two 16-bit halves -- vrow[0] collects the low
+        // halves, vrow[1] the high ones, so no carry ever crosses a word and rank / batch sums stay element-wise
+        unsigned long long N, S;
+        if (kind == KIND_PURE) { N = rec.x; S = N * (rec.y & 0xFFFFu); }
+        else { N = rec.y & 0x3FFFFFFFu; const uint32_t* lc = leafc + (uint64_t)rec.x * 2; S = (unsigned long long)lc[0] | ((unsigned long long)lc[1] << 32); }
+        if (N) {
+            const uint32_t v = (uint32_t)((S << 16) / N);
+            if (ATOMIC) { atomicAdd(&vrow[0], v & 0xFFFFu); atomicAdd(&vrow[1], v >> 16); } else { vrow[0] += v & 0xFFFFu; vrow[1] += v >> 16; }
+        }
+        return;
+    }
     if (kind == KIND_PURE) {
         if (rec.x) { if (ATOMIC) atomicAdd(&vrow[rec.y & 0xFFu], 65536u); else vrow[rec.y & 0xFFu] += 65536u; }
     } else {
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(256) k_oof_infer(GrowCtx g, const InferPart* _
                 rec = nodes[slot];
                 steps++;
             }
-            add_leaf_votes<ATOMIC>(rec, g.leafc + (uint64_t)arena * g.leafc_stride, g.C, vrow);
+            add_leaf_votes<ATOMIC>(rec, g.leafc + (uint64_t)arena * g.leafc_stride, g.C, vrow, g.criterion == TST_REG);
         }
     }
     // warp-aggregate the step counter
@@ -385,7 +398,7 @@ __global__ void __launch_bounds__(256) k_oof_infer(GrowCtx g, const InferPart* _
 __global__ void __launch_bounds__(256) k_predict(const uint8_t* __restrict__ rm, uint32_t dstride, int64_t n, int C,
                                                  const uint2* __restrict__ nodes_all, uint64_t node_stride,
                                                  const uint32_t* __restrict__ leafc_all, uint64_t leafc_stride,
-                                                 const uint32_t* __restrict__ arenas, uint32_t n_trees, uint32_t* __restrict__ votes) {
+                                                 const uint32_t* __restrict__ arenas, uint32_t n_trees, uint32_t* __restrict__ votes, bool reg) {
     int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     const uint8_t* __restrict__ rp = rm + row * dstride;
@@ -400,7 +413,7 @@ __global__ void __launch_bounds__(256) k_predict(const uint8_t* __restrict__ rm,
             slot = rp[f] <= b ? slot + 1u : rec.x;
             rec = nodes[slot];
         }
-        add_leaf_votes<false>(rec, leafc_all + (uint64_t)arena * leafc_stride, C, vrow);
+        add_leaf_votes<false>(rec, leafc_all + (uint64_t)arena * leafc_stride, C, vrow, reg);
     }
 }
 

@@ -40,7 +40,7 @@ def resolve_max_features(max_features, d: int) -> int:
     return max(1, min(d, int(max_features)))
 
 
-CRITERIA = {"gini": 0, "squared_error": 1}  # include/tst.h: TST_GINI, TST_SQUARED_ERROR
+CRITERIA = {"gini": 0, "squared_error_levels": 1, "squared_error": 2}  # include/tst.h: TST_GINI, TST_SQUARED_ERROR_LEVELS, TST_SQUARED_ERROR
 
 
 def make_params(d, max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features="sqrt",
@@ -174,6 +174,14 @@ class Engine:
                                  n_edges.ctypes.data_as(C.c_void_p), self._stream()))
         torch.cuda.current_stream(self.dev).synchronize()  # edges/X staging buffers may be released
         self.n, self.d, self.edges, self.n_edges = n, d, edges, n_edges
+        return self
+
+    def set_target(self, yq):
+        """Continuous target of criterion "squared_error": uint16 fixed point, one value per row of the binned table."""
+        torch = _torch()
+        t = self.to_dev(np.ascontiguousarray(yq, dtype=np.uint16).view(np.int16), torch.int16)
+        check(_lib.lib().tst_set_target(self._h, self._ptr(t), C.c_int64(t.numel()), self._stream()))
+        torch.cuda.current_stream(self.dev).synchronize()
         return self
 
     def set_bins(self, bins_cm):
@@ -382,11 +390,30 @@ def run_tst(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, max_depth=No
 
 # ------------------------------------------------------------------------------------------------- numeric answers
 # the squared-error criterion (SK/tree/_criterion.pyx:707-1000) for question types whose answer is a
-# number.  The target is uniformly quantised into <= 32 ordinal levels on the host; the kernels grow the same
-# histogram trees with S = sum_c c * count_c in place of the class-count squares, leaves keep level counts, and the
-# prediction is the vote-weighted mean level mapped back to the target's scale.
+# number.  criterion="squared_error": the target is mapped to 16-bit fixed point on the host; the kernels build (weight, sum y)
+# histograms with exact integer sums, leaves hold (N, sum y), every tree votes its leaf mean in Q16.16.
+# criterion="squared_error_levels" (round 1) histograms <= 32 ordinal levels like classes; kept for comparison.
+def quantise_target16(y):
+    """-> (yq uint16 [n], lo, span): yq = round((y - lo) / span * 65535); y ~ lo + yq / 65535 * span."""
+    y = np.asarray(y, dtype=np.float64)
+    if y.size == 0 or not np.all(np.isfinite(y)):
+        raise ValueError("numeric target must be non-empty and finite")
+    lo, hi = float(y.min()), float(y.max())
+    span = hi - lo if hi > lo else 1.0
+    return np.round((y - lo) / span * 65535.0).astype(np.uint16), lo, span
+
+
+def votes16_to_value(votes, n_trees: int, lo: float, span: float) -> np.ndarray:
+    """[n, 2] vote words (low / high 16-bit halves of the Q16.16 leaf means, summed over trees) -> mean prediction on the
+    target's scale; NaN for rows no tree voted on."""
+    v = np.asarray(votes).astype(np.float64)
+    tot = v[:, 1] * 65536.0 + v[:, 0]
+    out = lo + tot / (float(n_trees) * 65536.0) / 65535.0 * span
+    return np.where((v[:, 0] == 0) & (v[:, 1] == 0), np.nan, out)
+
+
 def quantise_target(y, n_levels: int = 32):
-    """-> (levels uint8 [n], lo, step): level = floor((y - lo) / step), step = (max - min) / n_levels."""
+    """(criterion "squared_error_levels") -> (levels uint8 [n], lo, step): level = floor((y - lo) / step), step = (max - min) / n_levels."""
     if not 2 <= n_levels <= 32:
         raise ValueError("n_levels must be in [2, 32]")
     y = np.asarray(y, dtype=np.float64)
@@ -399,7 +426,7 @@ def quantise_target(y, n_levels: int = 32):
 
 
 def votes_to_value(votes, lo: float, step: float) -> np.ndarray:
-    """Vote-weighted mean level -> target scale (level c stands for the centre of its interval); NaN without votes."""
+    """(criterion "squared_error_levels") vote-weighted mean level -> target scale; NaN without votes."""
     v = np.asarray(votes).astype(np.float64)
     tot = v.sum(axis=1)
     mean_level = np.divide(v @ np.arange(v.shape[1], dtype=np.float64), tot, out=np.full(v.shape[0], np.nan), where=tot > 0)
@@ -410,40 +437,50 @@ def votes_to_value(votes, lo: float, step: float) -> np.ndarray:
 class TsTRegressionResult:
     y_pred: np.ndarray          # [n] float64 out-of-fold blind prediction of the numeric answer (NaN if never held out)
     s: np.ndarray               # [n] float64 bias score 1 - |y_pred - y| / (max(y) - min(y)) in [0, 1]
-    oof_votes: np.ndarray       # [n, n_levels] uint32 Q0.16 vote sums
+    oof_votes: np.ndarray       # [n, 2] uint32 vote words (criterion "squared_error") or [n, n_levels] Q0.16 level votes
     fold_id: np.ndarray
-    levels: np.ndarray          # [n] uint8 quantised target
+    levels: np.ndarray          # [n] uint8 stratification levels of the fold assignment
     lo: float = 0.0
-    step: float = 1.0
+    step: float = 1.0           # span of the target ("squared_error") or width of one level ("squared_error_levels")
     stats: dict = field(default_factory=dict)
+    feature_importances: np.ndarray | None = None
 
 
-def run_tst_regression(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, n_levels: int = 32, max_depth=None,
-                       min_samples_split=2, min_samples_leaf=1, max_features=1.0, n_bins=256, group=None,
+def run_tst_regression(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, criterion: str = "squared_error", n_levels: int = 32,
+                       max_depth=None, min_samples_split=2, min_samples_leaf=1, max_features=1.0, n_bins=256, group=None,
                        engine: Engine | None = None, trees_in_flight=0) -> TsTRegressionResult:
-    """k-fold x n_trees diagnostic for numeric answers (max_features default 1.0 as in RandomForestRegressor)."""
+    """k-fold x n_trees diagnostic for numeric answers (max_features default 1.0 as in RandomForestRegressor).
+    Folds are stratified by `n_levels` coarse levels of the target."""
     torch = _torch()
     eng = engine or get_engine()
-    lev, lo, step = quantise_target(y, n_levels)
+    if criterion not in ("squared_error", "squared_error_levels"):
+        raise ValueError("criterion must be 'squared_error' or 'squared_error_levels'")
     eng.bin(X, n_bins=n_bins)
-    y_dev = eng.to_dev(lev, torch.uint8)
     g_dev, n_groups = None, 1
     if group is not None:
         gi = np.asarray(group, dtype=np.int32)
         n_groups = int(gi.max()) + 1
         g_dev = eng.to_dev(gi, torch.int32)
     active = torch.ones(eng.n, dtype=torch.uint8, device=eng.dev)
+    y64 = np.asarray(y, dtype=np.float64)
+    if criterion == "squared_error":
+        yq, lo, span = quantise_target16(y64)
+        lev = np.minimum((yq.astype(np.uint32) * n_levels) >> 16, n_levels - 1).astype(np.uint8)
+        eng.set_target(yq)
+        n_classes, step = 2, span
+    else:
+        lev, lo, step = quantise_target(y64, n_levels)
+        n_classes, span = n_levels, n_levels * step
+    y_dev = eng.to_dev(lev, torch.uint8)
     fold_dev = eng.assign_folds(y_dev, active, k, n_levels, g_dev, n_groups)  # folds stratified by level
-    prm = make_params(eng.d, max_depth, min_samples_split, min_samples_leaf, max_features, trees_in_flight,
-                      criterion="squared_error")
-    votes = eng.new_votes(n_levels)
+    prm = make_params(eng.d, max_depth, min_samples_split, min_samples_leaf, max_features, trees_in_flight, criterion=criterion)
+    votes = eng.new_votes(n_classes)
     eng.stats(reset=True)
-    eng.fit_oof(y_dev, fold_dev, k, n_trees, n_levels, prm, seed=seed, group_dev=g_dev, n_groups=n_groups, votes=votes)
+    eng.fit_oof(y_dev, fold_dev, k, n_trees, n_classes, prm, seed=seed, group_dev=g_dev, n_groups=n_groups, votes=votes)
     votes_h = eng.allreduce_votes(votes).cpu().numpy().view(np.uint32)
-    y_pred = votes_to_value(votes_h, lo, step)
-    span = n_levels * step
-    s = 1.0 - np.minimum(1.0, np.abs(y_pred - np.asarray(y, dtype=np.float64)) / span)
-    return TsTRegressionResult(y_pred, s, votes_h, fold_dev.cpu().numpy(), lev, lo, step, eng.stats())
+    y_pred = votes16_to_value(votes_h, n_trees, lo, span) if criterion == "squared_error" else votes_to_value(votes_h, lo, step)
+    s = 1.0 - np.minimum(1.0, np.abs(y_pred - y64) / span)
+    return TsTRegressionResult(y_pred, s, votes_h, fold_dev.cpu().numpy(), lev, lo, step, eng.stats(), eng.feature_importances())
 
 
 # ------------------------------------------------------------------------------------------------- IBP
@@ -513,20 +550,27 @@ class TsTForest:
         self.n_estimators, self.max_depth = n_estimators, max_depth
         self.min_samples_split, self.min_samples_leaf = min_samples_split, min_samples_leaf
         self.max_features, self.n_bins, self.random_state = max_features, n_bins, random_state
-        self.criterion, self.n_levels = criterion, n_levels  # "squared_error": y is numeric, predict() returns numbers
+        self.criterion, self.n_levels = criterion, n_levels  # "squared_error" / "squared_error_levels": y is numeric, predict() returns numbers
         self._engine = engine
 
     def fit(self, X, y):
         torch = _torch()
         # a kept forest lives in its engine: use a private one unless the caller shares one
         self._eng = self._engine or Engine(torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        yq = None
         if self.criterion == "squared_error":
+            yq, self._lo, self._step = quantise_target16(y)
+            yi = np.zeros(len(yq), dtype=np.uint8)  # labels only stratify folds; a plain fit has none
+            self.classes_ = np.arange(2)
+        elif self.criterion == "squared_error_levels":
             yi, self._lo, self._step = quantise_target(y, self.n_levels)
             self.classes_ = np.arange(self.n_levels)
         else:
             self.classes_, yi = encode_labels(y)
         self.n_classes_ = int(self.classes_.shape[0])
         self._eng.bin(X, n_bins=self.n_bins)
+        if yq is not None:
+            self._eng.set_target(yq)
         self.n_features_in_ = self._eng.d
         y_dev = self._eng.to_dev(yi, torch.uint8)
         fold = torch.full((self._eng.n,), FOLD_TRAIN_ONLY, dtype=torch.uint8, device=self._eng.dev)
@@ -545,6 +589,8 @@ class TsTForest:
 
     def predict(self, X):
         if self.criterion == "squared_error":
+            return votes16_to_value(self.predict_votes(X), self.n_estimators, self._lo, self._step)
+        if self.criterion == "squared_error_levels":
             return votes_to_value(self.predict_votes(X), self._lo, self._step)
         return self.classes_[np.argmax(self.predict_votes(X), axis=1)]
 

@@ -68,7 +68,7 @@ def spec_regression_vectors():
     edges, ne = H.find_edges(X)
     bins = H.bin_table(X, edges, ne)
     fold = H.assign_folds(lev, np.ones(len(lev), np.uint8), 3, 16)
-    prm = H.make_params(10, max_features=1.0, criterion="squared_error")
+    prm = H.make_params(10, max_features=1.0, criterion="squared_error_levels")
     votes, st, forest = H.fit_oof(bins, lev, fold, 3, 5, 16, prm, seed=21, keep=True, nthreads=1)
     t = forest.tree(1, 2)
     np.savez_compressed(os.path.join(HERE, "spec_regression.npz"), X=X, y=y, levels=lev, lo=lo, step=step, bins=bins, fold=fold,

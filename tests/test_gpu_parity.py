@@ -554,7 +554,7 @@ def test_squared_error_criterion_bit_exact(eng, n, d, L, k, mf, pk):
     lev, lo, step = quantise_target(y, L)
     edges, ne, bins = oracle_table(X)
     fold = H.assign_folds(lev, np.ones(n, np.uint8), k, L)
-    gv, ov, gst, ost, forest = run_both(eng, bins, lev, fold, k, 4, L, seed=3, keep=True, criterion="squared_error", max_features=mf, **pk)
+    gv, ov, gst, ost, forest = run_both(eng, bins, lev, fold, k, 4, L, seed=3, keep=True, criterion="squared_error_levels", max_features=mf, **pk)
     assert np.array_equal(gv, ov)
     check_stats(gst, ost)
     for part, t in ((0, 0), (k - 1, 3)):
@@ -572,7 +572,7 @@ def test_squared_error_dense_root_bit_exact(eng, request):
     lev, lo, step = quantise_target(y, 20)
     edges, ne, bins = oracle_table(X)
     fold = H.assign_folds(lev, np.ones(len(lev), np.uint8), 3, 20)
-    gv, ov, gst, ost, forest = run_both(eng, bins, lev, fold, 3, 4, 20, seed=1, keep=True, criterion="squared_error", max_features=6)
+    gv, ov, gst, ost, forest = run_both(eng, bins, lev, fold, 3, 4, 20, seed=1, keep=True, criterion="squared_error_levels", max_features=6)
     assert gst["launches_root"] > 0
     assert np.array_equal(gv, ov)
     check_stats(gst, ost)
@@ -587,19 +587,94 @@ def test_regression_golden_and_public_api(eng):
     import tst
 
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spec_regression.npz"))
-    gv, ov, gst, ost, forest = run_both(eng, g["bins"], g["levels"], g["fold"], 3, 5, 16, seed=21, keep=True, criterion="squared_error", max_features=1.0)
+    gv, ov, gst, ost, forest = run_both(eng, g["bins"], g["levels"], g["fold"], 3, 5, 16, seed=21, keep=True, criterion="squared_error_levels", max_features=1.0)
     assert np.array_equal(gv, g["votes"]) and np.array_equal(ov, g["votes"])
     gn, gc = eng.export_tree(1, 2, 16)
     compare_tree(gn, gc, g["tree_nodes"], g["tree_counts"], "golden regression tree")
     # host-to-host call
-    res = tst.run_tst_regression(g["X"], g["y"], k=3, n_trees=5, seed=21, n_levels=16, engine=eng)
+    res = tst.run_tst_regression(g["X"], g["y"], k=3, n_trees=5, seed=21, n_levels=16, engine=eng, criterion="squared_error_levels")
     assert np.array_equal(res.fold_id, g["fold"]) and np.array_equal(res.oof_votes, g["votes"]) and np.array_equal(res.levels, g["levels"])
     assert np.allclose(res.y_pred, tst.votes_to_value(g["votes"], float(g["lo"]), float(g["step"])))
     assert ((res.s >= 0) & (res.s <= 1)).all()
     # sklearn-like regressor: fully grown trees reproduce the training targets up to the quantisation step
-    reg = tst.TsTForest(n_estimators=20, criterion="squared_error", n_levels=32, max_features=1.0, random_state=2).fit(g["X"], g["y"])
+    reg = tst.TsTForest(n_estimators=20, criterion="squared_error_levels", n_levels=32, max_features=1.0, random_state=2).fit(g["X"], g["y"])
     err = np.abs(reg.predict(g["X"]) - g["y"])
     assert np.median(err) < 2.0 * (g["y"].max() - g["y"].min()) / 32
+
+
+# --------------------------------------------------------------------------------------------- continuous squared error (criterion 2)
+def run_both_reg(eng, bins, yq, lev, fold, k, T, seed=0, keep=False, **pk):
+    """criterion "squared_error" on GPU and oracle: votes [n, 2], stats, importances, forest."""
+    import tst
+
+    torch = _torch()
+    d = bins.shape[0]
+    eng.set_bins(bins)
+    eng.set_target(yq)
+    y_dev, fold_dev = eng.to_dev(lev, torch.uint8), eng.to_dev(fold, torch.uint8)
+    prm = tst.make_params(d, keep_forest=keep, criterion="squared_error", **pk)
+    votes = eng.new_votes(2)
+    eng.stats(reset=True)
+    eng.fit_oof(y_dev, fold_dev, k, T, 2, prm, seed=seed, votes=votes)
+    gst = eng.stats()
+    H.set_target(yq)
+    oimp = np.zeros(d + 1, np.uint64)
+    ov, ost, forest = H.fit_oof(bins, lev, fold, k, T, 2, H.make_params(d, criterion="squared_error", **pk), seed=seed, keep=keep, importances=oimp)
+    gimp, gcnt = eng.importance_sums()
+    assert gcnt == int(oimp[d]) and np.array_equal(gimp, oimp[:d]), "importance sums differ"
+    return votes.cpu().numpy().view(np.uint32), ov, gst, ost, forest
+
+
+@pytest.mark.parametrize("n,d,k,mf,ties,pk", [(3000, 10, 3, 1.0, False, {}), (5000, 32, 5, 1.0, False, {}), (700, 6, 4, None, True, {}),
+                                              (40000, 12, 2, 4, False, {}), (2500, 9, 3, 3, True, {}), (4000, 8, 2, "sqrt", False, dict(max_depth=6)),
+                                              (1500, 14, 3, 0.5, True, dict(min_samples_leaf=4, min_samples_split=10)), (3000, 70, 2, 12, False, {})])
+def test_continuous_squared_error_bit_exact(eng, n, d, k, mf, ties, pk):
+    """Numeric answers on a continuous target (16-bit fixed point): (weight, sum y) histograms in every tier -- CTA per node,
+    warp per node, warp per subtree, thread per subtree -- against the oracle: votes, counters, importances, whole trees.
+    `ties`: integer-valued targets (counts), so many multi-row nodes are constant and must become leaves unsearched."""
+    import tst
+    from tst import synth
+
+    X, y = synth.numeric_table(n, d, seed=n)
+    if ties:
+        y = np.round(y / y.max() * 9)
+    yq, lo, span = tst.quantise_target16(y)
+    lev = np.minimum((yq.astype(np.uint32) * 16) >> 16, 15).astype(np.uint8)
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(lev, np.ones(n, np.uint8), k, 16)
+    gv, ov, gst, ost, forest = run_both_reg(eng, bins, yq, lev, fold, k, 4, seed=3, keep=True, max_features=mf, **pk)
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    for part, t in ((0, 0), (k - 1, 3)):
+        gn, gc = eng.export_tree(part, t, 2)
+        ot = forest.tree(part, t)
+        compare_tree(gn, gc, ot.nodes, ot.counts, f"continuous regression tree({part},{t})")
+
+
+def test_continuous_squared_error_public_api(eng):
+    """run_tst_regression / TsTForest(criterion="squared_error") host to host; out-of-fold R^2 against the oracle's votes."""
+    import tst
+    from tst import synth
+
+    X, y = synth.numeric_table(3000, 16, seed=4)
+    res = tst.run_tst_regression(X, y, k=4, n_trees=30, seed=5, engine=eng)
+    yq, lo, span = tst.quantise_target16(y)
+    lev = np.minimum((yq.astype(np.uint32) * 32) >> 16, 31).astype(np.uint8)
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(lev, np.ones(len(y), np.uint8), 4, 32)
+    H.set_target(yq)
+    ov, _, _ = H.fit_oof(bins, lev, fold, 4, 30, 2, H.make_params(16, max_features=1.0, criterion="squared_error"), seed=5)
+    assert np.array_equal(res.fold_id, fold) and np.array_equal(res.oof_votes, ov)
+    assert np.allclose(res.y_pred, tst.votes16_to_value(ov, 30, lo, span))
+    r2 = 1.0 - ((res.y_pred - y) ** 2).sum() / ((y - y.mean()) ** 2).sum()
+    assert 0.3 < r2 < 0.9 and ((res.s >= 0) & (res.s <= 1)).all() and abs(res.feature_importances.sum() - 1.0) < 1e-9
+    # sklearn-like regressor: fully grown trees reproduce their training targets (bootstrap: ~63 % of the rows per tree)
+    reg = tst.TsTForest(n_estimators=25, criterion="squared_error", max_features=1.0, random_state=2).fit(X, y)
+    pred = reg.predict(X)
+    assert 1.0 - ((pred - y) ** 2).sum() / ((y - y.mean()) ** 2).sum() > 0.85
+    gn, gc = reg.export_tree(3)
+    S = gc[:, 0].astype(np.uint64) | (gc[:, 1].astype(np.uint64) << np.uint64(32))
+    assert S[0] == S[gn["left"][0]] + S[gn["right"][0]] and gn["n_weighted"][0] == 3000
 
 
 # --------------------------------------------------------------------------------------------- full size (BASELINE.json configs[4])
