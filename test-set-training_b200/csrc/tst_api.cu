@@ -1,6 +1,7 @@
 // tst_api.cu -- host side of libtst.so: the C ABI declared in include/tst.h.
 // One translation unit; kernels live in the .cuh files next to it.  sm_100a only, no CPU fallback.
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up in Nsight Systems / Compute timelines, no-ops without a tool attached
 
 #include <algorithm>
 #include <cctype>
@@ -31,6 +32,17 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
             return fail(TST_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
     } while (0)
 #define CKL() CK(cudaGetLastError())
+
+struct NvtxRange {  // one host-side range per phase of a fit (tracing)
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+struct NvtxPhase {  // consecutive phases inside one scope; closes the open one on every return path
+    bool open = false;
+    void next(const char* name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = true; }
+    ~NvtxPhase() { if (open) nvtxRangePop(); }
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -67,6 +79,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, tst_nccl_id, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
+    int (*CommGetAsyncError)(void*, int*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -80,6 +93,7 @@ static int load_nccl() {
     g_nccl.CommInitRank = (int (*)(void**, int, tst_nccl_id, int))dlsym(lib, "ncclCommInitRank");
     g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    g_nccl.CommGetAsyncError = (int (*)(void*, int*))dlsym(lib, "ncclCommGetAsyncError");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) return -1;
     g_nccl.lib = lib;
@@ -691,7 +705,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         fprintf(stderr, "[tst trace] setup %.3f ms: caller's queued work %.3f, kernel attributes %.3f, partitions %.3f, L2 window %.3f, buffers %.3f\n", ms_since(t_entry),
                 tr_wait, tr_attrs - tr_wait, tr_parts - tr_attrs, tr_l2 - tr_parts, ms_since(t_entry) - tr_l2);
     }
+    NvtxRange nvtx_fit("tst_fit_oof");
     for (size_t b0 = 0; b0 < total_trees; b0 += B) {
+        NvtxRange nvtx_batch("tst batch of trees");
         const auto t_batch = now();
         double tr_boot = 0, tr_levels = 0, tr_tail = 0;
         const uint32_t nb = (uint32_t)std::min(B, total_trees - b0);
@@ -702,6 +718,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         g.qtiny_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qtiny_per + qtiny_slack);
 
         // ---- bootstrap + compaction
+        NvtxPhase phase;
+        phase.next("tst bootstrap + roots");
         CK(cudaEventRecord(h->ev0, st));
         CK(cudaMemsetAsync(h->counts8.p, 0, (size_t)nb * n_pad, st));
         CK(cudaMemsetAsync(counters, 0, 256, st));
@@ -740,6 +758,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         CK(cudaStreamSynchronize(st));
         { float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->stats.ms_prep += ms; }
         tr_boot = ms_since(t_batch);
+        phase.next("tst level-synchronous growth");
 
         // ---- level-synchronous growth: CTA per node (> mid_max rows) and warp per node (33 .. mid_max rows).
         // One host round trip per level sizes the grids exactly.  Once a level is thin (the long tail of an unbalanced
@@ -811,6 +830,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             if (nbig > g.qbig_cap || nmid > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
         tr_levels = ms_since(t_batch);
+        phase.next("tst subtree tiers + inference");
         // ---- subtrees of 33 .. sub_max rows: one CTA each, rows cached in shared memory, every level of the subtree in one launch
         const uint32_t nsub = g.sub_max ? h->h_pinned[20] : 0u;
         if (nsub > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "subtree queue overflowed");
@@ -933,6 +953,11 @@ extern "C" int tst_allreduce_votes(tst_handle* h, uint32_t* votes_dev, int64_t n
     ENSURE(h->gather, (size_t)h->world * nv * 4);
     int rc = g_nccl.AllGather(votes_dev, h->gather.p, (size_t)nv, NCCL_UINT32, h->comm, st);
     if (rc) return fail(TST_ERR_CUDA, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    if (g_nccl.CommGetAsyncError) {  // a peer that died or a link error surfaces here instead of as a hang in the caller's next sync
+        int aerr = 0;
+        if (g_nccl.CommGetAsyncError(h->comm, &aerr) == 0 && aerr != 0)
+            return fail(TST_ERR_CUDA, std::string("ncclCommGetAsyncError: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(aerr) : "error"));
+    }
     k_reduce_votes<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(h->gather.as<uint32_t>(), h->world, nv, votes_dev);
     CKL();
     h->stats.kernel_launches++;

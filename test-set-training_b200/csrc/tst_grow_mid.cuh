@@ -264,11 +264,12 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         }
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < R; ++k)
+        for (int k = 0; k < R; ++k) {
             if (e[k].y) {
                 if (REG) atomicAdd((unsigned long long*)&s_hist[(b[k] >> 3) * 20u + (b[k] & 7u) * 2u], reg_cell(ent_w(e[k]), ent_cls(e[k])));
                 else atomicAdd(&s_hist[(b[k] >> 3) * 20u + (b[k] & 7u) * 2u + (ent_cls(e[k]) >> 1)], ent_w(e[k]) << (16u * (ent_cls(e[k]) & 1u)));
             }
+        }
         __syncwarp();
         // packed prefix scan over bins
         const uint4* hl = (const uint4*)(s_hist + lane * 20u);

@@ -111,6 +111,89 @@ def extract_features(records, max_options: int = 5, vocab_size: int = 16, numeri
     return X, y.astype(np.uint8), names, group, classes
 
 
+# ------------------------------------------------------------------------------------------------- benchmark record schemas
+# Adapters from the row layouts of the four benchmarks the paper diagnoses (REF/README.md:35) to the record dict above.  The
+# field names follow the public Hugging Face datasets named at REF/README.md:14-15 AS REMEMBERED -- the datasets are not
+# reachable offline, so every adapter only touches the fields listed in its docstring and raises a KeyError that names the
+# missing field; nothing visual (image / video paths) is ever read.
+_LETTERS = "ABCDEFGHIJ"
+_OPT_PREFIX = re.compile(r"^\s*\(?([A-Ja-j])[\).:]\s*")
+
+
+def _strip_option_prefix(o) -> str:
+    return _OPT_PREFIX.sub("", str(o)).strip()
+
+
+def _letter_index(ans) -> int | None:
+    a = str(ans).strip().strip("()").strip(".").upper()
+    return _LETTERS.index(a) if len(a) == 1 and a in _LETTERS else None
+
+
+def _need(row, *names):
+    for nm in names:
+        if nm not in row:
+            raise KeyError(f"record has no field {nm!r} (fields: {sorted(row)})")
+    return [row[nm] for nm in names]
+
+
+def from_vsibench(row) -> dict:
+    """VSI-Bench (nyu-visionx/VSI-Bench): question, question_type, options (list of 'A. ...' or None for numeric answers),
+    ground_truth (option letter, or a number for the numeric-answer types: object counting, distances, room size)."""
+    q, qt, gt = _need(row, "question", "question_type", "ground_truth")
+    opts = row.get("options")
+    if opts:
+        opts = [_strip_option_prefix(o) for o in opts]
+        idx = _letter_index(gt)
+        return dict(question=q, options=opts, answer=idx if idx is not None else str(gt), question_type=qt)
+    return dict(question=q, options=None, answer=float(gt), question_type=qt)
+
+
+def from_cvbench(row) -> dict:
+    """CV-Bench (nyu-visionx/CV-Bench): question, choices (list), answer ('(A)'), task (Count / Relation / Depth / Distance)."""
+    q, ch, ans, task = _need(row, "question", "choices", "answer", "task")
+    idx = _letter_index(ans)
+    return dict(question=q, options=[str(c) for c in ch], answer=idx if idx is not None else str(ans), question_type=str(task))
+
+
+def from_mmmu(row) -> dict:
+    """MMMU (MMMU/MMMU): question, options (a list or its string repr), answer (letter; free text for open questions),
+    question_type ('multiple-choice' / 'open'), subfield.  Open questions without a numeric answer are skipped (None)."""
+    import ast
+
+    q, opts, ans = _need(row, "question", "options", "answer")
+    if isinstance(opts, str):
+        opts = ast.literal_eval(opts) if opts.strip() else []
+    qt = str(row.get("subfield", row.get("question_type", "")))
+    if opts:
+        idx = _letter_index(ans)
+        return dict(question=q, options=[str(o) for o in opts], answer=idx if idx is not None else str(ans), question_type=qt)
+    try:
+        return dict(question=q, options=None, answer=float(str(ans).replace(",", "")), question_type=qt)
+    except ValueError:
+        return None
+
+
+def from_videomme(row) -> dict:
+    """Video-MME (lmms-lab/Video-MME): question, options (list of 'A. ...'), answer (letter), task_type, duration (short / medium /
+    long: a non-visual property of the item, kept in the question type)."""
+    q, opts, ans, task = _need(row, "question", "options", "answer", "task_type")
+    qt = f"{task}/{row['duration']}" if "duration" in row else str(task)
+    idx = _letter_index(ans)
+    return dict(question=q, options=[_strip_option_prefix(o) for o in opts], answer=idx if idx is not None else str(ans), question_type=qt)
+
+
+ADAPTERS = {"vsibench": from_vsibench, "cvbench": from_cvbench, "mmmu": from_mmmu, "videomme": from_videomme}
+
+
+def records_from(benchmark: str, rows) -> list:
+    """rows of one of the four benchmarks (dicts, e.g. a datasets.Dataset iterated) -> records for extract_features."""
+    try:
+        f = ADAPTERS[benchmark.lower().replace("-", "").replace("_", "")]
+    except KeyError:
+        raise ValueError(f"unknown benchmark {benchmark!r}; known: {sorted(ADAPTERS)}") from None
+    return [r for r in (f(row) for row in rows) if r is not None]
+
+
 # ------------------------------------------------------------------------------------------------- interpretability
 def gini_importances(nodes: np.ndarray, counts: np.ndarray, n_features: int) -> np.ndarray:
     """Mean decrease in impurity of one exported tree (SK/tree/_tree.pyx:1244-1280), on bootstrap-weighted counts."""

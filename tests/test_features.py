@@ -104,3 +104,35 @@ def test_path_contributions_telescope_to_the_leaf_probability():
         assert np.allclose(prior + contrib.sum(1), leaf, atol=1e-12)
         total += np.abs(contrib).sum(0)
     assert set(np.argsort(total)[-2:]) == {2, 5}
+
+
+def test_benchmark_record_adapters():
+    """Row layouts of the four benchmarks named at REF/README.md:14-15 -> records -> feature table."""
+    import pytest
+    from tst import extract_features, records_from
+
+    vsi = [dict(id=1, dataset="arkitscenes", scene_name="s1", question_type="object_rel_direction_easy",
+                question="If I am standing by the sofa and facing the TV, is the lamp to my left or right?", options=["A. left", "B. right"], ground_truth="B"),
+           dict(id=2, dataset="scannet", scene_name="s2", question_type="object_counting", question="How many chairs are in this room?", options=None, ground_truth="4"),
+           dict(id=3, dataset="scannet", scene_name="s2", question_type="room_size_estimation", question="What is the size of this room (in square meters)?", options=None, ground_truth=23.5)]
+    r = records_from("VSI-Bench", vsi)
+    assert r[0]["options"] == ["left", "right"] and r[0]["answer"] == 1 and r[1]["options"] is None and r[1]["answer"] == 4.0 and r[2]["answer"] == 23.5
+    cvb = [dict(idx=0, type="2D", task="Count", question="How many cups are in the image?", choices=["2", "3", "4", "5"], answer="(C)", source="ADE20K"),
+           dict(idx=1, type="3D", task="Depth", question="Which object is closer to the camera, the chair or the desk?", choices=["chair", "desk"], answer="(A)", source="Omni3D")]
+    r = records_from("cvbench", cvb)
+    assert r[0]["answer"] == 2 and r[0]["question_type"] == "Count" and r[1]["answer"] == 0
+    mmmu = [dict(id="validation_Math_1", question="What is the value of x in <image 1>?", options="['1', '2', '3', '4']", answer="D", question_type="multiple-choice", subfield="Algebra"),
+            dict(id="validation_Physics_2", question="Compute the force in newtons.", options="[]", answer="12.5", question_type="open", subfield="Mechanics"),
+            dict(id="validation_Art_3", question="Name the painter.", options="[]", answer="Monet", question_type="open", subfield="Art History")]
+    r = records_from("MMMU", mmmu)
+    assert len(r) == 2 and r[0]["answer"] == 3 and r[0]["question_type"] == "Algebra" and r[1]["answer"] == 12.5  # the free-text open question is skipped
+    vmme = [dict(video_id="001", duration="short", domain="Knowledge", sub_category="Humanity & History", question_id="001-1", task_type="Counting Problem",
+                 question="How many people appear in the video?", options=["A. 1.", "B. 2.", "C. 3.", "D. 4."], answer="C")]
+    r = records_from("Video-MME", vmme)
+    assert r[0]["answer"] == 2 and r[0]["options"][1] == "2." and r[0]["question_type"] == "Counting Problem/short"
+    X, y, names, group, classes = extract_features(records_from("vsibench", vsi) + records_from("cvbench", cvb) + records_from("videomme", vmme))
+    assert X.shape[0] == 6 and len(names) == X.shape[1] and group.max() >= 3
+    with pytest.raises(KeyError, match="ground_truth"):
+        records_from("vsibench", [dict(question="q", question_type="t")])
+    with pytest.raises(ValueError, match="unknown benchmark"):
+        records_from("imagenet", [])

@@ -393,16 +393,39 @@ def test_fewer_rows_than_folds(eng):
     check_stats(gst, ost)
 
 
-def test_grouped_forests_one_launch(eng):
-    """BASELINE.json configs[2]: per-question-type forests (MMMU-shaped: 30 groups x 30 rows)."""
+@pytest.mark.parametrize("kind,T", [("mmmu", 20), ("cvbench", 12), ("videomme", 10)])
+def test_grouped_forests_one_launch(eng, kind, T):
+    """BASELINE.json configs[2]: per-question-type forests, every group's k x T forests in the same launches --
+    MMMU-shaped (30 groups x 30 rows x 16), CV-Bench-shaped (4 x 660 x 16), VideoMME-shaped (12 x 225 x 24)."""
     from tst import synth
 
-    X, y, group, n_groups = synth.grouped_table("mmmu")
+    X, y, group, n_groups = synth.grouped_table(kind)
     edges, ne, bins = oracle_table(X)
     fold = H.assign_folds(y, np.ones(len(y), np.uint8), 5, 4, group, n_groups)
-    gv, ov, gst, ost, _ = run_both(eng, bins, y, fold, 5, 20, 4, seed=4, group=group, n_groups=n_groups)
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, 5, T, 4, seed=4, group=group, n_groups=n_groups, keep=True)
     assert np.array_equal(gv, ov)
     check_stats(gst, ost)
+    assert gst["trees"] == n_groups * 5 * T
+    part = (n_groups - 1) * 5 + 2  # (last group, fold 2)
+    gn, gc = eng.export_tree(part, T - 1, 4)
+    ot = forest.tree(part, T - 1)
+    compare_tree(gn, gc, ot.nodes, ot.counts, f"{kind} tree({part},{T - 1})")
+
+
+def test_grouped_public_api_matches_per_group_runs(eng):
+    """run_tst(group=...) == one run per question type: s(x) of a row only depends on its own group's forests."""
+    import tst
+    from tst import synth
+
+    X, y, group, n_groups = synth.grouped_table("cvbench")
+    res = tst.run_tst(X, y, k=5, n_trees=8, seed=2, group=group, engine=eng)
+    edges, ne, bins = oracle_table(X)
+    fold = H.assign_folds(y, np.ones(len(y), np.uint8), 5, 4, group, n_groups)
+    ov, _, _ = H.fit_oof(bins, y, fold, 5, 8, 4, H.make_params(16), seed=2, group=group, n_groups=n_groups)
+    os_, cor, tot = H.finalize(ov, y, fold, 5, 8, group, n_groups)
+    assert np.array_equal(res.fold_id, fold) and np.array_equal(res.oof_votes, ov)
+    assert np.array_equal(res.s.view(np.uint32), os_.view(np.uint32)) and res.fold_accuracy.shape == (n_groups * 5,)
+    assert np.allclose(res.fold_accuracy, cor / tot)
 
 
 def test_batching_does_not_change_results(eng, vsi_small):

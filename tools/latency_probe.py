@@ -1,19 +1,37 @@
+"""Latency of the benchmark-sized configurations (BASELINE.json configs 1-3) through the public API; knobs from the environment
+(TST_SUB_ROWS, TST_THIN_NODES, TST_BLIND_LEVELS, TST_TRACE ...).  python tools/latency_probe.py"""
 import os, sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/test-set-training_b200')
-import numpy as np, torch, tst
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "test-set-training_b200"))
+import numpy as np, torch
+import tst
 from tst import synth
-X, y = synth.vsi_table()
+
+
+def best_of(f, n=5):
+    f()
+    b = 1e9
+    for _ in range(n):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = f()
+        b = min(b, time.perf_counter() - t)
+    return b * 1e3, r
+
+
 eng = tst.Engine(0)
-tst.run_tst(X, y, k=5, n_trees=100, seed=0, engine=eng)
-best = 1e9
-for i in range(5):
-    torch.cuda.synchronize(); t = time.perf_counter()
-    r = tst.run_tst(X, y, k=5, n_trees=100, seed=1 + i, engine=eng)
-    best = min(best, time.perf_counter() - t)
-tst.ibp(X, y, rounds=2, k=5, n_trees=200, tau=0.5, batch=250, seed=0, want_s=False, engine=eng)
-bi = 1e9
-for i in range(3):
-    torch.cuda.synchronize(); t = time.perf_counter()
-    rb = tst.ibp(X, y, rounds=10, k=5, n_trees=200, tau=0.5, batch=250, seed=0, want_s=False, engine=eng)
-    bi = min(bi, time.perf_counter() - t)
-print(os.environ.get("TST_THIN_NODES"), os.environ.get("TST_BLIND_LEVELS"), "vsi ms %.2f ibp ms %.2f levels %d launches %d" % (best * 1e3, bi * 1e3, r.stats["levels"], r.stats["kernel_launches"]))
+X, y = synth.vsi_table()
+ms, r = best_of(lambda: tst.run_tst(X, y, k=5, n_trees=100, seed=1, engine=eng))
+print(f"vsi 5x100: {ms:.2f} ms, launches {r.stats['kernel_launches']}, levels {r.stats['levels']}, "
+      f"ms big {r.stats['ms_grow_big']:.2f} mid {r.stats['ms_grow_mid']:.2f} small {r.stats['ms_grow_small']:.2f} sub {r.stats['ms_grow_sub']:.2f} tiny {r.stats['ms_grow_tiny']:.2f} prep {r.stats['ms_prep']:.2f} infer {r.stats['ms_infer']:.2f}")
+# where the host time goes outside the fit
+torch.cuda.synchronize(); t = time.perf_counter(); eng.bin(X); torch.cuda.synchronize(); print(f"  bin (H2D + edges + map): {1e3 * (time.perf_counter() - t):.2f} ms")
+ms, r = best_of(lambda: tst.ibp(X, y, rounds=10, k=5, n_trees=200, tau=0.5, batch=250, seed=0, want_s=False, engine=eng), 3)
+print(f"  ibp 10 x 5 x 200: {ms:.2f} ms")
+for kind in ("cvbench", "mmmu", "videomme"):
+    Xg, yg, gg, ng = synth.grouped_table(kind)
+    ms, r = best_of(lambda: tst.run_tst(Xg, yg, k=5, n_trees=100, seed=1, group=gg, engine=eng))
+    print(f"  {kind}: {ms:.2f} ms, launches {r.stats['kernel_launches']}")
+if os.environ.get("TST_TRACE_ONE"):
+    eng.set_option("TRACE", 1)
+    tst.run_tst(X, y, k=5, n_trees=100, seed=1, engine=eng)
