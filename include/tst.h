@@ -195,7 +195,7 @@ int tst_export_tree(tst_handle* h, int32_t part, int32_t t, tst_node* nodes_host
 /* (f3) "interpretable auditing" (REF/README.md:35): feature importances (mean decrease in impurity) of the trees this rank
  * built in the LAST tst_fit_oof / tst_ibp round, accumulated on the device while the trees grew -- no kept forest needed, so
  * they exist for the out-of-fold forests too.  Replaces SK/tree/_tree.pyx:1244-1280 + SK/ensemble/_forest.py feature_importances_.
- * sums_host [d]: sum over those trees of floor(imp_t[f] * 2^32 / sum_f imp_t[f]) with imp_t in Q24 fixed point -- integers, so
+ * sums_host [d]: sum over those trees of floor((double)imp_t[f] / (double)sum_f imp_t[f] * 2^32) with imp_t in Q24 fixed point -- integers, so
  * the sums of several ranks / calls add up in any order; forest importance = sums[f] / sum_f sums[f].  *n_counted = trees
  * with at least one split.  raw_host (optional, [raw_cap_trees][d]): the per-tree Q24 impurity decreases, in the order the
  * trees were enumerated (part-major, then t). */

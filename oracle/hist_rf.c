@@ -499,7 +499,7 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
                 const int32_t* group, int32_t n_groups, int32_t k, int32_t n_trees, int32_t C,
                 const orc_params* prm, uint64_t seed, uint32_t gid_base, int32_t t0, int32_t t1,
                 int32_t rank, int32_t world, uint32_t* votes, orc_stats* stats, orc_forest** keep,
-                int32_t nthreads, uint64_t* imp_sums /* [d + 1] or NULL: sum over trees of floor(imp_t[f] * 2^32 / sum_f imp_t[f]); [d] = trees with a split */) {
+                int32_t nthreads, uint64_t* imp_sums /* [d + 1] or NULL: sum over trees of floor((double)imp_t[f] / (double)sum_f imp_t[f] * 2^32); [d] = trees with a split */) {
     if (n < 0 || n >= 0x7FFFFFF0LL || d < 1 || C < 1 || C > 256 || k < 1 || k > 250 || n_trees < 1 ||
         n_trees > 65535 || t0 < 0 || t1 > n_trees || t0 > t1 || world < 1 || rank < 0 || rank >= world ||
         prm->max_features < 1 || prm->max_features > d || prm->min_samples_leaf < 1 || prm->min_samples_split < 2 ||
@@ -570,11 +570,15 @@ int orc_fit_oof(const uint8_t* bins_cm, int64_t n, int32_t d, const uint8_t* y, 
             if (prm->criterion == 2) grow_tree_reg(bins_cm, n, d, g_target16, prm, k0, k1, gid, ent, tmp, ni, &S, &st, imp);
             else grow_tree(bins_cm, n, d, y, C, prm, k0, k1, gid, ent, tmp, ni, &S, &st, imp);
             st.trees++; st.inbag_rows += ni;
-            if (imp) {  /* per-tree normalisation in integers: the forest-level figure is a sum of these, in any order */
-                unsigned __int128 tsum = 0;
+            if (imp) {  /* per-tree normalisation, quantised to Q32: the forest-level figure is an integer sum of these, in any order */
+                uint64_t tsum = 0;
                 for (int32_t f2 = 0; f2 < d; ++f2) tsum += imp[f2];
                 if (tsum) {
-                    for (int32_t f2 = 0; f2 < d; ++f2) imp_loc[f2] += (uint64_t)((((unsigned __int128)imp[f2]) << 32) / tsum);
+                    for (int32_t f2 = 0; f2 < d; ++f2) {
+                        volatile double q = (double)imp[f2] / (double)tsum;  /* both < 2^53: exact conversions, one IEEE division */
+                        volatile double sc = q * 4294967296.0;
+                        imp_loc[f2] += (uint64_t)floor(sc);
+                    }
                     imp_loc[d]++;
                 }
             }

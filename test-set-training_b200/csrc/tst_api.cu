@@ -114,7 +114,7 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qmid0, qmid1, qsmall, qsub, qtiny, qtiny2, imp, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
+        qmid0, qmid1, qsmall, qsub, qtiny, qtiny2, imp, imp_sums, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
@@ -255,7 +255,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qsub, &h->imp, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qsub, &h->imp, &h->imp_sums, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk, &h->gather};
     for (DevBuf* b : bufs) b->release();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -1154,19 +1154,18 @@ extern "C" int tst_feature_importances(tst_handle* h, uint64_t* sums_host, int64
     for (int f = 0; f < d; ++f) sums_host[f] = 0;
     *n_counted = 0;
     if (T == 0) return TST_OK;
-    std::vector<uint64_t> raw((size_t)T * d);
-    CK(cudaMemcpy(raw.data(), h->imp.p, (size_t)T * d * 8, cudaMemcpyDeviceToHost));
-    for (int64_t t = 0; t < T; ++t) {
-        const uint64_t* r = raw.data() + (size_t)t * d;
-        unsigned __int128 tsum = 0;
-        for (int f = 0; f < d; ++f) tsum += r[f];
-        if (!tsum) continue;  // a one-leaf tree has no importances (SK/ensemble/_forest.py: node_count > 1)
-        for (int f = 0; f < d; ++f) sums_host[f] += (uint64_t)((((unsigned __int128)r[f]) << 32) / tsum);
-        ++*n_counted;
-    }
+    ENSURE(h->imp_sums, (size_t)(d + 1) * 8);
+    CK(cudaMemsetAsync(h->imp_sums.p, 0, (size_t)(d + 1) * 8, 0));
+    k_imp_reduce<<<(unsigned)((T + 127) / 128), 128>>>(h->imp.as<unsigned long long>(), T, d, h->imp_sums.as<unsigned long long>());
+    CKL();
+    h->stats.kernel_launches++;
+    std::vector<uint64_t> sums((size_t)d + 1);
+    CK(cudaMemcpy(sums.data(), h->imp_sums.p, (size_t)(d + 1) * 8, cudaMemcpyDeviceToHost));
+    memcpy(sums_host, sums.data(), (size_t)d * 8);
+    *n_counted = (int64_t)sums[d];
     if (raw_host) {
         if (raw_cap_trees < T) return fail(TST_ERR_INVALID, "tst_feature_importances: raw buffer holds fewer trees than the last fit built");
-        memcpy(raw_host, raw.data(), (size_t)T * d * 8);
+        CK(cudaMemcpy(raw_host, h->imp.p, (size_t)T * d * 8, cudaMemcpyDeviceToHost));
     }
     return TST_OK;
 }

@@ -417,6 +417,23 @@ __global__ void __launch_bounds__(256) k_predict(const uint8_t* __restrict__ rm,
     }
 }
 
+// Feature importances: per-tree normalisation and the forest-level integer sums (one thread per tree).
+// sums[f] += floor((double)imp_t[f] / (double)sum_f imp_t[f] * 2^32); sums[d] counts the trees with at least one split.
+__global__ void k_imp_reduce(const unsigned long long* __restrict__ imp, int64_t n_trees, int d, unsigned long long* __restrict__ sums) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    const unsigned long long* r = imp + t * d;
+    unsigned long long tsum = 0;
+    for (int f = 0; f < d; ++f) tsum += r[f];
+    if (!tsum) return;  // a one-leaf tree has no importances (SK/ensemble/_forest.py: node_count > 1)
+    const double ds = __ull2double_rn(tsum);
+    for (int f = 0; f < d; ++f) {
+        const unsigned long long v = r[f];
+        if (v) atomicAdd(&sums[f], __double2ull_rd(__dmul_rn(__ddiv_rn(__ull2double_rn(v), ds), 4294967296.0)));
+    }
+    atomicAdd(&sums[d], 1ull);
+}
+
 // K9 rank-ordered vote reduction (integers: the order cannot matter, it is fixed anyway).
 __global__ void k_reduce_votes(const uint32_t* __restrict__ gathered, int world, int64_t nv, uint32_t* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

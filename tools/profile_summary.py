@@ -41,7 +41,12 @@ def launches(src, dst):
 KEYS = ["Duration", "DRAM Throughput", "Memory Throughput", "L1/TEX Hit Rate", "L2 Hit Rate", "Executed Ipc Active", "Issue Slots Busy",
         "Registers Per Thread", "Theoretical Occupancy", "Achieved Occupancy", "Grid Size", "Block Size", "Dynamic Shared Memory Per Block"]
 RAW = ["dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed_op_shared_atom.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_atom.sum",
-       "lts__t_sectors_op_read.sum", "gpu__time_duration.sum", "smsp__inst_executed.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"]
+       "lts__t_sectors_op_read.sum", "gpu__time_duration.sum", "smsp__inst_executed.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+       # the LSU data pipe (wavefronts as a share of its peak rate) and its shared-memory parts; issue slots
+       "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+       "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed",
+       "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum.pct_of_peak_sustained_elapsed", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
+       "sm__inst_issued.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 
 
 def kernel(src, dst, traffic_json=None):
