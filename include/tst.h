@@ -130,6 +130,11 @@ int tst_bin(tst_handle* h, const float* X_dev, int64_t n, int32_t d, const doubl
  * edges_out_host [d][TST_MAX_EDGES] / n_edges_out_host [d] receive the chosen edges (may be NULL). */
 int tst_bin_auto(tst_handle* h, const float* X_dev, int64_t n, int32_t d, int32_t n_bins, double* edges_out_host,
                  int32_t* n_edges_out_host, void* stream);
+/* The bin edges of the current table (as chosen by tst_bin_auto or given to tst_bin): edges_out_host [d][TST_MAX_EDGES],
+ * n_edges_out_host [d].  Synchronises with the binning.  tst_bin_auto(..., NULL, NULL, stream) + this call later lets the host
+ * queue the fit while the table is still being copied and binned on another stream: tst_fit_oof waits for the binned table
+ * on the device, after its bootstrap kernels (which only need labels and folds). */
+int tst_get_edges(tst_handle* h, double* edges_out_host, int32_t* n_edges_out_host);
 /* Same, from an already binned column-major table [d][n] on the device (tests, pre-binned data). */
 int tst_set_bins(tst_handle* h, const uint8_t* bins_cm_dev, int64_t n, int32_t d, void* stream);
 /* Copy the column-major table out: out_dev [d][n]. */

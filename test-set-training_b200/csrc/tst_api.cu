@@ -132,6 +132,11 @@ struct tst_handle {
     cudaEvent_t ev_lvl[8][3] = {};  // per level of a group of blind levels: before big, between, after mid
     cudaEvent_t evi0 = nullptr, evi1 = nullptr;  // OOF inference
     cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // CTA-per-subtree tier
+    // The table may be binned on another stream than the one the fit runs on (the host overlaps the H2D copy + binning with the
+    // bootstrap of the first batch): every consumer of the binned table waits for this event on its own stream first.
+    cudaEvent_t ev_bins = nullptr;
+    cudaStream_t bins_stream = nullptr;
+    bool bins_recorded = false;
     size_t l2_carve_set = 0, l2_carve_saved = 0;
     bool l2_carve_touched = false;
     // tuning / diagnostic knobs, read from the environment once in tst_create
@@ -210,6 +215,7 @@ static int create_resources(tst_handle* h, int world, int rank, const void* nccl
     CK(cudaEventCreate(&h->ev2));
     CK(cudaEventCreate(&h->evm0)); CK(cudaEventCreate(&h->evm1)); CK(cudaEventCreate(&h->evs0)); CK(cudaEventCreate(&h->evs1));
     CK(cudaEventCreate(&h->evi0)); CK(cudaEventCreate(&h->evi1)); CK(cudaEventCreate(&h->evk0)); CK(cudaEventCreate(&h->evk1));
+    CK(cudaEventCreateWithFlags(&h->ev_bins, cudaEventDisableTiming));
     for (auto& lv : h->ev_lvl) for (auto& e : lv) CK(cudaEventCreate(&e));
     if (nccl_unique_id && world > 1) {
         if (load_nccl()) return fail(TST_ERR_UNSUPPORTED, "tst_create: libnccl.so.2 not found");
@@ -263,7 +269,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
-    for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1, h->evi0, h->evi1, h->evk0, h->evk1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {h->evm0, h->evm1, h->evs0, h->evs1, h->evi0, h->evi1, h->evk0, h->evk1, h->ev_bins}) if (e) cudaEventDestroy(e);
     // cudaLimitPersistingL2CacheSize is device-wide: hand it back the way the host application (torch) had it
     if (h->l2_carve_touched) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_carve_saved); cudaGetLastError(); }
     for (auto& lv : h->ev_lvl) for (auto& e : lv) if (e) cudaEventDestroy(e);
@@ -295,6 +301,16 @@ static int set_kernel_attrs(tst_handle* h) {
 }
 
 // --------------------------------------------------------------------------------------------- binning
+static int bins_done(tst_handle* h, cudaStream_t st) {  // the producer's last step
+    CK(cudaEventRecord(h->ev_bins, st));
+    h->bins_stream = st; h->bins_recorded = true;
+    return 0;
+}
+static int wait_bins(tst_handle* h, cudaStream_t st) {  // a consumer's first step (no-op on the producer's own stream)
+    if (h->bins_recorded && h->bins_stream != st) CK(cudaStreamWaitEvent(st, h->ev_bins, 0));
+    return 0;
+}
+
 static int alloc_table(tst_handle* h, int64_t n, int32_t d) {
     if (n < 1 || n >= TST_MAX_ROWS) return fail(TST_ERR_INVALID, "table: need 1 <= n < 2^31 - 16 rows");
     if (d < 1 || d > TST_MAX_FEATURES) return fail(TST_ERR_INVALID, "table: need 1 <= d <= 1024 features");
@@ -331,7 +347,7 @@ extern "C" int tst_bin(tst_handle* h, const float* X_dev, int64_t n, int32_t d, 
     CKL();
     h->stats.kernel_launches++;
     h->have_edges = true;
-    return TST_OK;
+    return bins_done(h, st);
 }
 
 extern "C" int tst_bin_auto(tst_handle* h, const float* X_dev, int64_t n, int32_t d, int32_t n_bins, double* edges_out_host,
@@ -366,9 +382,20 @@ extern "C" int tst_bin_auto(tst_handle* h, const float* X_dev, int64_t n, int32_
     CKL();
     h->stats.kernel_launches += 4;
     h->have_edges = true;
+    if (int rc2 = bins_done(h, st)) return rc2;
     if (edges_out_host) CK(cudaMemcpyAsync(edges_out_host, h->edges.p, (size_t)d * TST_MAX_EDGES * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (n_edges_out_host) CK(cudaMemcpyAsync(n_edges_out_host, h->n_edges.p, (size_t)d * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (edges_out_host || n_edges_out_host) CK(cudaStreamSynchronize(st));
+    return TST_OK;
+}
+
+extern "C" int tst_get_edges(tst_handle* h, double* edges_out_host, int32_t* n_edges_out_host) {
+    if (!h || !edges_out_host || !n_edges_out_host) return fail(TST_ERR_INVALID, "tst_get_edges: null argument");
+    if (!h->n || !h->have_edges) return fail(TST_ERR_STATE, "tst_get_edges: the table was not binned by tst_bin / tst_bin_auto");
+    CK(cudaSetDevice(h->device));
+    if (h->bins_recorded) CK(cudaEventSynchronize(h->ev_bins));
+    CK(cudaMemcpy(edges_out_host, h->edges.p, (size_t)h->d * TST_MAX_EDGES * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(n_edges_out_host, h->n_edges.p, (size_t)h->d * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return TST_OK;
 }
 
@@ -386,13 +413,14 @@ extern "C" int tst_set_bins(tst_handle* h, const uint8_t* bins_cm_dev, int64_t n
     CKL();
     h->stats.kernel_launches++;
     h->have_edges = false;
-    return TST_OK;
+    return bins_done(h, st);
 }
 
 extern "C" int tst_get_bins(tst_handle* h, uint8_t* out_dev, void* stream) {
     if (!h || !out_dev) return fail(TST_ERR_INVALID, "tst_get_bins: null argument");
     if (!h->n) return fail(TST_ERR_STATE, "tst_get_bins: no table");
     CK(cudaSetDevice(h->device));
+    if (int rcw = wait_bins(h, (cudaStream_t)stream)) return rcw;
     int64_t tot = h->n * h->d;
     k_copy_cm<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->bins_cm.as<uint8_t>(), h->n, h->d, h->ld, out_dev);
     CKL();
@@ -736,6 +764,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             k_boot_scatter<<<gridc, 256, 0, st>>>(h->counts8.as<uint32_t>(), n_pad, n_chunks, h->chunk_cnt.as<uint32_t>(), y_dev, reg ? h->target16.as<uint16_t>() : nullptr, g.entA, n_cap);
             CKL();
             g.rsplit = nullptr;
+            // everything above only needed labels and folds; from here on the kernels read the binned table
+            if ((rc = wait_bins(h, st))) return rc;
             if (root_dense) {
                 CK(cudaMemsetAsync(h->ghist.p, 0, (size_t)nb * g.m * g.FS * 4, st));
                 dim3 gr((unsigned)((n + ROOT_CHUNK - 1) / ROOT_CHUNK), nb);
@@ -1055,6 +1085,7 @@ extern "C" int tst_predict(tst_handle* h, const float* X_dev, int64_t n, uint32_
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int d = h->d;
+    if (int rcw = wait_bins(h, st)) return rcw;  // the edges come from the binning stream
     int64_t ld = (n + 15) / 16 * 16;
     ENSURE(h->pred_cm, (size_t)ld * d);
     ENSURE(h->pred_rm, (size_t)n * h->dstride);

@@ -117,7 +117,9 @@ class Engine:
         with torch.cuda.device(self.dev):
             check(_lib.lib().tst_create(C.byref(self._h), self.device, rank, world, uid))
         self.n = self.d = 0
-        self.edges = self.n_edges = None
+        self._edges = self._n_edges = None
+        self._edges_lazy = False
+        self._side = None  # side stream: H2D copy + binning of a host table overlap whatever the caller queues next
 
     def close(self):
         if self._h:
@@ -129,6 +131,24 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # ---- bin edges: fetched from the device on first use (the fit does not need them on the host)
+    def _fetch_edges(self):
+        if self._edges_lazy:
+            edges = np.zeros((self.d, binning.MAX_EDGES), np.float64)
+            n_edges = np.zeros(self.d, np.int32)
+            check(_lib.lib().tst_get_edges(self._h, edges.ctypes.data_as(C.c_void_p), n_edges.ctypes.data_as(C.c_void_p)))
+            self._edges, self._n_edges, self._edges_lazy = edges, n_edges, False
+
+    @property
+    def edges(self):
+        self._fetch_edges()
+        return self._edges
+
+    @property
+    def n_edges(self):
+        self._fetch_edges()
+        return self._n_edges
 
     def set_option(self, name: str, value: int):
         """Tuning / diagnostic knob of this handle (include/tst.h: tst_set_option)."""
@@ -156,15 +176,27 @@ class Engine:
         (tst_bin_auto: per-column radix sort + integer-rank quantiles); `edges=` / `host_edges=True` use the
         host rule of binning.py (bit-identical, kept as the cross-check)."""
         torch = _torch()
+        if edges is None and not host_edges:
+            # Host tables: the H2D copy and the binning kernels go to a side stream and the call returns at once; whatever the
+            # caller queues next that does not need the table (label upload, fold assignment, the bootstrap inside tst_fit_oof)
+            # overlaps them, and tst_fit_oof waits for the binned table on the device (include/tst.h: tst_get_edges).
+            on_host = not (isinstance(X, torch.Tensor) and X.is_cuda) and int(np.prod(X.shape)) >= (1 << 20)  # small tables: nothing to hide
+            cur = torch.cuda.current_stream(self.dev)
+            if on_host:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.dev)
+                self._side.wait_stream(cur)
+            st = self._side if on_host else cur
+            with torch.cuda.stream(st):
+                Xd = self.to_dev(X, torch.float32)
+                n, d = Xd.shape
+                check(_lib.lib().tst_bin_auto(self._h, self._ptr(Xd), C.c_int64(n), C.c_int32(d), C.c_int32(n_bins), None, None,
+                                              C.c_void_p(st.cuda_stream)))
+            Xd.record_stream(st)
+            self.n, self.d, self._edges, self._n_edges, self._edges_lazy = n, d, None, None, True
+            return self
         Xd = self.to_dev(X, torch.float32)
         n, d = Xd.shape
-        if edges is None and not host_edges:
-            edges = np.zeros((d, binning.MAX_EDGES), np.float64)
-            n_edges = np.zeros(d, np.int32)
-            check(_lib.lib().tst_bin_auto(self._h, self._ptr(Xd), C.c_int64(n), C.c_int32(d), C.c_int32(n_bins),
-                                          edges.ctypes.data_as(C.c_void_p), n_edges.ctypes.data_as(C.c_void_p), self._stream()))
-            self.n, self.d, self.edges, self.n_edges = n, d, edges, n_edges
-            return self
         if edges is None:
             Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
             edges, n_edges = binning.table_edges(Xh, n_bins)
@@ -173,7 +205,7 @@ class Engine:
         check(_lib.lib().tst_bin(self._h, self._ptr(Xd), C.c_int64(n), C.c_int32(d), edges.ctypes.data_as(C.c_void_p),
                                  n_edges.ctypes.data_as(C.c_void_p), self._stream()))
         torch.cuda.current_stream(self.dev).synchronize()  # edges/X staging buffers may be released
-        self.n, self.d, self.edges, self.n_edges = n, d, edges, n_edges
+        self.n, self.d, self._edges, self._n_edges, self._edges_lazy = n, d, edges, n_edges, False
         return self
 
     def set_target(self, yq):
@@ -190,7 +222,7 @@ class Engine:
         d, n = b.shape
         check(_lib.lib().tst_set_bins(self._h, self._ptr(b), C.c_int64(n), C.c_int32(d), self._stream()))
         torch.cuda.current_stream(self.dev).synchronize()
-        self.n, self.d, self.edges, self.n_edges = n, d, None, None
+        self.n, self.d, self._edges, self._n_edges, self._edges_lazy = n, d, None, None, False
         return self
 
     def get_bins(self) -> np.ndarray:
