@@ -305,6 +305,7 @@ def main():
     peak, peak_src = measured_hbm_peak()
     tiers = {}
     for name, vis, tms, nl in (("k_grow_big", st["row_visits_big"], st["ms_grow_big"], st["launches_grow_big"]),
+                               ("k_grow_wide", st["row_visits_wide"], st["ms_grow_wide"], st["launches_grow_wide"]),
                                ("k_grow_mid4", st["row_visits_mid"], st["ms_grow_mid"], st["launches_grow_mid"]),
                                ("k_grow_small4", st["row_visits_small"], st["ms_grow_small"], st["launches_grow_small"])):
         ab = (15 + m) * vis
@@ -318,9 +319,9 @@ def main():
                     traffic=traffic, traffic_launches=traffic_of, peak_source=peak_src,
                     algorithmic_bytes_per_launch=T_["algorithmic_bytes_per_launch"], avg_launch_ms=T_["avg_launch_ms"],
                     launches=T_["launches"], kernel_share_of_step=T_["share_of_step"], tiers=tiers,
-                    whole_tree=dict(algorithmic_bytes_per_tree=((15 + m) * (st["row_visits_big"] + st["row_visits_mid"] + st["row_visits_small"])
+                    whole_tree=dict(algorithmic_bytes_per_tree=((15 + m) * (st["row_visits_big"] + st["row_visits_wide"] + st["row_visits_mid"] + st["row_visits_small"])
                                                                 + st["inbag_rows"] + 9 * st["oof_steps"]) / max(1, trees_per_rank),
-                                    achieved=((15 + m) * (st["row_visits_big"] + st["row_visits_mid"] + st["row_visits_small"]) + st["inbag_rows"]
+                                    achieved=((15 + m) * (st["row_visits_big"] + st["row_visits_wide"] + st["row_visits_mid"] + st["row_visits_small"]) + st["inbag_rows"]
                                               + 9 * st["oof_steps"]) / (ms / 1e3) / 1e9,
                                     ms_infer=st["ms_infer"], ms_prep=st["ms_prep"], ms_tiny=st.get("ms_grow_tiny", 0.0)),
                     note="level kernels are bound by L2->SM gather latency / issue slots, not by DRAM: the binned table (64 MB) is L2-resident; see DESIGN.md section 4")
@@ -385,7 +386,7 @@ def main():
             # parity on the headline table itself: the GPU fit of the sample's trees against the oracle's votes and counters
             same_votes = bool(np.array_equal(gv_h, ovotes))
             same_stats = all(int(gst[k]) == int(ost[k]) for k in ("nodes", "leaves", "searched", "fallback", "inbag_rows", "trees", "oof_steps", "max_depth")) \
-                and int(gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"] + gst.get("row_visits_sub", 0)) == int(ost["row_visits"])
+                and int(gst["row_visits_big"] + gst["row_visits_wide"] + gst["row_visits_mid"] + gst["row_visits_small"] + gst["row_visits_sub"]) == int(ost["row_visits"])
             line["parity_1Mx64"] = same_votes and same_stats
             line["parity_1Mx64_detail"] = dict(trees=K_FOLDS * per_fold, votes_equal=same_votes, counters_equal=same_stats,
                                                nodes=int(ost["nodes"]), row_visits=int(ost["row_visits"]))

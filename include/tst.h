@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TST_ABI_VERSION 2
+#define TST_ABI_VERSION 3
 #define TST_MAX_EDGES 255        /* per feature; bins 0..254 + bin 255 for NaN */
 #define TST_MAX_CLASSES 32
 #define TST_MAX_FEATURES 1024
@@ -93,6 +93,9 @@ typedef struct {
     uint64_t row_visits_sub;    /* ... by the CTA-per-subtree kernel (k_grow_sub: rows cached in shared memory) */
     double ms_grow_sub;
     uint64_t launches_grow_sub;
+    uint64_t row_visits_wide;   /* ... by the four-warps-per-node kernel (k_grow_wide: 257 .. 2048-row nodes, warp-privatised histograms) */
+    double ms_grow_wide;
+    uint64_t launches_grow_wide;
 } tst_stats;
 
 /* Canonical tree export: nodes in breadth-first order, i.e. sorted by (depth, begin). */

@@ -18,6 +18,7 @@
 #include "tst_grow_mid.cuh"
 #include "tst_grow_tiny.cuh"
 #include "tst_grow_sub.cuh"
+#include "tst_grow_wide.cuh"
 #include "tst_root.cuh"
 #include "tst_prep.cuh"
 #include "tst_quantile.cuh"
@@ -114,7 +115,7 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qmid0, qmid1, qsmall, qsub, qtiny, qtiny2, imp, imp_sums, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
+        qmid0, qmid1, qwide0, qwide1, qsmall, qsub, qtiny, qtiny2, imp, imp_sums, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
@@ -129,7 +130,7 @@ struct tst_handle {
     void* comm = nullptr;  // ncclComm_t
     uint32_t* h_pinned = nullptr;  // 16 words
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
-    cudaEvent_t ev_lvl[8][3] = {};  // per level of a group of blind levels: before big, between, after mid
+    cudaEvent_t ev_lvl[8][4] = {};  // per level of a group of blind levels: before big, after big, after wide, after mid
     cudaEvent_t evi0 = nullptr, evi1 = nullptr;  // OOF inference
     cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // CTA-per-subtree tier
     // The table may be binned on another stream than the one the fit runs on (the host overlaps the H2D copy + binning with the
@@ -146,6 +147,7 @@ struct tst_handle {
         int tiny_max = -1, mid_max = -1, stash_max = -1;
         int blind_levels = 4;
         long thin_nodes = 2048;
+        int wide_max = -1;            // largest node of the four-warps-per-node tier (0 = tier off; default 2048)
         int sub_rows = -1;            // row capacity of the CTA-per-subtree tier (<= 0 = tier off, the default)
     } knobs;
     tst_stats stats;
@@ -195,6 +197,7 @@ static int set_option(tst_handle* h, const std::string& nm, long v) {
     else if (nm == "BLIND_LEVELS") kn.blind_levels = (int)std::max(1l, std::min(8l, v));
     else if (nm == "THIN_NODES") kn.thin_nodes = std::max(0l, v);
     else if (nm == "SUB_ROWS") kn.sub_rows = (int)v;
+    else if (nm == "WIDE_MAX") kn.wide_max = (int)v;
     else return -1;
     return 0;
 }
@@ -245,7 +248,7 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize; h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     // tuning / diagnostic knobs: defaults from the environment (TST_<NAME>), read once here; tst_set_option changes them later
     for (const char* nm : {"L2_PERSIST", "TRACE", "STASH", "BIG_PACKED", "ROOT_DENSE", "TINY_MAX", "MID_MAX", "STASH_MAX", "BLIND_LEVELS",
-                           "THIN_NODES", "SUB_ROWS"}) {
+                           "THIN_NODES", "SUB_ROWS", "WIDE_MAX"}) {
         const std::string env = std::string("TST_") + nm;
         if (const char* v = getenv(env.c_str())) set_option(h, nm, atol(v));
     }
@@ -261,7 +264,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qsmall, &h->qsub, &h->imp, &h->imp_sums, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qwide0, &h->qwide1, &h->qsmall, &h->qsub, &h->imp, &h->imp_sums, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk, &h->gather};
     for (DevBuf* b : bufs) b->release();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -292,6 +295,7 @@ static int set_kernel_attrs(tst_handle* h) {
     CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_sub<16, 2048, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sub_smem_bytes(16, 2048, 64)));
     CK(cudaFuncSetAttribute(k_grow_sub<8, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sub_smem_bytes(8, 1024, 64)));
+    CK(cudaFuncSetAttribute(k_grow_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(4, TST_MAX_FEATURES)));
     CK(cudaFuncSetAttribute(k_root_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_root_split, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_bin_map, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -493,7 +497,7 @@ static int pull_stats(tst_handle* h, cudaStream_t st) {
     CK(cudaMemcpyAsync(&ds, h->dstats.p, sizeof(ds), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     h->stats.row_visits_big += ds.row_visits_big; h->stats.row_visits_mid += ds.row_visits_mid; h->stats.row_visits_small += ds.row_visits_small;
-    h->stats.row_visits_sub += ds.row_visits_sub;
+    h->stats.row_visits_sub += ds.row_visits_sub; h->stats.row_visits_wide += ds.row_visits_wide;
 #ifdef SUB_PROFILE
     fprintf(stderr, "[sub profile] CTAs %llu: cycles/CTA load %.0f wide %.0f phase2 %.0f | per CTA summed over warps: narrow %.0f small %.0f idle %.0f\n", ds.prof[6],
             (double)ds.prof[0] / std::max(1ull, ds.prof[6]), (double)ds.prof[1] / std::max(1ull, ds.prof[6]), (double)ds.prof[2] / std::max(1ull, ds.prof[6]),
@@ -597,15 +601,16 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     // queue slots per tree.  With the thread-per-subtree tier on, qsmall only sees subtrees of >= 7 rows (<= n/7 of them); with it
     // off (many classes, squared error, d > 64) every 2..32-row subtree lands there: up to n/2 tasks for a tree that peels rows off.
     const uint64_t tiny_eff = (((C <= 4 && prm->criterion == TST_GINI) || reg) && d <= TINY_FY_MAX) ? (uint64_t)(kn.tiny_max >= 0 ? std::min(kn.tiny_max, TINY_MAX) : TINY_MAX) : 0;
+    const uint64_t qwide_per = n_cap / 256 + 2;  // disjoint segments of > 256 rows
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / std::max<uint64_t>(2, tiny_eff + 1) + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
     const bool want_stash = kn.stash;  // see use_stash below
-    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (5 * qbig_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (5 * qbig_per + 2 * qwide_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
-                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qsmall.cap + h->qsub.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
+                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qwide0.cap + h->qwide1.cap + h->qsmall.cap + h->qsub.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
     size_t budget = (size_t)((free_b + reclaim) * 0.6);
     if (keep) {
         size_t need = total_trees * arena_bytes;
@@ -629,6 +634,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->qmid1, B * qbig_per * sizeof(Task));
     ENSURE(h->qsmall, B * qsmall_per * sizeof(Task));
     ENSURE(h->qsub, B * qbig_per * sizeof(Task));
+    ENSURE(h->qwide0, B * qwide_per * sizeof(Task));
+    ENSURE(h->qwide1, B * qwide_per * sizeof(Task));
     // every warp of k_grow_small4 may leave up to TINY_RESERVE - 1 reserved slots unused
     const uint64_t qtiny_slack = (uint64_t)h->sm_count * 64u * SMALL_WARPS * TINY_RESERVE;
     ENSURE(h->qtiny, (B * qtiny_per + qtiny_slack) * 16);
@@ -712,7 +719,11 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.sub_max = (uint32_t)sub_rows;
     g.qsub = h->qsub.as<Task>(); g.qsub_count = counters + 20;
     if (sub_rows) g.mid_max = SMALL_MAX;
-    g.big_min = sub_rows ? (uint32_t)sub_rows : g.mid_max;
+    // four-warps-per-node tier (tst_grow_wide.cuh): the packed Gini nodes of mid_max + 1 .. 2048 rows that k_grow_big would take
+    g.wide_max = (packed_ok && !reg && !sub_rows && g.mid_max > SMALL_MAX) ? WIDE_MAXR : 0u;
+    if (kn.wide_max >= 0 && g.wide_max) g.wide_max = (uint32_t)std::min<int>(kn.wide_max, (int)WIDE_MAXR) > g.mid_max ? (uint32_t)std::min<int>(kn.wide_max, (int)WIDE_MAXR) : 0u;
+    const size_t wide_smem = wide_smem_bytes(4, d);
+    g.big_min = sub_rows ? (uint32_t)sub_rows : (g.wide_max ? g.wide_max : g.mid_max);
     const size_t sub_smem = sub_rows ? sub_smem_bytes(sub_rows == 2048 ? 16 : 8, sub_rows, h->dstride) : 0;
     // dense root histograms (tst_root.cuh): big tables only; needs m <= 8 and the histogram + 2 TMA stages in shared memory
     const size_t root_smem = (size_t)g.m * g.FS * 4 + 2 * (size_t)(g.m + 2) * ROOT_TILE;
@@ -742,6 +753,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         for (uint32_t i = 0; i < nb; ++i) { all[b0 + i].arena = keep ? (uint32_t)(b0 + i) : i; all[b0 + i].imp_row = (uint32_t)(b0 + i); }
         CK(cudaMemcpyAsync(h->trees.p, all.data() + b0, (size_t)nb * sizeof(TreeDesc), cudaMemcpyHostToDevice, st));
         g.qbig_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qbig_per);
+        g.qwide_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qwide_per);
         g.qsmall_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qsmall_per);
         g.qtiny_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFFFull, nb * qtiny_per + qtiny_slack);
 
@@ -779,6 +791,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             }
             g.qnext = h->qbig0.as<Task>(); g.qnext_count = counters + 0;
             g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 1;
+            g.qwide_next = h->qwide0.as<Task>(); g.qwide_next_count = counters + 8;
             k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb);
             CKL();
             h->stats.kernel_launches += 5;
@@ -799,13 +812,13 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         bool small_started = false, tiny_timed = false, sub_timed = false;
         const int blind_levels = kn.blind_levels;
         const uint64_t thin_nodes = (uint64_t)kn.thin_nodes;  // a level with at most this many nodes starts a group of blind levels
-        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1];
+        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1], nwide = h->h_pinned[8];
         double tr_gap = 0; int tr_groups = 0;
-        while (nbig > 0 || nmid > 0) {
+        while (nbig > 0 || nmid > 0 || nwide > 0) {
             const auto t_level = now();
-            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid <= thin_nodes;
+            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid + nwide <= thin_nodes;
             const int J = thin ? blind_levels : 1;
-            uint64_t ub_big = nbig, ub_mid = nmid;
+            uint64_t ub_big = nbig, ub_mid = nmid, ub_wide = nwide;
             for (int j = 0; j < J; ++j) {
                 Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
                 Task* qmcur = cur ? h->qmid1.as<Task>() : h->qmid0.as<Task>();
@@ -813,7 +826,13 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 g.qnext_count = counters + 2 * (cur ^ 1);
                 g.qmid_next = cur ? h->qmid0.as<Task>() : h->qmid1.as<Task>();
                 g.qmid_next_count = counters + 2 * (cur ^ 1) + 1;
+                Task* qwcur = cur ? h->qwide1.as<Task>() : h->qwide0.as<Task>();
+                g.qwide_next = cur ? h->qwide0.as<Task>() : h->qwide1.as<Task>();
+                g.qwide_next_count = counters + 8 + (cur ^ 1);
                 CK(cudaMemsetAsync(g.qnext_count, 0, 8, st));  // both counters of the next level
+                if (g.wide_max) CK(cudaMemsetAsync(g.qwide_next_count, 0, 4, st));
+                const uint32_t gw = g.wide_max ? (uint32_t)std::min<uint64_t>(ub_wide, g.qwide_cap) : 0u;
+                const uint32_t* cw = j ? counters + 8 + cur : nullptr;
                 const uint32_t gb = (uint32_t)std::min<uint64_t>(ub_big, g.qbig_cap);
                 const uint32_t gm = g.mid_max > SMALL_MAX ? (uint32_t)std::min<uint64_t>(ub_mid, g.qbig_cap) : 0u;  // tier off: its histogram does not fit
                 const uint32_t* cb = j ? counters + 2 * cur : nullptr;  // j == 0: counts are exact, no device read needed
@@ -827,6 +846,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                     h->stats.kernel_launches++; h->stats.launches_grow_big++;
                 }
                 CK(cudaEventRecord(h->ev_lvl[j][1], st));
+                if (gw) {
+                    k_grow_wide<4><<<gw, 128, wide_smem, st>>>(g, qwcur, gw, cw);
+                    CKL();
+                    h->stats.kernel_launches++; h->stats.launches_grow_wide++;
+                }
+                CK(cudaEventRecord(h->ev_lvl[j][3], st));
                 if (gm) {
                     if (reg) k_grow_mid4<MID_WARPS, MID_R, true><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
                     else if (mid_packed) k_grow_mid4<MID_WARPS, MID_R><<<(gm + MID_WARPS - 1) / MID_WARPS, MID_WARPS * 32, mid_smem, st>>>(g, qmcur, gm, cm);
@@ -839,25 +864,27 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 CK(cudaEventRecord(h->ev_lvl[j][2], st));
                 h->stats.levels++;
                 cur ^= 1;
-                const uint64_t nb2 = 2 * ub_big, nm2 = 2 * (ub_big + ub_mid);
-                ub_big = nb2; ub_mid = nm2;
+                const uint64_t nb2 = 2 * ub_big, nw2 = 2 * (ub_big + ub_wide), nm2 = 2 * (ub_big + ub_wide + ub_mid);
+                ub_big = nb2; ub_wide = nw2; ub_mid = nm2;
                 if (++level_guard > n_cap + 8) return fail(TST_ERR_STATE, "tree growth did not terminate");
             }
             CK(cudaMemcpyAsync(h->h_pinned, counters, 128, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             {   // every level is timed, also the ones launched blind (the top levels of a small batch of trees are "thin" too)
-                float ms_b = 0, ms_m = 0;
+                float ms_b = 0, ms_m = 0, ms_w = 0;
                 for (int j = 0; j < J; ++j) {
                     float ms = 0;
                     cudaEventElapsedTime(&ms, h->ev_lvl[j][0], h->ev_lvl[j][1]); ms_b += ms;
-                    cudaEventElapsedTime(&ms, h->ev_lvl[j][1], h->ev_lvl[j][2]); ms_m += ms;
+                    cudaEventElapsedTime(&ms, h->ev_lvl[j][1], h->ev_lvl[j][3]); ms_w += ms;
+                    cudaEventElapsedTime(&ms, h->ev_lvl[j][3], h->ev_lvl[j][2]); ms_m += ms;
                 }
-                h->stats.ms_grow_big += ms_b; h->stats.ms_grow_mid += ms_m;
-                if (trace) { tr_gap += ms_since(t_level) - ms_b - ms_m; ++tr_groups; }
+                h->stats.ms_grow_big += ms_b; h->stats.ms_grow_mid += ms_m; h->stats.ms_grow_wide += ms_w;
+                if (trace) { tr_gap += ms_since(t_level) - ms_b - ms_m - ms_w; ++tr_groups; }
             }
             nbig = h->h_pinned[2 * cur];
             nmid = h->h_pinned[2 * cur + 1];
-            if (nbig > g.qbig_cap || nmid > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
+            nwide = g.wide_max ? h->h_pinned[8 + cur] : 0u;
+            if (nbig > g.qbig_cap || nmid > g.qbig_cap || nwide > g.qwide_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
         tr_levels = ms_since(t_batch);
         phase.next("tst subtree tiers + inference");

@@ -119,7 +119,7 @@ struct TreeDesc {  // one tree of the batch in flight
 };
 
 struct DevStats {
-    unsigned long long row_visits_big, row_visits_mid, row_visits_small, nodes, leaves, searched, fallback, oof_steps, inbag_rows, row_visits_sub;
+    unsigned long long row_visits_big, row_visits_mid, row_visits_small, nodes, leaves, searched, fallback, oof_steps, inbag_rows, row_visits_sub, row_visits_wide;
     unsigned long long prof[8];  // -DSUB_PROFILE builds: clock cycles of k_grow_sub (load, wide, phase 2 per CTA; narrow, small, idle per warp)
     uint32_t max_depth;
     uint32_t error;  // sticky: 1 = multiplicity overflow, 2 = queue overflow, 3 = bootstrap weight mismatch
@@ -159,6 +159,10 @@ struct GrowCtx {
     uint32_t* qsub_count;
     uint32_t sub_max; // 0 disables the tier
     uint32_t big_min; // a tree root with more distinct rows than this is a "big root" (dense root kernels + k_grow_big)
+    Task* qwide_next; // four-warps-per-node queue for the next level (mid_max < rows <= wide_max, weight < 2^16): k_grow_wide
+    uint32_t* qwide_next_count;
+    uint32_t qwide_cap;
+    uint32_t wide_max; // 0 disables the tier
     uint32_t mid_max; // == SMALL_MAX disables the mid tier
     uint32_t mid_packed; // k_grow_mid4: 16-bit packed class counts, nodes must weigh <= 65535
     Task* qsmall;

@@ -1,0 +1,219 @@
+// tst_grow_wide.cuh -- four warps per node for nodes of 257 .. WIDE_MAXR distinct rows that weigh < 2^16 (<= 4 classes, Gini).
+//
+// These are the deep levels of the CTA-per-node kernel (levels 8-13 of a 1M-row tree: 85 of its 165 ms per 640 trees):
+// k_grow_big spends eight barriers, a 256-thread CTA and a shared row tile on a node of a few hundred rows, ~20 k
+// warp-instructions per node.  Here the node's entry list is cached in shared memory once (8 bytes per row) and every warp
+// owns its sampled features END TO END: its own packed 16-bit histogram (warp-privatised: no cross-warp atomics), the
+// gathers of that feature's bytes for all rows of the node (4 in flight per lane), the prefix scan and the fp32-estimate /
+// fp64-gain evaluation (scan_feature_packed4).  No barrier inside the search; one to combine the warps' best splits, two in
+// the partition (per-warp blocks, ballots parked in shared memory so the split feature is gathered once).  27 KB of shared
+// memory and 128 threads per node: the occupancy of k_grow_mid4 instead of k_grow_big's three CTAs per SM.
+// Same draws, candidates, gains and tie-breaks as every other tier; checked against oracle/hist_rf.c.
+#pragma once
+#include "tst_grow_mid.cuh"
+
+#define WIDE_MAXR 2048u
+#ifndef WIDE_MINB
+#define WIDE_MINB 5
+#endif
+#ifndef WIDE_U
+#define WIDE_U 4
+#endif
+
+#define WIDE_MAXCH 32u  // ballot words a warp may have to park: its block of the partition is <= WIDE_MAXR / WARPS rounded up to 32 rows
+__host__ __device__ __forceinline__ size_t wide_smem_bytes(int warps, int d) {
+    // histograms [warps][640] | entries [WIDE_MAXR] x 8 bytes | permutation (d 16-bit values) | parked ballots [warps][WIDE_MAXCH]
+    return 4u * ((size_t)warps * MID4_HIST + 2u * WIDE_MAXR + (size_t)((d + 1) / 2) + (size_t)warps * WIDE_MAXCH) + 16u;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
+    constexpr int THREADS = WARPS * 32;
+    constexpr uint32_t MAXCH = WIDE_MAXCH;
+    static_assert(WIDE_MAXR / WARPS / 32u + 1u <= WIDE_MAXCH, "parked ballots");
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    __shared__ double s_wgain[WARPS];
+    __shared__ uint32_t s_wpos[WARPS], s_wbin[WARPS], s_wP0[WARPS], s_wP1[WARPS], s_cnt[WARPS];
+    __shared__ uint32_t s_tot[4], s_bestL[4], s_T0, s_T1, s_fb;  // s_fb: fallback result (0 = none, else (pos + 1))
+    __shared__ double s_fbgain;
+    __shared__ uint32_t s_fbbin, s_fbP0, s_fbP1;
+
+    if (ntasks_dev) ntasks = min(ntasks, *ntasks_dev);
+    if (blockIdx.x >= ntasks) return;
+    const Task t = tasks[blockIdx.x];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const int C = g.C, d = g.d, m = g.m;
+    const TreeDesc td = g.trees[t.tree];
+    const Entry* __restrict__ ent_in = ((t.depth & 1u) ? g.entB : g.entA) + (uint64_t)t.tree * g.n_cap;
+    Entry* __restrict__ ent_out = ((t.depth & 1u) ? g.entA : g.entB) + (uint64_t)t.tree * g.n_cap;
+    uint2* nodes = g.nodes + (uint64_t)td.arena * g.node_stride;
+    uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
+    const uint8_t* __restrict__ bins = g.bins_rm;
+    const uint32_t dstride = g.dstride;
+    const uint32_t r = t.end - t.begin;
+
+    uint32_t* s_hist = s_mem + wid * MID4_HIST;
+    Entry* s_ent = (Entry*)(s_mem + WARPS * MID4_HIST);
+    uint16_t* s_perm = (uint16_t*)(s_ent + WIDE_MAXR);
+    uint32_t* s_bal = (uint32_t*)(s_perm + ((d + 1) / 2) * 2) + wid * MAXCH;
+
+    for (uint32_t i = tid; i < r; i += THREADS) s_ent[i] = ent_load(ent_in + t.begin + i);
+    if (wid == 0) {
+        for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
+        __syncwarp();
+        warp_draw_primary(s_perm, d, m, t.begin, t.depth, td.gid, g.k0, g.k1, lane);
+    }
+    if (tid == 0) s_fb = 0;
+    __syncthreads();
+
+    // One feature of the node, by one warp, into that warp's histogram: WIDE_U byte gathers per lane in flight.
+    // (Two features per pass over the entries -- 8 gathers in flight, two histograms per warp -- measured slower: 76 -> 85 ms.)
+    auto feature = [&](uint32_t f, double& bg, uint32_t& bb, uint32_t& P0, uint32_t& P1, uint32_t& X0, uint32_t& X1) {
+        {
+            uint4* hz = (uint4*)(s_hist + lane * 20u);
+            hz[0] = hz[1] = hz[2] = hz[3] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncwarp();
+        for (uint32_t i0 = 0; i0 < r; i0 += 32u * WIDE_U) {
+            Entry q[WIDE_U];
+            uint32_t b[WIDE_U];
+#pragma unroll
+            for (int u = 0; u < WIDE_U; ++u) {
+                const uint32_t i = i0 + 32u * u + lane;
+                q[u] = i < r ? s_ent[i] : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < WIDE_U; ++u) b[u] = q[u].y ? (uint32_t)bins[(uint64_t)q[u].x * dstride + f] : 0u;
+#pragma unroll
+            for (int u = 0; u < WIDE_U; ++u)
+                if (q[u].y) {
+                    const uint32_t cls = ent_cls(q[u]);
+                    atomicAdd(&s_hist[(b[u] >> 3) * 20u + (b[u] & 7u) * 2u + (cls >> 1)], ent_w(q[u]) << (16u * (cls & 1u)));
+                }
+        }
+        __syncwarp();
+        scan_feature_packed4(s_hist, g.msl, lane, bg, bb, P0, P1, X0, X1);
+        __syncwarp();
+    };
+
+    // ---- the first m positions of the draw: warp w takes positions w, w + WARPS, ...
+    double best_gain = -1.0;
+    uint32_t best_pos = 0xFFFFFFFFu, best_bin = 0, bestP0 = 0, bestP1 = 0, T0 = 0, T1 = 0;
+    for (int j = (int)wid; j < m; j += WARPS) {
+        double bg; uint32_t bb, P0 = 0, P1 = 0, X0, X1;
+        feature(s_perm[j], bg, bb, P0, P1, X0, X1);
+        T0 = X0; T1 = X1;
+        if (bb != 0xFFFFFFFFu && bg > best_gain) { best_gain = bg; best_pos = (uint32_t)j; best_bin = bb; bestP0 = P0; bestP1 = P1; }  // earlier position keeps a tie
+    }
+    if (lane == 0) {
+        s_wgain[wid] = best_gain; s_wpos[wid] = best_pos; s_wbin[wid] = best_bin; s_wP0[wid] = bestP0; s_wP1[wid] = bestP1;
+        if (wid == 0) { s_T0 = T0; s_T1 = T1; }  // m >= 1: warp 0 always scanned position 0
+    }
+    __syncthreads();
+    T0 = s_T0; T1 = s_T1;
+    const uint32_t t0 = T0 & 0xFFFFu, t1 = T0 >> 16, t2 = T1 & 0xFFFFu, t3 = T1 >> 16, N = t0 + t1 + t2 + t3;
+    const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
+    const bool stop = stop_rule(g, N, t.depth, pure);  // only a tree root can arrive unchecked
+    bool found = false;
+    best_gain = -1.0; best_pos = 0xFFFFFFFFu;
+    if (!stop) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {  // max gain; ties -> the feature drawn first (lowest position), then its lowest bin
+            const uint32_t p = s_wpos[w];
+            if (p != 0xFFFFFFFFu && (s_wgain[w] > best_gain || (s_wgain[w] == best_gain && p < best_pos))) {
+                best_gain = s_wgain[w]; best_pos = p; best_bin = s_wbin[w]; bestP0 = s_wP0[w]; bestP1 = s_wP1[w]; found = true;
+            }
+        }
+        if (!found) {
+            // fallback (rare): no valid split among the first m features -- warp 0 continues the draw one position at a time
+            if (wid == 0) {
+                uint4 rnd = make_uint4(0, 0, 0, 0);
+                for (int i = m; i < d; ++i) {
+                    if (lane == 0) {
+                        if (i == m || (i & 3) == 0)
+                            rnd = philox4x32_10(t.begin, t.depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);
+                        const int j = i + (int)mulhi32(pick4(rnd, i & 3), (uint32_t)(d - i));
+                        const uint16_t fj = s_perm[j];
+                        s_perm[j] = s_perm[i];
+                        s_perm[i] = fj;
+                        if (i == m) atomicAdd(&g.stats->fallback, 1ull);
+                    }
+                    __syncwarp();
+                    double bg; uint32_t bb, P0 = 0, P1 = 0, X0, X1;
+                    feature(s_perm[i], bg, bb, P0, P1, X0, X1);
+                    if (bb != 0xFFFFFFFFu) {
+                        if (lane == 0) { s_fb = (uint32_t)i + 1u; s_fbgain = bg; s_fbbin = bb; s_fbP0 = P0; s_fbP1 = P1; }
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_fb) { found = true; best_gain = s_fbgain; best_pos = s_fb - 1u; best_bin = s_fbbin; bestP0 = s_fbP0; bestP1 = s_fbP1; }
+        }
+    }
+    if (tid == 0) {
+        s_tot[0] = t0; s_tot[1] = t1; s_tot[2] = t2; s_tot[3] = t3;
+        s_bestL[0] = bestP0 & 0xFFFFu; s_bestL[1] = bestP0 >> 16; s_bestL[2] = bestP1 & 0xFFFFu; s_bestL[3] = bestP1 >> 16;
+    }
+    if (stop || !found) {
+        if (tid == 0) {
+            int pc = -1;
+            for (int c = 0; c < C; ++c) if (s_tot[c] == N) pc = c;
+            if (pc >= 0) write_pure_leaf(nodes, t.slot, N, (uint32_t)pc);
+            else {
+                for (int c = 0; c < C; ++c) leafc[(uint64_t)(t.begin >> 1) * C + c] = s_tot[c];
+                write_mixed_leaf(nodes, t.slot, t.begin);
+            }
+            atomicAdd(&g.stats->nodes, 1ull);
+            atomicAdd(&g.stats->leaves, 1ull);
+            if (!stop) { atomicAdd(&g.stats->searched, 1ull); atomicAdd(&g.stats->row_visits_wide, (unsigned long long)r); }
+            atomicMax(&g.stats->max_depth, t.depth);
+        }
+        return;
+    }
+
+    // ---- stable partition: every warp owns a contiguous block; the split feature is gathered once, the ballots wait in shared memory
+    const uint32_t bf = s_perm[best_pos], bbin = best_bin;
+    const uint32_t rpw = ((r + THREADS - 1u) / THREADS) * 32u;
+    const uint32_t blo = min(r, wid * rpw), bhi = min(r, blo + rpw);
+    {
+        uint32_t c = 0, k = 0;
+        for (uint32_t i0 = blo; i0 < bhi; i0 += 32u, ++k) {
+            const uint32_t i = i0 + lane;
+            const bool l = i < bhi && bins[(uint64_t)s_ent[min(i, r - 1u)].x * dstride + bf] <= bbin;
+            const uint32_t bal = __ballot_sync(0xffffffffu, l);
+            if (lane == 0) s_bal[k] = bal;
+            c += __popc(bal);
+        }
+        if (lane == 0) s_cnt[wid] = c;
+    }
+    __syncthreads();
+    uint32_t lbase = 0, nL = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { const uint32_t c = s_cnt[w]; if (w < (int)wid) lbase += c; nL += c; }
+    if (nL == 0 || nL == r) {  // cannot happen for a valid split; never loop on it
+        if (tid == 0) g.stats->error = 4;
+        return;
+    }
+    {
+        uint32_t rbase = blo - lbase, k = 0;
+        for (uint32_t i0 = blo; i0 < bhi; i0 += 32u, ++k) {
+            const uint32_t i = i0 + lane;
+            const bool v = i < bhi;
+            const uint32_t balL = s_bal[k], balR = ~balL & __ballot_sync(0xffffffffu, v);
+            const bool l = (balL >> lane) & 1u;
+            if (v) {
+                const Entry e = s_ent[i];
+                if (l) ent_store(ent_out + t.begin + lbase + __popc(balL & lanemask_lt()), e);
+                else ent_store(ent_out + t.begin + nL + rbase + __popc(balR & lanemask_lt()), e);
+            }
+            lbase += __popc(balL);
+            rbase += __popc(balR);
+        }
+    }
+    __syncthreads();  // s_tot / s_bestL written by thread 0 above are read by it again: keep the CTA together until here
+    if (tid == 0) {
+        emit_split(g, t, nodes, leafc, s_tot, s_bestL, N, nL, bf, bbin, best_gain);
+        atomicAdd(&g.stats->row_visits_wide, (unsigned long long)r);
+    }
+}

@@ -42,7 +42,8 @@ class Stats(C.Structure):
                 ("pad", C.c_uint32), ("ms_grow_big", C.c_double), ("ms_grow_small", C.c_double),
                 ("ms_prep", C.c_double), ("ms_infer", C.c_double), ("launches_grow_big", C.c_uint64),
                 ("launches_grow_small", C.c_uint64), ("ms_grow_mid", C.c_double), ("launches_grow_mid", C.c_uint64), ("row_visits_mid", C.c_uint64), ("ms_grow_tiny", C.c_double), ("launches_grow_tiny", C.c_uint64), ("launches_root", C.c_uint64),
-                ("row_visits_sub", C.c_uint64), ("ms_grow_sub", C.c_double), ("launches_grow_sub", C.c_uint64)]
+                ("row_visits_sub", C.c_uint64), ("ms_grow_sub", C.c_double), ("launches_grow_sub", C.c_uint64),
+                ("row_visits_wide", C.c_uint64), ("ms_grow_wide", C.c_double), ("launches_grow_wide", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad"}

@@ -64,7 +64,7 @@ def run_both(eng, bins, y, fold, k, T, C, seed=0, keep=False, group=None, n_grou
 
 
 def check_stats(gst, ost):
-    assert gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"] + gst["row_visits_sub"] == ost["row_visits"]
+    assert gst["row_visits_big"] + gst["row_visits_mid"] + gst["row_visits_small"] + gst["row_visits_sub"] + gst["row_visits_wide"] == ost["row_visits"]
     for key in ("nodes", "leaves", "searched", "fallback", "inbag_rows", "trees", "oof_steps", "max_depth"):
         assert gst[key] == ost[key], f"stat {key}: gpu {gst[key]} oracle {ost[key]}"
 
@@ -254,7 +254,8 @@ def test_random_configurations_bit_exact(eng, seed):
 def test_dense_root_kernels_bit_exact(eng, request, n, d, C, k):
     """k_root_hist / k_root_split (TMA-streamed column-major histogram of the root) forced on small tables."""
     eng.set_option("ROOT_DENSE", 2)
-    request.addfinalizer(lambda: eng.set_option("ROOT_DENSE", -1))
+    eng.set_option("WIDE_MAX", 0)  # roots of <= 2048 rows would go to the four-warps-per-node tier instead of dense root + k_grow_big
+    request.addfinalizer(lambda: (eng.set_option("ROOT_DENSE", -1), eng.set_option("WIDE_MAX", -1)))
     rng = np.random.default_rng(n)
     bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
     y = ((bins[1].astype(int) * C) // 256).astype(np.uint8)
@@ -313,8 +314,8 @@ def test_wide_tables_bit_exact(eng, d, C, mf):
 def test_two_class_packed_cta_tier_bit_exact(eng, request, n, d, mf):
     """Binary labels, 256-valued bins, non-root nodes of > 256 rows that weigh < 2^16: k_grow_big's packed 16-bit
     histogram (640 words per feature) is larger than the unpacked 2-class layout (544) -- the region must hold it."""
-    eng.set_option("SUB_ROWS", 0)  # keep the 257 .. 2048-row nodes on k_grow_big
-    request.addfinalizer(lambda: eng.set_option("SUB_ROWS", -1))
+    eng.set_option("WIDE_MAX", 0)  # keep the 257 .. 2048-row nodes on k_grow_big
+    request.addfinalizer(lambda: eng.set_option("WIDE_MAX", -1))
     rng = np.random.default_rng(n + d)
     bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
     y = ((bins[0].astype(int) + bins[d - 1].astype(int)) > 255).astype(np.uint8)

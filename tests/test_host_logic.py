@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     L.tst_abi_version.restype = ctypes.c_int
-    assert L.tst_abi_version() == 2
+    assert L.tst_abi_version() == 3
 
 
 def test_ctypes_structs_match_the_header(tmp_path):
