@@ -601,7 +601,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     // queue slots per tree.  With the thread-per-subtree tier on, qsmall only sees subtrees of >= 7 rows (<= n/7 of them); with it
     // off (many classes, squared error, d > 64) every 2..32-row subtree lands there: up to n/2 tasks for a tree that peels rows off.
     const uint64_t tiny_eff = (((C <= 4 && prm->criterion == TST_GINI) || reg) && d <= TINY_FY_MAX) ? (uint64_t)(kn.tiny_max >= 0 ? std::min(kn.tiny_max, TINY_MAX) : TINY_MAX) : 0;
-    const uint64_t qwide_per = n_cap / 256 + 2;  // disjoint segments of > 256 rows
+    const uint64_t wide_lo = (uint64_t)std::max(32, kn.mid_max >= 0 ? std::min(kn.mid_max, 32 * MID_R) : 32 * MID_R);
+    const uint64_t qwide_per = n_cap / (wide_lo + 1) + 2;  // disjoint segments of more rows than the warp-per-node tier takes
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / std::max<uint64_t>(2, tiny_eff + 1) + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
     const bool want_stash = kn.stash;  // see use_stash below

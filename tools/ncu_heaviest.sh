@@ -1,8 +1,7 @@
 #!/bin/bash
 # ncu --set full of the HEAVIEST launches of one kernel in the timed step of the headline bench.
 #   tools/ncu_heaviest.sh <kernel regex> <output name> [launches to capture]
-# Pass 1 lists every launch of the kernel with its duration, pass 2 captures the 3 (default) launches starting at the longest one
-# of the last step.  Run under gpurun; the bench command must have exited 0 without ncu before (done here first).
+# Pass 1 lists every launch of the kernel with its duration, pass 2 captures the 3 (default) launches around the longest one.  Run under gpurun; the bench command must have exited 0 without ncu before (done here first).
 K=$1; OUT=$2; N=${3:-3}
 CMD="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-secondary --no-job"
 $CMD > gpurun_out/${OUT}_plain.log 2>&1 || exit 1
@@ -11,9 +10,8 @@ IDX=$(python - <<PY
 import csv
 rows=[r for r in csv.DictReader(l for l in open("gpurun_out/${OUT}_list.csv") if not l.startswith("=="))]
 v=[float(r["Metric Value"].replace(",","")) for r in rows]
-n=len(v); lo=3*n//4            # the timed step is the last quarter (3 warm-up steps + 1)
-i=max(range(lo,n), key=lambda k:v[k])
-print(max(lo, i-1))
+i=max(range(len(v)), key=lambda k:v[k])   # every step does the same work: the longest launch of any of them
+print(max(0, i-1))
 PY
 )
 echo "capturing $N launches of $K from launch $IDX"
