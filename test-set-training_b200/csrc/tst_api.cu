@@ -695,7 +695,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint32_t small_per_warp = small_packed ? ((64u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
-    uint32_t* counters = h->counters.as<uint32_t>();  // [2p], [2p+1] big / mid queue counts of parity p, [4] small, [5] tiny, [6+r] tiny histogram
+    // [2p], [2p+1] big / mid queue counts of parity p, [4] small, [5] tiny, [6 + r] tiny size histogram (r <= 6), [16 + p] four-warps-per-node
+    // queue of parity p, [20] subtree queue, [32 + r] tiny cursors
+    uint32_t* counters = h->counters.as<uint32_t>();
     g.qsmall_count = counters + 4;
     g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
     g.tiny_max = (packed_ok && d <= TINY_FY_MAX && B <= 65535) ? TINY_MAX : 0;  // packed 4-class thread-per-subtree tier
@@ -792,7 +794,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             }
             g.qnext = h->qbig0.as<Task>(); g.qnext_count = counters + 0;
             g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 1;
-            g.qwide_next = h->qwide0.as<Task>(); g.qwide_next_count = counters + 8;
+            g.qwide_next = h->qwide0.as<Task>(); g.qwide_next_count = counters + 16;
             k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb);
             CKL();
             h->stats.kernel_launches += 5;
@@ -813,7 +815,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         bool small_started = false, tiny_timed = false, sub_timed = false;
         const int blind_levels = kn.blind_levels;
         const uint64_t thin_nodes = (uint64_t)kn.thin_nodes;  // a level with at most this many nodes starts a group of blind levels
-        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1], nwide = h->h_pinned[8];
+        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1], nwide = h->h_pinned[16];
         double tr_gap = 0; int tr_groups = 0;
         while (nbig > 0 || nmid > 0 || nwide > 0) {
             const auto t_level = now();
@@ -829,11 +831,11 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 g.qmid_next_count = counters + 2 * (cur ^ 1) + 1;
                 Task* qwcur = cur ? h->qwide1.as<Task>() : h->qwide0.as<Task>();
                 g.qwide_next = cur ? h->qwide0.as<Task>() : h->qwide1.as<Task>();
-                g.qwide_next_count = counters + 8 + (cur ^ 1);
+                g.qwide_next_count = counters + 16 + (cur ^ 1);
                 CK(cudaMemsetAsync(g.qnext_count, 0, 8, st));  // both counters of the next level
                 if (g.wide_max) CK(cudaMemsetAsync(g.qwide_next_count, 0, 4, st));
                 const uint32_t gw = g.wide_max ? (uint32_t)std::min<uint64_t>(ub_wide, g.qwide_cap) : 0u;
-                const uint32_t* cw = j ? counters + 8 + cur : nullptr;
+                const uint32_t* cw = j ? counters + 16 + cur : nullptr;
                 const uint32_t gb = (uint32_t)std::min<uint64_t>(ub_big, g.qbig_cap);
                 const uint32_t gm = g.mid_max > SMALL_MAX ? (uint32_t)std::min<uint64_t>(ub_mid, g.qbig_cap) : 0u;  // tier off: its histogram does not fit
                 const uint32_t* cb = j ? counters + 2 * cur : nullptr;  // j == 0: counts are exact, no device read needed
@@ -884,7 +886,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             }
             nbig = h->h_pinned[2 * cur];
             nmid = h->h_pinned[2 * cur + 1];
-            nwide = g.wide_max ? h->h_pinned[8 + cur] : 0u;
+            nwide = g.wide_max ? h->h_pinned[16 + cur] : 0u;
             if (nbig > g.qbig_cap || nmid > g.qbig_cap || nwide > g.qwide_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
         tr_levels = ms_since(t_batch);

@@ -332,6 +332,35 @@ def test_two_class_packed_cta_tier_bit_exact(eng, request, n, d, mf):
         compare_tree(gn, gc, ot.nodes, ot.counts, f"C=2 tree({part},{t})")
 
 
+@pytest.mark.parametrize("n,d,C,mf,pk", [(9000, 12, 4, 3, {}), (7000, 40, 3, None, {}), (12000, 9, 2, 1, {}), (5000, 20, 4, 12, dict(min_samples_leaf=7, min_samples_split=20)),
+                                         (8000, 16, 4, "sqrt", dict(max_depth=4)), (2300, 6, 4, 2, {})])
+def test_wide_tier_bit_exact(eng, n, d, C, mf, pk):
+    """k_grow_wide (four warps per node, 257..2048 rows): constant, duplicated and two-valued columns force its fallback draw
+    (warp 0 continues the draw alone), m = 1 / 3 / 12 / all features exercise the warp-to-position mapping and its tie-breaks,
+    leaf / split minima and a depth limit its stop rules; tree roots of <= 2048 rows enter the tier unchecked."""
+    rng = np.random.default_rng(n + d)
+    bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
+    bins[1] = 9                        # constant
+    bins[2] = bins[3]                  # duplicated: exact gain ties between two features
+    bins[4] = (bins[4] > 128) * 7      # two-valued
+    if d > 8:
+        bins[6:9] = 3                  # more constants: the first m positions often hold no valid split
+    y = ((bins[0].astype(int) * C) // 256).astype(np.uint8)
+    flip = rng.random(n) < 0.35
+    y[flip] = rng.integers(0, C, int(flip.sum()))
+    fold = H.assign_folds(y, np.ones(n, np.uint8), 3, C)
+    gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, 3, 5, C, seed=11, keep=True, max_features=mf, **pk)
+    assert gst["row_visits_wide"] > 0 and gst["launches_grow_wide"] > 0
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    if isinstance(mf, int) and mf <= 3:
+        assert ost["fallback"] > 0  # the draw had to go beyond the first m positions somewhere
+    for part, t in ((0, 1), (2, 4)):
+        gn, gc = eng.export_tree(part, t, C)
+        ot = forest.tree(part, t)
+        compare_tree(gn, gc, ot.nodes, ot.counts, f"wide tier tree({part},{t})")
+
+
 @pytest.mark.parametrize("sub_rows", [2048, 1024, 0])
 @pytest.mark.parametrize("shape", [(20000, 24, 4, 3, "sqrt"), (5000, 32, 4, 5, "sqrt"), (3100, 9, 3, 2, None), (2500, 64, 2, 2, 20), (900, 5, 4, 3, 1)])
 def test_subtree_tier_bit_exact(eng, request, sub_rows, shape):
