@@ -413,6 +413,47 @@ def test_subtree_tier_growth_parameters(eng, request, pk):
     compare_tree(gn, gc, ot.nodes, ot.counts, f"params {pk}")
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_random_large_configurations_bit_exact(eng, seed):
+    """Randomised tables large enough for every level-synchronous tier at once (CTA per node, four warps per node, warp per
+    node, warp per subtree, thread per subtree) with random knobs: blind-level group sizes, tier boundaries, batch sizes --
+    the queue / counter plumbing between the tiers is what this test is after."""
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.choice([2600, 5000, 9000, 20000, 45000]))
+    d = int(rng.choice([3, 8, 16, 33, 64]))
+    C = int(rng.choice([2, 3, 4]))
+    card = int(rng.choice([3, 12, 256]))
+    k = int(rng.integers(1, 4))
+    bins = rng.integers(0, card, (d, n)).astype(np.uint8)
+    y = ((bins[0].astype(int) * C) // card).clip(0, C - 1).astype(np.uint8)
+    flip = rng.random(n) < 0.3
+    y[flip] = rng.integers(0, C, int(flip.sum()))
+    fold = H.assign_folds(y, np.ones(n, np.uint8), k, C)
+    pk = {}
+    if rng.random() < 0.4:
+        pk["max_depth"] = int(rng.integers(2, 14))
+    if rng.random() < 0.3:
+        pk["min_samples_leaf"] = int(rng.integers(1, 9)); pk["min_samples_split"] = int(rng.integers(2, 30))
+    if rng.random() < 0.4:
+        pk["max_features"] = int(rng.integers(1, d + 1))
+    knobs = dict(BLIND_LEVELS=int(rng.choice([1, 2, 4, 8])), THIN_NODES=int(rng.choice([0, 64, 2048, 100000])),
+                 WIDE_MAX=int(rng.choice([0, 600, 2048])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])))
+    for kk, v in knobs.items():
+        eng.set_option(kk, v)
+    try:
+        T = int(rng.integers(2, 6))
+        gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, T, C, seed=seed, keep=True, **pk)
+    finally:
+        for kk, v in dict(BLIND_LEVELS=4, THIN_NODES=2048, WIDE_MAX=-1, MID_MAX=-1, TINY_MAX=-1).items():
+            eng.set_option(kk, v)
+    assert np.array_equal(gv, ov), (n, d, C, card, k, pk, knobs)
+    check_stats(gst, ost)
+    part, t = int(rng.integers(0, k)), int(rng.integers(0, T))
+    gn, gc = eng.export_tree(part, t, C)
+    ot = forest.tree(part, t)
+    compare_tree(gn, gc, ot.nodes, ot.counts, f"large seed {seed} {knobs} tree({part},{t})")
+
+
 def test_fewer_rows_than_folds(eng):
     rng = np.random.default_rng(2)
     bins = rng.integers(0, 9, (3, 4)).astype(np.uint8)
