@@ -680,8 +680,12 @@ class TsTForest:
         from .interop import ExportedForest
 
         trees = [self.export_tree(t) for t in range(self.n_estimators)]
+        if self.criterion == "squared_error_levels":
+            raise ValueError("export: use criterion='squared_error' (the level-based criterion keeps level counts, not target sums)")
+        reg = self.criterion == "squared_error"
         return ExportedForest([n for n, _ in trees], [c for _, c in trees], self._eng.edges.copy(), self._eng.n_edges.copy(),
-                              np.asarray(self.classes_), int(self.n_features_in_), self.criterion)
+                              np.asarray(self.classes_), int(self.n_features_in_), self.criterion,
+                              float(self._lo) if reg else 0.0, float(self._step) if reg else 1.0)
 
     def save(self, path: str) -> None:
         self.export().save(path)

@@ -32,7 +32,9 @@ class ExportedForest:
     n_edges: np.ndarray  # [d] int32
     classes: np.ndarray
     n_features: int
-    criterion: str = "gini"
+    criterion: str = "gini"      # "squared_error": counts[t] is [n_nodes, 2] = (low, high) 32 bits of S = sum of w * yq, see node_values
+    target_lo: float = 0.0       # squared_error: y = target_lo + yq / 65535 * target_span
+    target_span: float = 1.0
     meta: dict | None = None
 
     # ---- disk
@@ -42,7 +44,7 @@ class ExportedForest:
             off[i + 1] = off[i] + len(n)
         np.savez_compressed(path, format_version=FORMAT_VERSION, tree_offsets=off, nodes=np.concatenate(self.nodes),
                             counts=np.concatenate(self.counts), edges=self.edges, n_edges=self.n_edges, classes=self.classes,
-                            n_features=self.n_features, criterion=self.criterion)
+                            n_features=self.n_features, criterion=self.criterion, target_lo=self.target_lo, target_span=self.target_span)
 
     # ---- sklearn
     def raw_thresholds(self, t: int) -> np.ndarray:
@@ -51,10 +53,37 @@ class ExportedForest:
         thr = np.where(b < self.n_edges[f], self.edges[f, np.minimum(b, self.edges.shape[1] - 1)], np.inf)
         return np.where(nd["feature"] >= 0, thr, -2.0)
 
+    def node_values(self, t: int) -> np.ndarray:
+        """squared_error: the mean target of every node of tree `t` on the target's scale (S / N mapped back)."""
+        c = self.counts[t]
+        S = c[:, 0].astype(np.float64) + c[:, 1].astype(np.float64) * 4294967296.0
+        N = self.nodes[t]["n_weighted"].astype(np.float64)
+        return self.target_lo + np.divide(S, N, out=np.zeros_like(S), where=N > 0) / 65535.0 * self.target_span
+
+    def _sklearn_regression_tree(self, t: int):
+        from sklearn.tree._tree import Tree
+
+        nd = self.nodes[t]
+        tree = Tree(self.n_features, np.array([1], dtype=np.intp), 1)
+        dt = tree.__getstate__()["nodes"].dtype
+        rec = np.zeros(len(nd), dtype=dt)
+        internal = nd["feature"] >= 0
+        rec["left_child"], rec["right_child"] = nd["left"], nd["right"]
+        rec["feature"] = np.where(internal, nd["feature"], -2)
+        rec["threshold"] = self.raw_thresholds(t)
+        rec["n_node_samples"] = nd["end"].astype(np.int64) - nd["begin"].astype(np.int64)
+        rec["weighted_n_node_samples"] = nd["n_weighted"]
+        # (node impurities would need the sum of squares, which the trees do not carry: left at 0)
+        tree.__setstate__(dict(max_depth=int(nd["depth"].max()), node_count=len(nd), nodes=rec,
+                               values=np.ascontiguousarray(self.node_values(t)[:, None, None])))
+        return tree
+
     def sklearn_tree(self, t: int):
         """Tree `t` as a genuine sklearn.tree._tree.Tree (state dict -> __setstate__)."""
         from sklearn.tree._tree import Tree
 
+        if self.criterion == "squared_error":
+            return self._sklearn_regression_tree(t)
         nd, cnt = self.nodes[t], self.counts[t].astype(np.float64)
         C = cnt.shape[1]
         tree = Tree(self.n_features, np.array([C], dtype=np.intp), 1)
@@ -76,9 +105,25 @@ class ExportedForest:
         return tree
 
     def to_sklearn(self):
-        """-> sklearn.ensemble.RandomForestClassifier whose estimators_ wrap the converted trees."""
+        """-> sklearn.ensemble.RandomForestClassifier (or RandomForestRegressor for criterion "squared_error") whose
+        estimators_ wrap the converted trees."""
         from sklearn.ensemble import RandomForestClassifier
         from sklearn.tree import DecisionTreeClassifier
+
+        if self.criterion == "squared_error":
+            from sklearn.ensemble import RandomForestRegressor
+            from sklearn.tree import DecisionTreeRegressor
+
+            ests = []
+            for t in range(len(self.nodes)):
+                e = DecisionTreeRegressor()
+                e.tree_ = self.sklearn_tree(t)
+                e.n_features_in_, e.n_outputs_, e.max_features_ = self.n_features, 1, self.n_features
+                ests.append(e)
+            rf = RandomForestRegressor(n_estimators=len(ests))
+            rf.estimators_ = ests
+            rf.n_features_in_, rf.n_outputs_ = self.n_features, 1
+            return rf
 
         C = len(self.classes)
         ests = []
@@ -123,4 +168,5 @@ def load_forest(path: str) -> ExportedForest:
     off = z["tree_offsets"]
     nodes = [z["nodes"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
     counts = [z["counts"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
-    return ExportedForest(nodes, counts, z["edges"], z["n_edges"], z["classes"], int(z["n_features"]), str(z["criterion"]))
+    return ExportedForest(nodes, counts, z["edges"], z["n_edges"], z["classes"], int(z["n_features"]), str(z["criterion"]),
+                          float(z["target_lo"]) if "target_lo" in z else 0.0, float(z["target_span"]) if "target_span" in z else 1.0)

@@ -96,3 +96,23 @@ def test_forest_export_save_load_sklearn_gpu(tmp_path):
     path = str(tmp_path / "f.npz")
     clf.save(path)
     assert np.array_equal(tst.load_forest(path).predict_votes(X[:500]), votes)
+
+
+@pytest.mark.gpu
+def test_regression_forest_to_sklearn_gpu(tmp_path):
+    """criterion="squared_error": the exported forest becomes a genuine RandomForestRegressor whose predictions equal the
+    device's Q16.16 leaf-mean votes to 2^-16 of the target's span."""
+    import tst
+    from tst import synth
+
+    X, y = synth.numeric_table(1500, 10, seed=6)
+    reg = tst.TsTForest(n_estimators=6, criterion="squared_error", max_features=1.0, random_state=4).fit(X, y)
+    ours = reg.predict(X[:400])
+    rf = reg.to_sklearn()
+    assert type(rf).__name__ == "RandomForestRegressor" and type(rf.estimators_[0].tree_).__name__ == "Tree"
+    span = float(y.max() - y.min())
+    assert np.abs(rf.predict(X[:400]) - ours).max() <= span * 2.0 ** -15
+    path = str(tmp_path / "r.npz")
+    reg.save(path)
+    back = tst.load_forest(path)
+    assert back.criterion == "squared_error" and np.allclose(back.to_sklearn().predict(X[:400]), rf.predict(X[:400]))
