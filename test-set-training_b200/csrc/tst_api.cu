@@ -608,20 +608,24 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const bool want_stash = kn.stash;  // see use_stash below
     const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (5 * qbig_per + 2 * qwide_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
     size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
                      h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qwide0.cap + h->qwide1.cap + h->qsmall.cap + h->qsub.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
-    size_t budget = (size_t)((free_b + reclaim) * 0.6);
-    if (keep) {
-        size_t need = total_trees * arena_bytes;
-        if (need > budget) return fail(TST_ERR_NOMEM, "keep_forest: node arrays of " + std::to_string(total_trees) + " trees (" + std::to_string(need >> 20) + " MiB) do not fit");
-        budget -= need;
-    }
-    size_t per_tree = work_bytes + (keep ? 0 : arena_bytes);
-    size_t B = std::min<size_t>(total_trees, std::max<size_t>(1, budget / per_tree));
-    B = std::min<size_t>(B, 4096);
+    const size_t per_tree = work_bytes + (keep ? 0 : arena_bytes);
+    size_t B = std::min<size_t>(total_trees, 4096);
     if (prm->trees_in_flight > 0) B = std::min<size_t>(B, (size_t)prm->trees_in_flight);
+    // cudaMemGetInfo costs 0.3 - 0.9 ms once tens of GB are allocated (a whole IBP round on a 5k-row table is 4 ms): only ask the
+    // driver when this job's buffers do not already fit into what the handle holds from earlier calls
+    if (B * per_tree + (keep ? total_trees * arena_bytes : 0) > reclaim) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = (size_t)((free_b + reclaim) * 0.6);
+        if (keep) {
+            size_t need = total_trees * arena_bytes;
+            if (need > budget) return fail(TST_ERR_NOMEM, "keep_forest: node arrays of " + std::to_string(total_trees) + " trees (" + std::to_string(need >> 20) + " MiB) do not fit");
+            budget -= need;
+        }
+        B = std::min<size_t>(B, std::max<size_t>(1, budget / per_tree));
+    }
 
     ENSURE(h->trees, B * sizeof(TreeDesc));
     ENSURE(h->counts8, B * n_pad);
