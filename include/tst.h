@@ -163,6 +163,14 @@ int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* fold_dev, co
                 int32_t n_groups, int32_t k, int32_t n_trees, int32_t n_classes, const tst_params* params,
                 uint64_t seed, uint32_t gid_base, int32_t t0, int32_t t1, uint32_t* votes_dev, void* stream);
 
+/* The whole diagnostic in one call on device buffers (the shape SURVEY 8(b) sketched for tst_fit_oof: active mask in, votes and
+ * s(x) out): stratified folds of the active rows -> fold_out_dev [n], this rank's share of the k x n_trees forests, the vote
+ * all-gather when the handle owns a communicator, votes_dev [n, C] (zeroed here), s_dev [n] (may be NULL).  Collective when
+ * world > 1.  Equivalent to tst_assign_folds + tst_fit_oof(t0 = 0, t1 = n_trees, gid_base = 0) + tst_allreduce_votes + tst_finalize. */
+int tst_run_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* active_dev, const int32_t* group_dev, int32_t n_groups,
+                int32_t k, int32_t n_trees, int32_t n_classes, const tst_params* params, uint64_t seed, uint8_t* fold_out_dev,
+                uint32_t* votes_dev, float* s_dev, void* stream);
+
 /* (C1/K9) Sum `world` gathered vote tensors [world][n*C] in rank order into votes_out_dev. */
 int tst_reduce_votes(tst_handle* h, const uint32_t* gathered_dev, int32_t world, int64_t n_values,
                      uint32_t* votes_out_dev, void* stream);

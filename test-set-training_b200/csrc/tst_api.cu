@@ -1044,6 +1044,26 @@ extern "C" int tst_finalize(tst_handle* h, const uint32_t* votes_dev, const uint
     return TST_OK;
 }
 
+// One call for the whole diagnostic on device buffers: folds of the active rows, this rank's share of the k x n_trees forests,
+// the vote exchange when the handle has a communicator, s(x).  The signature SURVEY 8(b) sketched for tst_fit_oof
+// (active mask in, votes and s out); the separate entry points above stay for callers that keep their own folds.
+extern "C" int tst_run_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* active_dev, const int32_t* group_dev, int32_t n_groups,
+                           int32_t k, int32_t n_trees, int32_t C, const tst_params* prm, uint64_t seed, uint8_t* fold_out_dev,
+                           uint32_t* votes_dev, float* s_dev, void* stream) {
+    if (!h || !y_dev || !active_dev || !prm || !fold_out_dev || !votes_dev) return fail(TST_ERR_INVALID, "tst_run_oof: null argument");
+    if (!h->n) return fail(TST_ERR_STATE, "tst_run_oof: bin the table first");
+    if (h->world != 1 && !h->comm) return fail(TST_ERR_STATE, "tst_run_oof: world > 1 needs a handle created with an NCCL unique id");
+    if (prm->criterion == TST_SQUARED_ERROR && s_dev) return fail(TST_ERR_UNSUPPORTED, "tst_run_oof: s(x) is defined on class votes; pass s_dev = NULL for the squared-error criterion");
+    CK(cudaSetDevice(h->device));
+    int rc = tst_assign_folds(h, y_dev, active_dev, group_dev, n_groups, k, C, fold_out_dev, stream);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(votes_dev, 0, (size_t)h->n * C * 4, (cudaStream_t)stream));
+    if ((rc = tst_fit_oof(h, y_dev, fold_out_dev, group_dev, n_groups, k, n_trees, C, prm, seed, 0u, 0, n_trees, votes_dev, stream))) return rc;
+    if ((rc = tst_allreduce_votes(h, votes_dev, (int64_t)h->n * C, stream))) return rc;
+    if (s_dev) rc = tst_finalize(h, votes_dev, y_dev, fold_out_dev, group_dev, n_groups, k, n_trees, C, s_dev, nullptr, nullptr, stream);
+    return rc;
+}
+
 // --------------------------------------------------------------------------------------------- IBP
 extern "C" int tst_ibp_select(tst_handle* h, const uint32_t* votes_dev, const uint8_t* y_dev, const uint8_t* fold_dev, int32_t k,
                               int32_t C, uint64_t vmin, int64_t batch, uint8_t* active_dev, int64_t* removed_host, void* stream) {

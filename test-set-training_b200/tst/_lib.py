@@ -81,7 +81,7 @@ def lib():
         L.tst_last_error.restype = C.c_char_p
         for name in ("tst_create", "tst_destroy", "tst_bin", "tst_bin_auto", "tst_set_bins", "tst_get_bins", "tst_assign_folds",
                      "tst_fit_oof", "tst_reduce_votes", "tst_allreduce_votes", "tst_nccl_unique_id", "tst_finalize", "tst_ibp_select", "tst_ibp", "tst_predict",
-                     "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_abi_version", "tst_set_option", "tst_feature_importances", "tst_set_target", "tst_get_edges"):
+                     "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_abi_version", "tst_set_option", "tst_feature_importances", "tst_set_target", "tst_get_edges", "tst_run_oof"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -89,7 +89,7 @@ def lib():
 
 EXPORTS = ["tst_abi_version", "tst_last_error", "tst_create", "tst_destroy", "tst_bin", "tst_bin_auto", "tst_set_bins", "tst_get_bins",
            "tst_assign_folds", "tst_fit_oof", "tst_reduce_votes", "tst_allreduce_votes", "tst_nccl_unique_id", "tst_finalize", "tst_ibp_select", "tst_ibp",
-           "tst_predict", "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_set_option", "tst_feature_importances", "tst_set_target", "tst_get_edges"]
+           "tst_predict", "tst_export_tree", "tst_get_stats", "tst_reset_stats", "tst_set_option", "tst_feature_importances", "tst_set_target", "tst_get_edges", "tst_run_oof"]
 
 
 def check(rc: int):

@@ -253,6 +253,18 @@ class Engine:
                                      self._ptr(votes), self._stream()))
         return votes
 
+    def run_oof(self, y_dev, active_dev, k, n_trees, n_classes, params: Params, seed=0, group_dev=None, n_groups=1, want_s=True):
+        """One C call for folds + forests + vote exchange + s(x) on device buffers (include/tst.h: tst_run_oof)
+        -> (fold uint8 [n], votes int32 [n, C] (uint32 bit pattern), s float32 [n] | None)."""
+        torch = _torch()
+        fold = torch.empty(self.n, dtype=torch.uint8, device=self.dev)
+        votes = torch.empty((self.n, n_classes), dtype=torch.int32, device=self.dev)
+        s = torch.empty(self.n, dtype=torch.float32, device=self.dev) if want_s else None
+        check(_lib.lib().tst_run_oof(self._h, self._ptr(y_dev), self._ptr(active_dev), self._ptr(group_dev), C.c_int32(n_groups),
+                                     C.c_int32(k), C.c_int32(n_trees), C.c_int32(n_classes), C.byref(params), C.c_uint64(seed),
+                                     self._ptr(fold), self._ptr(votes), self._ptr(s), self._stream()))
+        return fold, votes, s
+
     def allreduce_votes(self, votes):
         """The path's one exchange step: NCCL all-gather of the per-rank votes, then a rank-ordered integer sum."""
         if self.world == 1:

@@ -483,6 +483,24 @@ def test_grouped_forests_one_launch(eng, kind, T):
     compare_tree(gn, gc, ot.nodes, ot.counts, f"{kind} tree({part},{T - 1})")
 
 
+def test_run_oof_single_call(eng, vsi_small):
+    """tst_run_oof (folds + forests + s(x) in one C call on device buffers) == the oracle, with a partly inactive table."""
+    import tst
+
+    torch = _torch()
+    v = vsi_small
+    rng = np.random.default_rng(3)
+    active = (rng.random(len(v["y"])) < 0.8).astype(np.uint8)
+    eng.set_bins(v["bins"])
+    fold, votes, s = eng.run_oof(eng.to_dev(v["y"], torch.uint8), eng.to_dev(active, torch.uint8), 4, 9, 4, tst.make_params(16), seed=8)
+    ofold = H.assign_folds(v["y"], active, 4, 4)
+    ov, _, _ = H.fit_oof(v["bins"], v["y"], ofold, 4, 9, 4, H.make_params(16), seed=8)
+    os_, _, _ = H.finalize(ov, v["y"], ofold, 4, 9)
+    assert np.array_equal(fold.cpu().numpy(), ofold) and np.array_equal(votes.cpu().numpy().view(np.uint32), ov)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    assert (s.cpu().numpy()[active == 0] == -1.0).all()  # pruned rows are never scored
+
+
 def test_grouped_public_api_matches_per_group_runs(eng):
     """run_tst(group=...) == one run per question type: s(x) of a row only depends on its own group's forests."""
     import tst
