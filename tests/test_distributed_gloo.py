@@ -37,8 +37,13 @@ def _worker(rank, world, port, out_dir):
     bins = H.bin_table(X, edges, ne)
     k, T, C = 4, 6, 3
     fold = H.assign_folds(y, np.ones(len(y), np.uint8), k, C)
-    votes, st, _ = H.fit_oof(bins, y, fold, k, T, C, H.make_params(12), seed=9, rank=rank, world=world, nthreads=1)
+    imp = np.zeros(13, np.uint64)
+    votes, st, _ = H.fit_oof(bins, y, fold, k, T, C, H.make_params(12), seed=9, rank=rank, world=world, nthreads=1, importances=imp)
     assert st["trees"] == len(tst.shard_trees(k, T, rank, world))  # the host's shard list is the engine's
+    # feature importances: every rank holds integer sums over ITS trees; one all-reduce of d + 1 integers gives the forest's
+    ti = torch.from_numpy(imp.view(np.int64).copy())
+    dist.all_reduce(ti)
+    np.save(os.path.join(out_dir, f"imp_{rank}.npy"), ti.numpy().view(np.uint64))
     mine = torch.from_numpy(votes.view(np.int32).copy())
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine)  # the path's one exchange step
@@ -60,6 +65,8 @@ def test_world2_votes_equal_single_rank(tmp_path):
     edges, ne = H.find_edges(X)
     bins = H.bin_table(X, edges, ne)
     fold = H.assign_folds(y, np.ones(len(y), np.uint8), 4, 3)
-    ref = H.fit_oof(bins, y, fold, 4, 6, 3, H.make_params(12), seed=9)[0]
+    imp = np.zeros(13, np.uint64)
+    ref = H.fit_oof(bins, y, fold, 4, 6, 3, H.make_params(12), seed=9, importances=imp)[0]
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"votes_{r}.npy"), ref), r
+        assert np.array_equal(np.load(tmp_path / f"imp_{r}.npy"), imp), r  # integer sums: the same on any number of ranks
