@@ -115,7 +115,7 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qmid0, qmid1, qwide0, qwide1, qsmall, qsub, qtiny, qtiny2, imp, imp_sums, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
+        qmid0, qmid1, qmidc[2][2], qwide0, qwide1, qsmall, qsub, qtiny, qtiny2, imp, imp_sums, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
@@ -130,7 +130,8 @@ struct tst_handle {
     void* comm = nullptr;  // ncclComm_t
     uint32_t* h_pinned = nullptr;  // 16 words
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, evm0 = nullptr, evm1 = nullptr, evs0 = nullptr, evs1 = nullptr;
-    cudaEvent_t ev_lvl[8][4] = {};  // per level of a group of blind levels: before big, after big, after wide, after mid
+    cudaEvent_t ev_lvl[8][4] = {};  // (the two launches of the warp-per-node tier are timed together)
+    //  // per level of a group of blind levels: before big, after big, after wide, after mid
     cudaEvent_t evi0 = nullptr, evi1 = nullptr;  // OOF inference
     cudaEvent_t evk0 = nullptr, evk1 = nullptr;  // CTA-per-subtree tier
     // The table may be binned on another stream than the one the fit runs on (the host overlaps the H2D copy + binning with the
@@ -147,6 +148,8 @@ struct tst_handle {
         int tiny_max = -1, mid_max = -1, stash_max = -1;
         int blind_levels = 4;
         long thin_nodes = 2048;
+        int mid_classes = -1;         // size classes of the warp-per-node tier with their own queue + kernel instantiation: bit 0 = 33..64 rows
+                                      // (2 row slots per lane), bit 1 = ..128 rows (4 slots); default 3, 0 = one queue for the whole tier
         int wide_max = -1;            // largest node of the four-warps-per-node tier (0 = tier off; default 2048)
         int sub_rows = -1;            // row capacity of the CTA-per-subtree tier (<= 0 = tier off, the default)
     } knobs;
@@ -171,6 +174,15 @@ static const int MID_WARPS = MID_WARPS_N;
 #define MID_R_N 8
 #endif
 static const int MID_R = MID_R_N;  // warp-per-node tier holds up to 32 * MID_R rows in registers
+// size classes of that tier (GrowCtx::midc_max): 33..64 rows are every second node of it, ..128 another third; with 2 / 4 row slots per
+// lane instead of 8 the kernel needs fewer registers and more warps are resident (it is latency bound: profiles/r02_k_grow_mid.md)
+#ifndef MIDC0_MINB_N
+#define MIDC0_MINB_N 8
+#endif
+#ifndef MIDC1_MINB_N
+#define MIDC1_MINB_N 6
+#endif
+static const int MIDC_R[2] = {2, 4};
 static const size_t BIG_SMEM_BUDGET = 64 * 1024;
 
 extern "C" int tst_abi_version(void) { return TST_ABI_VERSION; }
@@ -198,6 +210,7 @@ static int set_option(tst_handle* h, const std::string& nm, long v) {
     else if (nm == "THIN_NODES") kn.thin_nodes = std::max(0l, v);
     else if (nm == "SUB_ROWS") kn.sub_rows = (int)v;
     else if (nm == "WIDE_MAX") kn.wide_max = (int)v;
+    else if (nm == "MID_CLASSES") kn.mid_classes = (int)v;
     else return -1;
     return 0;
 }
@@ -248,7 +261,7 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize; h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     // tuning / diagnostic knobs: defaults from the environment (TST_<NAME>), read once here; tst_set_option changes them later
     for (const char* nm : {"L2_PERSIST", "TRACE", "STASH", "BIG_PACKED", "ROOT_DENSE", "TINY_MAX", "MID_MAX", "STASH_MAX", "BLIND_LEVELS",
-                           "THIN_NODES", "SUB_ROWS", "WIDE_MAX"}) {
+                           "THIN_NODES", "SUB_ROWS", "WIDE_MAX", "MID_CLASSES"}) {
         const std::string env = std::string("TST_") + nm;
         if (const char* v = getenv(env.c_str())) set_option(h, nm, atol(v));
     }
@@ -264,7 +277,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qwide0, &h->qwide1, &h->qsmall, &h->qsub, &h->imp, &h->imp_sums, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qmidc[0][0], &h->qmidc[0][1], &h->qmidc[1][0], &h->qmidc[1][1], &h->qwide0, &h->qwide1, &h->qsmall, &h->qsub, &h->imp, &h->imp_sums, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk, &h->gather};
     for (DevBuf* b : bufs) b->release();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -288,6 +301,10 @@ static int set_kernel_attrs(tst_handle* h) {
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, MID_R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, 2, false, MIDC0_MINB_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, 2, true, MIDC0_MINB_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, 4, false, MIDC1_MINB_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, 4, true, MIDC1_MINB_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<MID_WARPS, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid<4, MID_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -606,10 +623,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / std::max<uint64_t>(2, tiny_eff + 1) + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
     const bool want_stash = kn.stash;  // see use_stash below
-    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (5 * qbig_per + 2 * qwide_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (9 * qbig_per + 2 * qwide_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
-                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qwide0.cap + h->qwide1.cap + h->qsmall.cap + h->qsub.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
+                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qmidc[0][0].cap + h->qmidc[0][1].cap + h->qmidc[1][0].cap + h->qmidc[1][1].cap + h->qwide0.cap + h->qwide1.cap + h->qsmall.cap + h->qsub.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
     const size_t per_tree = work_bytes + (keep ? 0 : arena_bytes);
     size_t B = std::min<size_t>(total_trees, 4096);
     if (prm->trees_in_flight > 0) B = std::min<size_t>(B, (size_t)prm->trees_in_flight);
@@ -637,6 +654,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->qbig1, B * qbig_per * sizeof(Task));
     ENSURE(h->qmid0, B * qbig_per * sizeof(Task));
     ENSURE(h->qmid1, B * qbig_per * sizeof(Task));
+    for (int c = 0; c < 2; ++c) for (int p = 0; p < 2; ++p) ENSURE(h->qmidc[c][p], B * qbig_per * sizeof(Task));
     ENSURE(h->qsmall, B * qsmall_per * sizeof(Task));
     ENSURE(h->qsub, B * qbig_per * sizeof(Task));
     ENSURE(h->qwide0, B * qwide_per * sizeof(Task));
@@ -700,14 +718,14 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
     // [2p], [2p+1] big / mid queue counts of parity p, [4] small, [5] tiny, [6 + r] tiny size histogram (r <= 6), [16 + p] four-warps-per-node
-    // queue of parity p, [20] subtree queue, [32 + r] tiny cursors
+    // queue of parity p, [22 + 2c + p] size class c of the warp-per-node tier, [20] subtree queue, [32 + r] tiny cursors
     uint32_t* counters = h->counters.as<uint32_t>();
     g.qsmall_count = counters + 4;
     g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
     g.tiny_max = (packed_ok && d <= TINY_FY_MAX && B <= 65535) ? TINY_MAX : 0;  // packed 4-class thread-per-subtree tier
     if (kn.tiny_max >= 0) g.tiny_max = std::min<uint32_t>(g.tiny_max, (uint32_t)kn.tiny_max);
     const bool mid_packed = packed_ok;  // packed 16-bit class counts (k_grow_mid4)
-    const uint32_t mid_per_warp = mid_packed ? ((MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
+    const uint32_t mid_per_warp = mid_packed ? mid4_per_warp(MID_R, d)
                                              : (uint32_t)g.FS + 2u * (uint32_t)C + (uint32_t)((d + 1) / 2);
     // warps per CTA of the warp-per-node tier: 8, or fewer when the unpacked histograms of many classes would not fit
     int mid_warps = MID_WARPS;
@@ -716,6 +734,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.mid_max = mid_smem <= 200 * 1024 ? 32u * MID_R : SMALL_MAX;
     g.mid_packed = mid_packed ? 1u : 0u;
     if (kn.mid_max >= 0) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)kn.mid_max));
+    const int mid_classes = (mid_packed && g.mid_max > SMALL_MAX) ? (kn.mid_classes >= 0 ? kn.mid_classes & 3 : 3) : 0;
+    size_t midc_smem[2];
+    for (int c = 0; c < 2; ++c) {
+        g.midc_max[c] = (mid_classes >> c & 1) ? 32u * MIDC_R[c] : 0u;
+        midc_smem[c] = (size_t)MID_WARPS * mid4_per_warp(MIDC_R[c], d) * 4;
+    }
     // CTA-per-subtree tier (tst_grow_sub.cuh): packed 4-class Gini, rows of <= 64 bytes.  It takes every node of 33 .. sub_max
     // rows that weighs < 2^16 and finishes the whole subtree, so the warp-per-node tier is off and the warp-per-subtree kernel only
     // sees the rare <= 32-row children of CTA-tier nodes.  SUB_ROWS: 2048 (16 warps, 1 CTA/SM, default), 1024 (8 warps, 2 CTAs/SM), 0 = off.
@@ -799,6 +823,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             g.qnext = h->qbig0.as<Task>(); g.qnext_count = counters + 0;
             g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 1;
             g.qwide_next = h->qwide0.as<Task>(); g.qwide_next_count = counters + 16;
+            for (int c = 0; c < 2; ++c) { g.qmidc_next[c] = h->qmidc[c][0].as<Task>(); g.qmidc_next_count[c] = counters + 22 + 2 * c; }
             k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb);
             CKL();
             h->stats.kernel_launches += 5;
@@ -819,13 +844,13 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         bool small_started = false, tiny_timed = false, sub_timed = false;
         const int blind_levels = kn.blind_levels;
         const uint64_t thin_nodes = (uint64_t)kn.thin_nodes;  // a level with at most this many nodes starts a group of blind levels
-        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1], nwide = h->h_pinned[16];
+        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1], nwide = h->h_pinned[16], nmidc[2] = {h->h_pinned[22], h->h_pinned[24]};
         double tr_gap = 0; int tr_groups = 0;
-        while (nbig > 0 || nmid > 0 || nwide > 0) {
+        while (nbig > 0 || nmid > 0 || nwide > 0 || nmidc[0] > 0 || nmidc[1] > 0) {
             const auto t_level = now();
-            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid + nwide <= thin_nodes;
+            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid + nwide + nmidc[0] + nmidc[1] <= thin_nodes;
             const int J = thin ? blind_levels : 1;
-            uint64_t ub_big = nbig, ub_mid = nmid, ub_wide = nwide;
+            uint64_t ub_big = nbig, ub_mid = nmid, ub_wide = nwide, ub_midc[2] = {nmidc[0], nmidc[1]};
             for (int j = 0; j < J; ++j) {
                 Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
                 Task* qmcur = cur ? h->qmid1.as<Task>() : h->qmid0.as<Task>();
@@ -837,6 +862,15 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 g.qwide_next = cur ? h->qwide0.as<Task>() : h->qwide1.as<Task>();
                 g.qwide_next_count = counters + 16 + (cur ^ 1);
                 CK(cudaMemsetAsync(g.qnext_count, 0, 8, st));  // both counters of the next level
+                Task* qmccur[2]; uint32_t gmc[2]; const uint32_t* cmc[2];
+                for (int c = 0; c < 2; ++c) {
+                    qmccur[c] = h->qmidc[c][cur].as<Task>();
+                    g.qmidc_next[c] = h->qmidc[c][cur ^ 1].as<Task>();
+                    g.qmidc_next_count[c] = counters + 22 + 2 * c + (cur ^ 1);
+                    if (g.midc_max[c]) CK(cudaMemsetAsync(g.qmidc_next_count[c], 0, 4, st));
+                    gmc[c] = g.midc_max[c] ? (uint32_t)std::min<uint64_t>(ub_midc[c], g.qbig_cap) : 0u;
+                    cmc[c] = j ? counters + 22 + 2 * c + cur : nullptr;
+                }
                 if (g.wide_max) CK(cudaMemsetAsync(g.qwide_next_count, 0, 4, st));
                 const uint32_t gw = g.wide_max ? (uint32_t)std::min<uint64_t>(ub_wide, g.qwide_cap) : 0u;
                 const uint32_t* cw = j ? counters + 16 + cur : nullptr;
@@ -868,11 +902,25 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                     CKL();
                     h->stats.kernel_launches++; h->stats.launches_grow_mid++;
                 }
+                if (gmc[1]) {
+                    const uint32_t nb = (gmc[1] + MID_WARPS - 1) / MID_WARPS;
+                    if (reg) k_grow_mid4<MID_WARPS, 4, true, MIDC1_MINB_N><<<nb, MID_WARPS * 32, midc_smem[1], st>>>(g, qmccur[1], gmc[1], cmc[1]);
+                    else k_grow_mid4<MID_WARPS, 4, false, MIDC1_MINB_N><<<nb, MID_WARPS * 32, midc_smem[1], st>>>(g, qmccur[1], gmc[1], cmc[1]);
+                    CKL();
+                    h->stats.kernel_launches++; h->stats.launches_grow_mid++;
+                }
+                if (gmc[0]) {
+                    const uint32_t nb = (gmc[0] + MID_WARPS - 1) / MID_WARPS;
+                    if (reg) k_grow_mid4<MID_WARPS, 2, true, MIDC0_MINB_N><<<nb, MID_WARPS * 32, midc_smem[0], st>>>(g, qmccur[0], gmc[0], cmc[0]);
+                    else k_grow_mid4<MID_WARPS, 2, false, MIDC0_MINB_N><<<nb, MID_WARPS * 32, midc_smem[0], st>>>(g, qmccur[0], gmc[0], cmc[0]);
+                    CKL();
+                    h->stats.kernel_launches++; h->stats.launches_grow_mid++;
+                }
                 CK(cudaEventRecord(h->ev_lvl[j][2], st));
                 h->stats.levels++;
                 cur ^= 1;
-                const uint64_t nb2 = 2 * ub_big, nw2 = 2 * (ub_big + ub_wide), nm2 = 2 * (ub_big + ub_wide + ub_mid);
-                ub_big = nb2; ub_wide = nw2; ub_mid = nm2;
+                const uint64_t nb2 = 2 * ub_big, nw2 = 2 * (ub_big + ub_wide), nm2 = 2 * (ub_big + ub_wide + ub_mid), nmc = 2 * (ub_big + ub_wide + ub_mid + ub_midc[0] + ub_midc[1]);
+                ub_big = nb2; ub_wide = nw2; ub_mid = nm2; ub_midc[0] = ub_midc[1] = nmc;  // (a child of any queued node can land in either class)
                 if (++level_guard > n_cap + 8) return fail(TST_ERR_STATE, "tree growth did not terminate");
             }
             CK(cudaMemcpyAsync(h->h_pinned, counters, 128, cudaMemcpyDeviceToHost, st));
@@ -891,7 +939,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             nbig = h->h_pinned[2 * cur];
             nmid = h->h_pinned[2 * cur + 1];
             nwide = g.wide_max ? h->h_pinned[16 + cur] : 0u;
-            if (nbig > g.qbig_cap || nmid > g.qbig_cap || nwide > g.qwide_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
+            for (int c = 0; c < 2; ++c) nmidc[c] = g.midc_max[c] ? h->h_pinned[22 + 2 * c + cur] : 0u;
+            if (nbig > g.qbig_cap || nmid > g.qbig_cap || nwide > g.qwide_cap || nmidc[0] > g.qbig_cap || nmidc[1] > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
         tr_levels = ms_since(t_batch);
         phase.next("tst subtree tiers + inference");

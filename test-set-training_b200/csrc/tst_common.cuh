@@ -163,6 +163,11 @@ struct GrowCtx {
     uint32_t* qwide_next_count;
     uint32_t qwide_cap;
     uint32_t wide_max; // 0 disables the tier
+    // size classes of the warp-per-node tier: nodes of SMALL_MAX < rows <= midc_max[0] and of midc_max[0] < rows <= midc_max[1] have their own
+    // (dense) queues, served by instantiations of k_grow_mid4 with 2 and 4 row slots per lane (more resident warps); 0 = class off
+    Task* qmidc_next[2];
+    uint32_t* qmidc_next_count[2];
+    uint32_t midc_max[2];
     uint32_t mid_max; // == SMALL_MAX disables the mid tier
     uint32_t mid_packed; // k_grow_mid4: 16-bit packed class counts, nodes must weigh <= 65535
     Task* qsmall;
@@ -281,4 +286,12 @@ __device__ __forceinline__ void tiny_push(const GrowCtx& g, uint32_t tree, uint3
 __device__ __forceinline__ void queue_push(Task* q, uint32_t* count, uint32_t cap, DevStats* st, const Task& t) {
     uint32_t i = atomicAdd(count, 1u);
     if (i < cap) q[i] = t; else st->error = 2;
+}
+
+// a node of `rows` <= mid_max rows: into the queue of its size class, if that class is on (<= 128 rows x 255 < 2^16: always packable)
+__device__ __forceinline__ bool mid_class_push(const GrowCtx& g, uint32_t rows, const Task& t) {
+    const int c = rows <= g.midc_max[0] ? 0 : (rows <= g.midc_max[1] ? 1 : -1);
+    if (c < 0) return false;
+    queue_push(g.qmidc_next[c], g.qmidc_next_count[c], g.qbig_cap, g.stats, t);
+    return true;
 }

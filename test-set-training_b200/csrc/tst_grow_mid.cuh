@@ -176,16 +176,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_grow_mid(GrowCtx g, const Task* 
 #ifndef MID_MINB
 #define MID_MINB 5
 #endif
-template <int WARPS, int R, bool REG = false>  // REG: criterion 2 -- a cell is (weight | sum of w * yq << 24) instead of four 16-bit class counts
-__global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
+// The candidate list of a node holds at most min(256, rows) entries: a kernel instantiated for <= 32 * R rows reserves 4 * NC words
+// per warp with NC = 32 * R candidates (NC = 256 for R = 8: the MID4_CAND layout).
+__host__ __device__ constexpr uint32_t mid4_ncand(int R) { return 32u * (uint32_t)R; }
+__host__ __device__ constexpr uint32_t mid4_per_warp(int R, int d) { return (MID4_HIST + 4u * mid4_ncand(R) + 8u + (uint32_t)((d + 1) / 2) + 3u) & ~3u; }
+
+template <int WARPS, int R, bool REG = false, int MINB = MID_MINB>  // REG: criterion 2 -- a cell is (weight | sum of w * yq << 24) instead of four 16-bit class counts
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_grow_mid4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     static_assert(REG || 32 * R * 255 < 65536, "packed 16-bit class counts need <= 256 rows per node");
     extern __shared__ __align__(16) uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int C = g.C, d = g.d, m = g.m;
-    const uint32_t per_warp = (MID4_HIST + MID4_CAND + 8u + (uint32_t)((d + 1) / 2) + 3u) & ~3u;  // 16-byte aligned warp slices
+    constexpr uint32_t NC = mid4_ncand(R);  // candidates: (P0, P1) pairs [0, 2 NC) | bin [2 NC, 3 NC) | gain estimate [3 NC, 4 NC)
+    const uint32_t per_warp = mid4_per_warp(R, d);  // 16-byte aligned warp slices
     uint32_t* s_hist = s_mem + warp * per_warp;
     uint32_t* s_cand = s_hist + MID4_HIST;
-    uint32_t* s_tot = s_cand + MID4_CAND;  // [4] totals, [4] left counts of the best split (for emit_split)
+    uint32_t* s_tot = s_cand + 4u * NC;  // [4] totals, [4] left counts of the best split (for emit_split)
     uint32_t* s_bestL = s_tot + 4;
     uint16_t* s_perm = (uint16_t*)(s_bestL + 4);
     const uint8_t* __restrict__ bins = g.bins_rm;
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
                         ((uint2*)s_cand)[j] = make_uint2((uint32_t)P, (uint32_t)(P >> 32));
                     } else
                     ((uint2*)s_cand)[j] = make_uint2(e0 + p0[q], e1 + p1[q]);  // one 64-bit store for both packed words
-                    s_cand[512u + j] = lane * 8u + q;
+                    s_cand[2u * NC + j] = lane * 8u + q;
                     ++j;
                 }
         }
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
                 ge = gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR));
                 lmax = fmaxf(lmax, ge);
             }
-            s_cand[768u + j] = __float_as_uint(ge);
+            s_cand[3u * NC + j] = __float_as_uint(ge);
         }
         float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lmax)));  // positive floats order like integers
         if (i < m && found) thr = fmaxf(thr, __double2float_rd(best_gain));  // a feature that cannot reach the node's best is skipped
@@ -351,9 +357,9 @@ __global__ void __launch_bounds__(WARPS * 32, MID_MINB) k_grow_mid4(GrowCtx g, c
         double bg = -1.0;
         uint32_t bb = 0xFFFFFFFFu, bP0 = 0, bP1 = 0;
         for (uint32_t j = lane; j < n_cand; j += 32) {
-            if (__uint_as_float(s_cand[768u + j]) >= thr) {
+            if (__uint_as_float(s_cand[3u * NC + j]) >= thr) {
                 const uint2 PP = ((const uint2*)s_cand)[j];
-                const uint32_t P0 = PP.x, P1 = PP.y, bin = s_cand[512u + j];
+                const uint32_t P0 = PP.x, P1 = PP.y, bin = s_cand[2u * NC + j];
                 const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
                 const unsigned long long P = (unsigned long long)P0 | ((unsigned long long)P1 << 32);
                 const uint32_t NL = REG ? reg_N(P) : L0 + L1 + L2 + L3, NR = N - NL;

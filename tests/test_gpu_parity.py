@@ -437,14 +437,14 @@ def test_random_large_configurations_bit_exact(eng, seed):
     if rng.random() < 0.4:
         pk["max_features"] = int(rng.integers(1, d + 1))
     knobs = dict(BLIND_LEVELS=int(rng.choice([1, 2, 4, 8])), THIN_NODES=int(rng.choice([0, 64, 2048, 100000])),
-                 WIDE_MAX=int(rng.choice([0, 600, 2048])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])))
+                 WIDE_MAX=int(rng.choice([0, 600, 2048])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])), MID_CLASSES=int(rng.integers(0, 4)))
     for kk, v in knobs.items():
         eng.set_option(kk, v)
     try:
         T = int(rng.integers(2, 6))
         gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, T, C, seed=seed, keep=True, **pk)
     finally:
-        for kk, v in dict(BLIND_LEVELS=4, THIN_NODES=2048, WIDE_MAX=-1, MID_MAX=-1, TINY_MAX=-1).items():
+        for kk, v in dict(BLIND_LEVELS=4, THIN_NODES=2048, WIDE_MAX=-1, MID_MAX=-1, TINY_MAX=-1, MID_CLASSES=-1).items():
             eng.set_option(kk, v)
     assert np.array_equal(gv, ov), (n, d, C, card, k, pk, knobs)
     check_stats(gst, ost)
@@ -761,6 +761,42 @@ def test_continuous_squared_error_bit_exact(eng, n, d, k, mf, ties, pk):
         gn, gc = eng.export_tree(part, t, 2)
         ot = forest.tree(part, t)
         compare_tree(gn, gc, ot.nodes, ot.counts, f"continuous regression tree({part},{t})")
+
+
+@pytest.mark.parametrize("classes", [0, 1, 2, 3])
+@pytest.mark.parametrize("crit", ["gini", "squared_error"])
+def test_mid_tier_size_classes_bit_exact(eng, request, classes, crit):
+    """The warp-per-node tier routes 33..64-row and 65..128-row nodes to their own queues / kernel instantiations (MID_CLASSES
+    bit 0 / bit 1); every combination must give the trees of the single-queue tier (= the oracle's), for both criteria."""
+    import tst
+    from tst import synth
+
+    eng.set_option("MID_CLASSES", classes)
+    request.addfinalizer(lambda: eng.set_option("MID_CLASSES", -1))
+    n, d, k = 12000, 16, 3
+    if crit == "gini":
+        rng = np.random.default_rng(77)
+        bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
+        y = ((bins[0].astype(int) + bins[1]) * 4 // 511).clip(0, 3).astype(np.uint8)
+        flip = rng.random(n) < 0.35
+        y[flip] = rng.integers(0, 4, int(flip.sum()))
+        fold = H.assign_folds(y, np.ones(n, np.uint8), k, 4)
+        gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, 4, 4, seed=5, keep=True)
+        C = 4
+    else:
+        X, yv = synth.numeric_table(n, d, seed=11)
+        yq, lo, span = tst.quantise_target16(yv)
+        lev = np.minimum((yq.astype(np.uint32) * 16) >> 16, 15).astype(np.uint8)
+        edges, ne, bins = oracle_table(X)
+        fold = H.assign_folds(lev, np.ones(n, np.uint8), k, 16)
+        gv, ov, gst, ost, forest = run_both_reg(eng, bins, yq, lev, fold, k, 4, seed=5, keep=True, max_features=0.5)
+        C = 2
+    assert np.array_equal(gv, ov)
+    check_stats(gst, ost)
+    assert gst["row_visits_mid"] > 0
+    gn, gc = eng.export_tree(1, 2, C)
+    ot = forest.tree(1, 2)
+    compare_tree(gn, gc, ot.nodes, ot.counts, f"size classes {classes} {crit}")
 
 
 def test_continuous_squared_error_public_api(eng):
