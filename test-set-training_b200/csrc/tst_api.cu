@@ -149,7 +149,7 @@ struct tst_handle {
         int blind_levels = 4;
         long thin_nodes = 2048;
         int mid_classes = -1;         // size classes of the warp-per-node tier with their own queue + kernel instantiation: bit 0 = 33..64 rows
-                                      // (2 row slots per lane), bit 1 = ..128 rows (4 slots); default 3, 0 = one queue for the whole tier
+                                      // (2 row slots per lane), bit 1 = ..128 rows (4 slots); 0 = one queue for the whole tier; default: 3 for batches of >= 2^24 (tree, row) pairs, else 0
         int wide_max = -1;            // largest node of the four-warps-per-node tier (0 = tier off; default 2048)
         int sub_rows = -1;            // row capacity of the CTA-per-subtree tier (<= 0 = tier off, the default)
     } knobs;
@@ -734,7 +734,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     g.mid_max = mid_smem <= 200 * 1024 ? 32u * MID_R : SMALL_MAX;
     g.mid_packed = mid_packed ? 1u : 0u;
     if (kn.mid_max >= 0) g.mid_max = std::max<uint32_t>(SMALL_MAX, std::min<uint32_t>(32u * MID_R, (uint32_t)kn.mid_max));
-    const int mid_classes = (mid_packed && g.mid_max > SMALL_MAX) ? (kn.mid_classes >= 0 ? kn.mid_classes & 3 : 3) : 0;
+    // Two more launches per level: they pay once the levels are many waves deep (measured crossover, tools/class_crossover.py:
+    // ~10M in-bag rows per batch; 5 x 100 trees on 5k rows lose 0.5 ms of 3.3 to the extra launches), so "auto" looks at the batch.
+    const bool deep_levels = (uint64_t)B * n_cap >= (1ull << 24);
+    const int mid_classes = (mid_packed && g.mid_max > SMALL_MAX) ? (kn.mid_classes >= 0 ? kn.mid_classes & 3 : (deep_levels ? 3 : 0)) : 0;
     size_t midc_smem[2];
     for (int c = 0; c < 2; ++c) {
         g.midc_max[c] = (mid_classes >> c & 1) ? 32u * MIDC_R[c] : 0u;

@@ -32,6 +32,10 @@ for kind in ("cvbench", "mmmu", "videomme"):
     Xg, yg, gg, ng = synth.grouped_table(kind)
     ms, r = best_of(lambda: tst.run_tst(Xg, yg, k=5, n_trees=100, seed=1, group=gg, engine=eng))
     print(f"  {kind}: {ms:.2f} ms, launches {r.stats['kernel_launches']}")
+Xn, yn = synth.numeric_table(5000, 32, seed=0)
+ms, r = best_of(lambda: tst.run_tst_regression(Xn, yn, k=5, n_trees=100, seed=1, engine=eng))
+print(f"  regression 5k x 32, 5 x 100, all features per split: {ms:.2f} ms, launches {r.stats['kernel_launches']}, levels {r.stats['levels']}, "
+      f"ms big {r.stats['ms_grow_big']:.2f} wide {r.stats['ms_grow_wide']:.2f} mid {r.stats['ms_grow_mid']:.2f} small {r.stats['ms_grow_small']:.2f} tiny {r.stats['ms_grow_tiny']:.2f}")
 if os.environ.get("TST_TRACE_ONE"):
     eng.set_option("TRACE", 1)
     tst.run_tst(X, y, k=5, n_trees=100, seed=1, engine=eng)
