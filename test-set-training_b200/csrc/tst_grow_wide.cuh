@@ -1,20 +1,23 @@
-// tst_grow_wide.cuh -- four warps per node for nodes of 257 .. WIDE_MAXR distinct rows that weigh < 2^16 (<= 4 classes, Gini).
+// tst_grow_wide.cuh -- four warps per node for nodes of 257 .. WIDE_MAXR (1024) distinct rows that weigh < 2^16 (<= 4 classes, Gini).
 //
-// These are the deep levels of the CTA-per-node kernel (levels 8-13 of a 1M-row tree: 85 of its 165 ms per 640 trees):
-// k_grow_big spends eight barriers, a 256-thread CTA and a shared row tile on a node of a few hundred rows, ~20 k
-// warp-instructions per node.  Here the node's entry list is cached in shared memory once (8 bytes per row) and every warp
-// owns its sampled features END TO END: its own packed 16-bit histogram (warp-privatised: no cross-warp atomics), the
-// gathers of that feature's bytes for all rows of the node (4 in flight per lane), the prefix scan and the fp32-estimate /
-// fp64-gain evaluation (scan_feature_packed4).  No barrier inside the search; one to combine the warps' best splits, two in
-// the partition (per-warp blocks, ballots parked in shared memory so the split feature is gathered once).  27 KB of shared
-// memory and 128 threads per node: the occupancy of k_grow_mid4 instead of k_grow_big's three CTAs per SM.
+// These were the deep levels of the CTA-per-node kernel: k_grow_big spends eight barriers, a 256-thread CTA and ~20 k
+// warp-instructions on a node of a few hundred rows.  Here the node's entry list is cached in shared memory once (8 bytes per
+// row), the rows are fetched ONCE through a row tile (fetch_rows32, 32 rows per warp and step) and the bins at the first 8
+// positions of the draw kept beside the entries (8 bytes per row), and every warp owns its sampled features END TO END: its
+// own packed 16-bit histogram (warp-privatised: no cross-warp atomics), filled from shared memory, the prefix scan and the
+// fp32-estimate / fp64-gain evaluation (scan_feature_packed4).  No barrier inside the search; one to combine the warps' best
+// splits, two in the partition (per-warp blocks, ballots parked in shared memory).  Positions that were not staged (beyond the
+// 8th, fallback draws, rows wider than 64 bytes) gather their bytes from the table, WIDE_U per lane in flight.
+// 64 registers, 27 KB of shared memory and 128 threads per node: 8 CTAs per SM.
 // Same draws, candidates, gains and tie-breaks as every other tier; checked against oracle/hist_rf.c.
 #pragma once
 #include "tst_grow_mid.cuh"
 
-#define WIDE_MAXR 2048u
+#ifndef WIDE_MAXR
+#define WIDE_MAXR 1024u
+#endif
 #ifndef WIDE_MINB
-#define WIDE_MINB 5
+#define WIDE_MINB 8
 #endif
 #ifndef WIDE_U
 #define WIDE_U 4
@@ -22,8 +25,9 @@
 
 #define WIDE_MAXCH 32u  // ballot words a warp may have to park: its block of the partition is <= WIDE_MAXR / WARPS rounded up to 32 rows
 __host__ __device__ __forceinline__ size_t wide_smem_bytes(int warps, int d) {
-    // histograms [warps][640] | entries [WIDE_MAXR] x 8 bytes | permutation (d 16-bit values) | parked ballots [warps][WIDE_MAXCH]
-    return 4u * ((size_t)warps * MID4_HIST + 2u * WIDE_MAXR + (size_t)((d + 1) / 2) + (size_t)warps * WIDE_MAXCH) + 16u;
+    // histograms [warps][640] (first the warps' row tiles) | entries [WIDE_MAXR] x 8 bytes | sampled bytes [2][WIDE_MAXR] words |
+    // permutation (d 16-bit values) | parked ballots [warps][WIDE_MAXCH]
+    return 4u * ((size_t)warps * MID4_HIST + 4u * WIDE_MAXR + (size_t)((d + 1) / 2) + (size_t)warps * WIDE_MAXCH) + 16u;
 }
 
 template <int WARPS>
@@ -54,7 +58,8 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
 
     uint32_t* s_hist = s_mem + wid * MID4_HIST;
     Entry* s_ent = (Entry*)(s_mem + WARPS * MID4_HIST);
-    uint16_t* s_perm = (uint16_t*)(s_ent + WIDE_MAXR);
+    uint32_t* s_samp = (uint32_t*)(s_ent + WIDE_MAXR);  // [0][i]: the bins of row i at positions 0..3 of the draw, [1][i]: positions 4..7
+    uint16_t* s_perm = (uint16_t*)(s_samp + 2u * WIDE_MAXR);
     uint32_t* s_bal = (uint32_t*)(s_perm + ((d + 1) / 2) * 2) + wid * MAXCH;
 
     for (uint32_t i = tid; i < r; i += THREADS) s_ent[i] = ent_load(ent_in + t.begin + i);
@@ -66,14 +71,52 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
     if (tid == 0) s_fb = 0;
     __syncthreads();
 
-    // One feature of the node, by one warp, into that warp's histogram: WIDE_U byte gathers per lane in flight.
-    // (Two features per pass over the entries -- 8 gathers in flight, two histograms per warp -- measured slower: 76 -> 85 ms.)
-    auto feature = [&](uint32_t f, double& bg, uint32_t& bb, uint32_t& P0, uint32_t& P1, uint32_t& X0, uint32_t& X1) {
+    // ---- the rows are fetched ONCE: 32 rows per warp and step through a row tile in the warp's histogram space (16-byte
+    // pieces: one L1 wavefront per row instead of one per sampled byte), and the bins at the first 8 positions of the draw are
+    // kept, 8 bytes per row.  Every histogram pass and the partition then read shared memory only: no global load is left in
+    // them, which is what lets the kernel run at 64 registers and 8 CTAs per SM.
+    const bool staged = dstride <= 64u && dstride >= 16u && (dstride & (dstride - 1u)) == 0u;
+    const uint32_t mstage = staged ? (uint32_t)min(m, 8) : 0u;  // (a fallback draw re-deals the positions >= m: never staged)
+    if (staged) {
+        const uint32_t pitch = (dstride >> 2) + 1u;
+        uint32_t featr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) featr[j] = s_perm[min(j, d - 1)];
+        const uint8_t* trow = (const uint8_t*)(s_hist + lane * pitch);
+        for (uint32_t c0 = wid * 32u; c0 < r; c0 += THREADS) {
+            const uint32_t i = c0 + lane;
+            const bool has = i < r;
+            const uint32_t row = has ? s_ent[i].x : 0u;
+            fetch_rows32(bins, dstride, row, has, s_hist, lane);
+            uint32_t s0 = 0, s1 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s0 |= (uint32_t)trow[featr[j]] << (8 * j); s1 |= (uint32_t)trow[featr[j + 4]] << (8 * j); }
+            if (has) { s_samp[i] = s0; s_samp[WIDE_MAXR + i] = s1; }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+
+    // One feature of the node (position `pos` of the draw), by one warp, into that warp's histogram.
+    // (Two features per pass over the entries -- two histograms per warp -- measured slower: 76 -> 85 ms.)
+    auto feature = [&](uint32_t pos, double& bg, uint32_t& bb, uint32_t& P0, uint32_t& P1, uint32_t& X0, uint32_t& X1) {
         {
             uint4* hz = (uint4*)(s_hist + lane * 20u);
             hz[0] = hz[1] = hz[2] = hz[3] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncwarp();
+        if (pos < mstage) {
+            const uint32_t* sp = s_samp + (pos >> 2) * WIDE_MAXR;
+            const uint32_t sh = 8u * (pos & 3u);
+            for (uint32_t i = lane; i < r; i += 32u) {
+                const Entry q = s_ent[i];
+                const uint32_t b = (sp[i] >> sh) & 0xFFu, cls = ent_cls(q);
+                atomicAdd(&s_hist[(b >> 3) * 20u + (b & 7u) * 2u + (cls >> 1)], ent_w(q) << (16u * (cls & 1u)));
+            }
+        } else {
+        // straight from the table (WIDE_U byte gathers per lane in flight): positions of the draw that were not staged --
+        // beyond the 8th, fallback draws, rows wider than 64 bytes
+        const uint32_t f = s_perm[pos];
         for (uint32_t i0 = 0; i0 < r; i0 += 32u * WIDE_U) {
             Entry q[WIDE_U];
             uint32_t b[WIDE_U];
@@ -91,6 +134,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
                     atomicAdd(&s_hist[(b[u] >> 3) * 20u + (b[u] & 7u) * 2u + (cls >> 1)], ent_w(q[u]) << (16u * (cls & 1u)));
                 }
         }
+        }
         __syncwarp();
         scan_feature_packed4(s_hist, g.msl, lane, bg, bb, P0, P1, X0, X1);
         __syncwarp();
@@ -101,7 +145,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
     uint32_t best_pos = 0xFFFFFFFFu, best_bin = 0, bestP0 = 0, bestP1 = 0, T0 = 0, T1 = 0;
     for (int j = (int)wid; j < m; j += WARPS) {
         double bg; uint32_t bb, P0 = 0, P1 = 0, X0, X1;
-        feature(s_perm[j], bg, bb, P0, P1, X0, X1);
+        feature((uint32_t)j, bg, bb, P0, P1, X0, X1);
         T0 = X0; T1 = X1;
         if (bb != 0xFFFFFFFFu && bg > best_gain) { best_gain = bg; best_pos = (uint32_t)j; best_bin = bb; bestP0 = P0; bestP1 = P1; }  // earlier position keeps a tie
     }
@@ -140,7 +184,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
                     }
                     __syncwarp();
                     double bg; uint32_t bb, P0 = 0, P1 = 0, X0, X1;
-                    feature(s_perm[i], bg, bb, P0, P1, X0, X1);
+                    feature((uint32_t)i, bg, bb, P0, P1, X0, X1);
                     if (bb != 0xFFFFFFFFu) {
                         if (lane == 0) { s_fb = (uint32_t)i + 1u; s_fbgain = bg; s_fbbin = bb; s_fbP0 = P0; s_fbP1 = P1; }
                         break;
@@ -180,7 +224,9 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
         uint32_t c = 0, k = 0;
         for (uint32_t i0 = blo; i0 < bhi; i0 += 32u, ++k) {
             const uint32_t i = i0 + lane;
-            const bool l = i < bhi && bins[(uint64_t)s_ent[min(i, r - 1u)].x * dstride + bf] <= bbin;
+            bool l;
+            if (best_pos < mstage) l = i < bhi && ((s_samp[(best_pos >> 2) * WIDE_MAXR + min(i, r - 1u)] >> (8u * (best_pos & 3u))) & 0xFFu) <= bbin;
+            else l = i < bhi && bins[(uint64_t)s_ent[min(i, r - 1u)].x * dstride + bf] <= bbin;
             const uint32_t bal = __ballot_sync(0xffffffffu, l);
             if (lane == 0) s_bal[k] = bal;
             c += __popc(bal);

@@ -254,7 +254,7 @@ def test_random_configurations_bit_exact(eng, seed):
 def test_dense_root_kernels_bit_exact(eng, request, n, d, C, k):
     """k_root_hist / k_root_split (TMA-streamed column-major histogram of the root) forced on small tables."""
     eng.set_option("ROOT_DENSE", 2)
-    eng.set_option("WIDE_MAX", 0)  # roots of <= 2048 rows would go to the four-warps-per-node tier instead of dense root + k_grow_big
+    eng.set_option("WIDE_MAX", 0)  # roots of <= 1024 rows would go to the four-warps-per-node tier instead of dense root + k_grow_big
     request.addfinalizer(lambda: (eng.set_option("ROOT_DENSE", -1), eng.set_option("WIDE_MAX", -1)))
     rng = np.random.default_rng(n)
     bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
@@ -314,7 +314,7 @@ def test_wide_tables_bit_exact(eng, d, C, mf):
 def test_two_class_packed_cta_tier_bit_exact(eng, request, n, d, mf):
     """Binary labels, 256-valued bins, non-root nodes of > 256 rows that weigh < 2^16: k_grow_big's packed 16-bit
     histogram (640 words per feature) is larger than the unpacked 2-class layout (544) -- the region must hold it."""
-    eng.set_option("WIDE_MAX", 0)  # keep the 257 .. 2048-row nodes on k_grow_big
+    eng.set_option("WIDE_MAX", 0)  # keep the 257 .. 1024-row nodes on k_grow_big
     request.addfinalizer(lambda: eng.set_option("WIDE_MAX", -1))
     rng = np.random.default_rng(n + d)
     bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
@@ -335,9 +335,9 @@ def test_two_class_packed_cta_tier_bit_exact(eng, request, n, d, mf):
 @pytest.mark.parametrize("n,d,C,mf,pk", [(9000, 12, 4, 3, {}), (7000, 40, 3, None, {}), (12000, 9, 2, 1, {}), (5000, 20, 4, 12, dict(min_samples_leaf=7, min_samples_split=20)),
                                          (8000, 16, 4, "sqrt", dict(max_depth=4)), (2300, 6, 4, 2, {})])
 def test_wide_tier_bit_exact(eng, n, d, C, mf, pk):
-    """k_grow_wide (four warps per node, 257..2048 rows): constant, duplicated and two-valued columns force its fallback draw
+    """k_grow_wide (four warps per node, 257..1024 rows; rows staged once through a tile when a row is <= 64 bytes): constant, duplicated and two-valued columns force its fallback draw
     (warp 0 continues the draw alone), m = 1 / 3 / 12 / all features exercise the warp-to-position mapping and its tie-breaks,
-    leaf / split minima and a depth limit its stop rules; tree roots of <= 2048 rows enter the tier unchecked."""
+    leaf / split minima and a depth limit its stop rules; tree roots of <= 1024 rows enter the tier unchecked."""
     rng = np.random.default_rng(n + d)
     bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
     bins[1] = 9                        # constant
@@ -437,7 +437,7 @@ def test_random_large_configurations_bit_exact(eng, seed):
     if rng.random() < 0.4:
         pk["max_features"] = int(rng.integers(1, d + 1))
     knobs = dict(BLIND_LEVELS=int(rng.choice([1, 2, 4, 8])), THIN_NODES=int(rng.choice([0, 64, 2048, 100000])),
-                 WIDE_MAX=int(rng.choice([0, 600, 2048])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])), MID_CLASSES=int(rng.integers(0, 4)))
+                 WIDE_MAX=int(rng.choice([0, 600, 1024])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])), MID_CLASSES=int(rng.integers(0, 4)))
     for kk, v in knobs.items():
         eng.set_option(kk, v)
     try:
