@@ -327,12 +327,23 @@ __device__ __forceinline__ void scan_feature_packed4(const uint32_t* __restrict_
         }
     }
     const float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lmax))) * TST_EST_MARGIN;
+    // exact fp64 gain of the contenders: usually ONE bin of one lane.  A loop over each lane's contender mask (lowest bin first)
+    // with the bin's prefix picked by a select chain: one copy of the division code instead of eight (the kernels using this scan
+    // were stalling on instruction fetch), typically one trip.
+    uint32_t cm = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cm |= (ge[q] >= thr ? 1u : 0u) << q;
     double bg = -1.0;
     uint32_t bb = 0xFFFFFFFFu, bP0 = 0, bP1 = 0;
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, cm != 0u)) {
+        if (cm) {
+            const uint32_t q = (uint32_t)__ffs(cm) - 1u;
+            cm &= cm - 1u;
+            uint32_t a0 = p0[0], a1 = p1[0];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        if (ge[q] >= thr) {
-            const uint32_t P0 = e0 + p0[q], P1 = e1 + p1[q];
+            for (int k = 1; k < 8; ++k) if (q == (uint32_t)k) { a0 = p0[k]; a1 = p1[k]; }
+            const uint32_t P0 = e0 + a0, P1 = e1 + a1;
             const uint32_t L0 = P0 & 0xFFFFu, L1 = P0 >> 16, L2 = P1 & 0xFFFFu, L3 = P1 >> 16;
             const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
             const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
