@@ -38,9 +38,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
     extern __shared__ __align__(16) uint32_t s_mem[];
     __shared__ double s_wgain[WARPS];
     __shared__ uint32_t s_wpos[WARPS], s_wbin[WARPS], s_wP0[WARPS], s_wP1[WARPS], s_cnt[WARPS];
-    __shared__ uint32_t s_tot[4], s_bestL[4], s_T0, s_T1, s_fb;  // s_fb: fallback result (0 = none, else (pos + 1))
-    __shared__ double s_fbgain;
-    __shared__ uint32_t s_fbbin, s_fbP0, s_fbP1;
+    __shared__ uint32_t s_tot[4], s_bestL[4], s_T0, s_T1;
 
     if (ntasks_dev) ntasks = min(ntasks, *ntasks_dev);
     if (blockIdx.x >= ntasks) return;
@@ -68,7 +66,6 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
         __syncwarp();
         warp_draw_primary(s_perm, d, m, t.begin, t.depth, td.gid, g.k0, g.k1, lane);
     }
-    if (tid == 0) s_fb = 0;
     __syncthreads();
 
     // ---- the rows are fetched ONCE: 32 rows per warp and step through a row tile in the warp's histogram space (16-byte
@@ -140,60 +137,55 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
         __syncwarp();
     };
 
-    // ---- the first m positions of the draw: warp w takes positions w, w + WARPS, ...
+    // ---- rounds of positions of the draw, warp w takes positions lo + w, lo + w + WARPS, ...: first the m sampled features (best
+    // gain; ties -> the feature drawn first, then its lowest bin); if none of them splits the node (rare), the draw continues
+    // WARPS positions at a time and the first position that separates the rows wins.  One loop, so `feature` is inlined once.
     double best_gain = -1.0;
     uint32_t best_pos = 0xFFFFFFFFu, best_bin = 0, bestP0 = 0, bestP1 = 0, T0 = 0, T1 = 0;
-    for (int j = (int)wid; j < m; j += WARPS) {
-        double bg; uint32_t bb, P0 = 0, P1 = 0, X0, X1;
-        feature((uint32_t)j, bg, bb, P0, P1, X0, X1);
-        T0 = X0; T1 = X1;
-        if (bb != 0xFFFFFFFFu && bg > best_gain) { best_gain = bg; best_pos = (uint32_t)j; best_bin = bb; bestP0 = P0; bestP1 = P1; }  // earlier position keeps a tie
-    }
-    if (lane == 0) {
-        s_wgain[wid] = best_gain; s_wpos[wid] = best_pos; s_wbin[wid] = best_bin; s_wP0[wid] = bestP0; s_wP1[wid] = bestP1;
-        if (wid == 0) { s_T0 = T0; s_T1 = T1; }  // m >= 1: warp 0 always scanned position 0
-    }
-    __syncthreads();
-    T0 = s_T0; T1 = s_T1;
-    const uint32_t t0 = T0 & 0xFFFFu, t1 = T0 >> 16, t2 = T1 & 0xFFFFu, t3 = T1 >> 16, N = t0 + t1 + t2 + t3;
-    const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
-    const bool stop = stop_rule(g, N, t.depth, pure);  // only a tree root can arrive unchecked
-    bool found = false;
-    best_gain = -1.0; best_pos = 0xFFFFFFFFu;
-    if (!stop) {
+    uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, N = 0;
+    bool found = false, stop = false;
+    for (uint32_t lo = 0, hi = (uint32_t)m;;) {
+        double wg = -1.0;
+        uint32_t wp = 0xFFFFFFFFu, wbin = 0, wP0 = 0, wP1 = 0;
+        for (uint32_t j = lo + wid; j < hi; j += WARPS) {
+            double bg; uint32_t bb, P0 = 0, P1 = 0, X0, X1;
+            feature(j, bg, bb, P0, P1, X0, X1);
+            T0 = X0; T1 = X1;
+            if (bb != 0xFFFFFFFFu && (lo ? wp == 0xFFFFFFFFu : bg > wg)) { wg = bg; wp = j; wbin = bb; wP0 = P0; wP1 = P1; }  // earlier position keeps a tie
+        }
+        if (lane == 0) {
+            s_wgain[wid] = wg; s_wpos[wid] = wp; s_wbin[wid] = wbin; s_wP0[wid] = wP0; s_wP1[wid] = wP1;
+            if (wid == 0 && lo == 0) { s_T0 = T0; s_T1 = T1; }  // m >= 1: warp 0 always scanned position 0
+        }
+        __syncthreads();
+        if (lo == 0) {
+            T0 = s_T0; T1 = s_T1;
+            t0 = T0 & 0xFFFFu; t1 = T0 >> 16; t2 = T1 & 0xFFFFu; t3 = T1 >> 16; N = t0 + t1 + t2 + t3;
+            const bool pure = t0 == N || t1 == N || t2 == N || t3 == N;
+            stop = stop_rule(g, N, t.depth, pure);  // only a tree root can arrive unchecked
+            if (stop) break;
+        }
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {  // max gain; ties -> the feature drawn first (lowest position), then its lowest bin
+        for (int w = 0; w < WARPS; ++w) {
             const uint32_t p = s_wpos[w];
-            if (p != 0xFFFFFFFFu && (s_wgain[w] > best_gain || (s_wgain[w] == best_gain && p < best_pos))) {
+            if (p != 0xFFFFFFFFu && (lo ? p < best_pos : (s_wgain[w] > best_gain || (s_wgain[w] == best_gain && p < best_pos)))) {
                 best_gain = s_wgain[w]; best_pos = p; best_bin = s_wbin[w]; bestP0 = s_wP0[w]; bestP1 = s_wP1[w]; found = true;
             }
         }
-        if (!found) {
-            // fallback (rare): no valid split among the first m features -- warp 0 continues the draw one position at a time
-            if (wid == 0) {
-                uint4 rnd = make_uint4(0, 0, 0, 0);
-                for (int i = m; i < d; ++i) {
-                    if (lane == 0) {
-                        if (i == m || (i & 3) == 0)
-                            rnd = philox4x32_10(t.begin, t.depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);
-                        const int j = i + (int)mulhi32(pick4(rnd, i & 3), (uint32_t)(d - i));
-                        const uint16_t fj = s_perm[j];
-                        s_perm[j] = s_perm[i];
-                        s_perm[i] = fj;
-                        if (i == m) atomicAdd(&g.stats->fallback, 1ull);
-                    }
-                    __syncwarp();
-                    double bg; uint32_t bb, P0 = 0, P1 = 0, X0, X1;
-                    feature((uint32_t)i, bg, bb, P0, P1, X0, X1);
-                    if (bb != 0xFFFFFFFFu) {
-                        if (lane == 0) { s_fb = (uint32_t)i + 1u; s_fbgain = bg; s_fbbin = bb; s_fbP0 = P0; s_fbP1 = P1; }
-                        break;
-                    }
-                }
+        if (found || hi >= (uint32_t)d) break;
+        lo = hi; hi = min((uint32_t)d, hi + WARPS);
+        if (tid == 0) {  // deal the next positions (Philox block i >> 2 holds the draws of positions 4 (i >> 2) ..)
+            uint4 rnd = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = lo; i < hi; ++i) {
+                if (i == lo || (i & 3u) == 0u) rnd = philox4x32_10(t.begin, t.depth, td.gid, TST_PURPOSE_FEAT | ((i >> 2) << 8), g.k0, g.k1);
+                const uint32_t jj = i + mulhi32(pick4(rnd, i & 3u), (uint32_t)d - i);
+                const uint16_t fj = s_perm[jj];
+                s_perm[jj] = s_perm[i];
+                s_perm[i] = fj;
             }
-            __syncthreads();
-            if (s_fb) { found = true; best_gain = s_fbgain; best_pos = s_fb - 1u; best_bin = s_fbbin; bestP0 = s_fbP0; bestP1 = s_fbP1; }
+            if (lo == (uint32_t)m) atomicAdd(&g.stats->fallback, 1ull);
         }
+        __syncthreads();
     }
     if (tid == 0) {
         s_tot[0] = t0; s_tot[1] = t1; s_tot[2] = t2; s_tot[3] = t3;
