@@ -288,10 +288,21 @@ __device__ __forceinline__ void queue_push(Task* q, uint32_t* count, uint32_t ca
     if (i < cap) q[i] = t; else st->error = 2;
 }
 
-// a node of `rows` <= mid_max rows: into the queue of its size class, if that class is on (<= 128 rows x 255 < 2^16: always packable)
-__device__ __forceinline__ bool mid_class_push(const GrowCtx& g, uint32_t rows, const Task& t) {
-    const int c = rows <= g.midc_max[0] ? 0 : (rows <= g.midc_max[1] ? 1 : -1);
-    if (c < 0) return false;
-    queue_push(g.qmidc_next[c], g.qmidc_next_count[c], g.qbig_cap, g.stats, t);
-    return true;
+// The queue of a node of `rows` > tiny_max distinct rows that weighs `weight` (an upper bound will do): warp per subtree, CTA per
+// subtree (opt-in), a size class of the warp-per-node tier, four warps per node, CTA per node, or the warp-per-node tier.  The
+// queue is SELECTED and pushed to once: the callers inline this, and eight copies of the 32-byte task store were 180 instructions.
+__device__ __forceinline__ void route_push(const GrowCtx& g, uint32_t rows, uint32_t weight, const Task& t) {
+    const bool light = weight <= 65535u;  // fits the packed 16-bit class counts
+    Task* q = g.qnext;
+    uint32_t* cnt = g.qnext_count;
+    uint32_t cap = g.qbig_cap;
+    if (rows <= SMALL_MAX) { q = g.qsmall; cnt = g.qsmall_count; cap = g.qsmall_cap; }
+    else if (rows <= g.sub_max && light) { q = g.qsub; cnt = g.qsub_count; }
+    else if (rows <= g.mid_max) {
+        if (rows <= g.midc_max[0]) { q = g.qmidc_next[0]; cnt = g.qmidc_next_count[0]; }  // (<= 128 rows x 255 < 2^16: always packable)
+        else if (rows <= g.midc_max[1]) { q = g.qmidc_next[1]; cnt = g.qmidc_next_count[1]; }
+        else if (light || !g.mid_packed || g.criterion == TST_REG) { q = g.qmid_next; cnt = g.qmid_next_count; }
+        // else: too heavy for 16-bit packed counts -> CTA per node
+    } else if (rows <= g.wide_max && light) { q = g.qwide_next; cnt = g.qwide_next_count; cap = g.qwide_cap; }
+    queue_push(q, cnt, cap, g.stats, t);
 }

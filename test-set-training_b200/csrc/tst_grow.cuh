@@ -65,13 +65,7 @@ __device__ __forceinline__ void emit_split(const GrowCtx& g, const Task& t, uint
             ct.pad1 = Nc;  // the node's weight: k_grow_big picks its packed path from it
             const uint32_t cr = ce - cb;
             if (cr <= g.tiny_max) tiny_push(g, t.tree, cb, cr, t.depth + 1u, cslot, (t.depth + 1u) & 1u);  // the children sit in the buffer of their depth
-            else if (cr <= SMALL_MAX) queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
-            else if (cr <= g.sub_max && Nc <= 65535u) queue_push(g.qsub, g.qsub_count, g.qbig_cap, g.stats, ct);  // whole subtree in one CTA
-            else if (cr <= g.mid_max && mid_class_push(g, cr, ct)) {}
-            else if (cr > g.mid_max && cr <= g.wide_max && Nc <= 65535u) queue_push(g.qwide_next, g.qwide_next_count, g.qwide_cap, g.stats, ct);  // four warps per node
-            else if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
-            else if (Nc <= 65535u || !g.mid_packed) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
-            else queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);  // too heavy for 16-bit packed counts
+            else route_push(g, cr, Nc, ct);
         }
     }
     atomicAdd(&g.stats->nodes, 1ull + new_leaves);
@@ -124,10 +118,7 @@ __device__ __forceinline__ void emit_split_reg(const GrowCtx& g, const Task& t, 
             ct.pad0 = ct.pad2 = 0;
             ct.pad1 = Nc;
             if (cr <= g.tiny_max) tiny_push(g, t.tree, cb, cr, t.depth + 1u, cslot, (t.depth + 1u) & 1u);
-            else if (cr <= SMALL_MAX) queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, ct);
-            else if (cr <= g.mid_max && mid_class_push(g, cr, ct)) {}
-            else if (cr > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, ct);
-            else queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, ct);
+            else route_push(g, cr, Nc, ct);
         }
     }
     atomicAdd(&g.stats->nodes, 1ull + new_leaves);

@@ -319,13 +319,7 @@ __global__ void k_init_roots(GrowCtx g, uint32_t n_trees) {
     k.tree = t; k.begin = 0; k.end = td.n_inbag; k.depth = 0; k.slot = 0; k.pad0 = k.pad1 = k.pad2 = 0;
     if (g.rsplit && td.n_inbag > g.big_min) k.pad0 = 1;  // pre-split by k_root_hist / k_root_split
     if (td.n_inbag <= g.tiny_max) tiny_push(g, t, 0u, td.n_inbag, 0u, 0u, 0u);
-    else if (td.n_inbag <= SMALL_MAX) queue_push(g.qsmall, g.qsmall_count, g.qsmall_cap, g.stats, k);
-    else if (td.n_inbag <= g.sub_max && td.n_train <= 65535u) queue_push(g.qsub, g.qsub_count, g.qbig_cap, g.stats, k);  // tree per CTA
-    else if (td.n_inbag <= g.mid_max && mid_class_push(g, td.n_inbag, k)) {}
-    else if (td.n_inbag > g.mid_max && td.n_inbag <= g.wide_max && td.n_train <= 65535u) queue_push(g.qwide_next, g.qwide_next_count, g.qwide_cap, g.stats, k);
-    else if (td.n_inbag > g.mid_max) queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, k);
-    else if (td.n_train <= 65535u || !g.mid_packed || g.criterion == TST_REG) queue_push(g.qmid_next, g.qmid_next_count, g.qbig_cap, g.stats, k);
-    else queue_push(g.qnext, g.qnext_count, g.qbig_cap, g.stats, k);
+    else route_push(g, td.n_inbag, td.n_train, k);
 }
 
 // ---------------------------------------------------------------------------------------------
