@@ -115,7 +115,7 @@ struct tst_handle {
     DevBuf bins_cm, bins_rm, edges, n_edges;
     // per-fit scratch
     DevBuf part_count, part_start, sorted, trees, counts8, chunk_cnt, chunk_sum, entA, entB, nodes, leafc, qbig0, qbig1,
-        qmid0, qmid1, qmidc[2][2], qwide0, qwide1, qsmall, qsub, qtiny, qtiny2, imp, imp_sums, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
+        qmid0, qmid1, qmidc[2][2], qbigl[2], qwide0, qwide1, qsmall, qsub, qtiny, qtiny2, imp, imp_sums, counters, dstats, infer_parts, ghist, rsplit, y_pad, stash;
     // kept forest
     DevBuf keep_nodes, keep_leafc, keep_arenas;
     std::vector<KeptTree> kept;
@@ -150,6 +150,7 @@ struct tst_handle {
         long thin_nodes = 2048;
         int mid_classes = -1;         // size classes of the warp-per-node tier with their own queue + kernel instantiation: bit 0 = 33..64 rows
                                       // (2 row slots per lane), bit 1 = ..128 rows (4 slots); 0 = one queue for the whole tier; default: 3 for batches of >= 2^24 (tree, row) pairs, else 0
+        int big_lite = -1;            // light CTA-tier nodes (packed Gini) in their own queue + the LITE instantiation of k_grow_big: 1 on, 0 off, default: on for deep batches
         int wide_max = -1;            // largest node of the four-warps-per-node tier (0 = tier off; default 2048)
         int sub_rows = -1;            // row capacity of the CTA-per-subtree tier (<= 0 = tier off, the default)
     } knobs;
@@ -211,6 +212,7 @@ static int set_option(tst_handle* h, const std::string& nm, long v) {
     else if (nm == "SUB_ROWS") kn.sub_rows = (int)v;
     else if (nm == "WIDE_MAX") kn.wide_max = (int)v;
     else if (nm == "MID_CLASSES") kn.mid_classes = (int)v;
+    else if (nm == "BIG_LITE") kn.big_lite = (int)v;
     else return -1;
     return 0;
 }
@@ -261,7 +263,7 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize; h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     // tuning / diagnostic knobs: defaults from the environment (TST_<NAME>), read once here; tst_set_option changes them later
     for (const char* nm : {"L2_PERSIST", "TRACE", "STASH", "BIG_PACKED", "ROOT_DENSE", "TINY_MAX", "MID_MAX", "STASH_MAX", "BLIND_LEVELS",
-                           "THIN_NODES", "SUB_ROWS", "WIDE_MAX", "MID_CLASSES"}) {
+                           "THIN_NODES", "SUB_ROWS", "WIDE_MAX", "MID_CLASSES", "BIG_LITE"}) {
         const std::string env = std::string("TST_") + nm;
         if (const char* v = getenv(env.c_str())) set_option(h, nm, atol(v));
     }
@@ -277,7 +279,7 @@ extern "C" int tst_destroy(tst_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->bins_cm, &h->bins_rm, &h->edges, &h->n_edges, &h->part_count, &h->part_start, &h->sorted, &h->trees,
                       &h->counts8, &h->chunk_cnt, &h->chunk_sum, &h->entA, &h->entB, &h->nodes, &h->leafc, &h->qbig0, &h->qbig1,
-                      &h->qmid0, &h->qmid1, &h->qmidc[0][0], &h->qmidc[0][1], &h->qmidc[1][0], &h->qmidc[1][1], &h->qwide0, &h->qwide1, &h->qsmall, &h->qsub, &h->imp, &h->imp_sums, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
+                      &h->qmid0, &h->qmid1, &h->qmidc[0][0], &h->qmidc[0][1], &h->qmidc[1][0], &h->qmidc[1][1], &h->qbigl[0], &h->qbigl[1], &h->qwide0, &h->qwide1, &h->qsmall, &h->qsub, &h->imp, &h->imp_sums, &h->target16, &h->qtiny, &h->qtiny2, &h->ghist, &h->rsplit, &h->y_pad, &h->stash, &h->counters, &h->dstats, &h->infer_parts, &h->keep_nodes, &h->keep_leafc, &h->keep_arenas,
                       &h->ibp_fold, &h->ibp_votes, &h->ibp_removed, &h->pred_cm, &h->pred_rm, &h->sort_a, &h->sort_b, &h->sort_dk, &h->gather};
     for (DevBuf* b : bufs) b->release();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -296,6 +298,7 @@ extern "C" int tst_destroy(tst_handle* h) {
 static int set_kernel_attrs(tst_handle* h) {
     if (h->attrs_set) return 0;
     CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
     CK(cudaFuncSetAttribute(k_grow_big<BIG_THREADS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BIG_SMEM_BUDGET + 40 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -623,10 +626,10 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const uint64_t qbig_per = n_cap / 32 + 2, qsmall_per = n_cap / std::max<uint64_t>(2, tiny_eff + 1) + 2, qtiny_per = n_cap / 2 + 2;
     const size_t arena_bytes = node_stride * sizeof(uint2) + leafc_stride * 4;
     const bool want_stash = kn.stash;  // see use_stash below
-    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (9 * qbig_per + 2 * qwide_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
+    const size_t work_bytes = n_pad + 2 * (size_t)n_chunks * 4 + (want_stash ? 3 : 2) * n_cap * sizeof(Entry) + (11 * qbig_per + 2 * qwide_per + qsmall_per) * sizeof(Task) + 2 * qtiny_per * 16 + sizeof(TreeDesc);
     const bool keep = prm->keep_forest != 0;
     size_t reclaim = h->counts8.cap + h->chunk_cnt.cap + h->chunk_sum.cap + h->entA.cap + h->entB.cap + h->nodes.cap + h->leafc.cap +
-                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qmidc[0][0].cap + h->qmidc[0][1].cap + h->qmidc[1][0].cap + h->qmidc[1][1].cap + h->qwide0.cap + h->qwide1.cap + h->qsmall.cap + h->qsub.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
+                     h->qbig0.cap + h->qbig1.cap + h->qmid0.cap + h->qmid1.cap + h->qmidc[0][0].cap + h->qmidc[0][1].cap + h->qmidc[1][0].cap + h->qmidc[1][1].cap + h->qbigl[0].cap + h->qbigl[1].cap + h->qwide0.cap + h->qwide1.cap + h->qsmall.cap + h->qsub.cap + h->qtiny.cap + h->qtiny2.cap + h->keep_nodes.cap + h->keep_leafc.cap + h->stash.cap;
     const size_t per_tree = work_bytes + (keep ? 0 : arena_bytes);
     size_t B = std::min<size_t>(total_trees, 4096);
     if (prm->trees_in_flight > 0) B = std::min<size_t>(B, (size_t)prm->trees_in_flight);
@@ -655,6 +658,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     ENSURE(h->qmid0, B * qbig_per * sizeof(Task));
     ENSURE(h->qmid1, B * qbig_per * sizeof(Task));
     for (int c = 0; c < 2; ++c) for (int p = 0; p < 2; ++p) ENSURE(h->qmidc[c][p], B * qbig_per * sizeof(Task));
+    for (int p = 0; p < 2; ++p) ENSURE(h->qbigl[p], B * qbig_per * sizeof(Task));
     ENSURE(h->qsmall, B * qsmall_per * sizeof(Task));
     ENSURE(h->qsub, B * qbig_per * sizeof(Task));
     ENSURE(h->qwide0, B * qwide_per * sizeof(Task));
@@ -718,7 +722,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
     // [2p], [2p+1] big / mid queue counts of parity p, [4] small, [5] tiny, [6 + r] tiny size histogram (r <= 6), [16 + p] four-warps-per-node
-    // queue of parity p, [22 + 2c + p] size class c of the warp-per-node tier, [20] subtree queue, [32 + r] tiny cursors
+    // queue of parity p, [22 + 2c + p] size class c of the warp-per-node tier, [26 + p] light nodes of the CTA tier, [20] subtree queue, [32 + r] tiny cursors
     uint32_t* counters = h->counters.as<uint32_t>();
     g.qsmall_count = counters + 4;
     g.qtiny = h->qtiny.p; g.qtiny_count = counters + 5;
@@ -738,6 +742,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     // ~10M in-bag rows per batch; 5 x 100 trees on 5k rows lose 0.5 ms of 3.3 to the extra launches), so "auto" looks at the batch.
     const bool deep_levels = (uint64_t)B * n_cap >= (1ull << 24);
     const int mid_classes = (mid_packed && g.mid_max > SMALL_MAX) ? (kn.mid_classes >= 0 ? kn.mid_classes & 3 : (deep_levels ? 3 : 0)) : 0;
+    // light nodes of the CTA tier (weight < 2^16: levels 5+ of a 1M-row tree) run the packed-Gini-only instantiation, 4 CTAs per SM
+    g.bigl = (!reg && packed_ok && g.big_packed && g.big_tile && (kn.big_lite >= 0 ? kn.big_lite != 0 : deep_levels)) ? 1u : 0u;
+    const size_t bigl_smem = (8 * (size_t)BIGP_FS + (size_t)BIG_THREADS * ((h->dstride >> 2) + 1)) * 4;
     size_t midc_smem[2];
     for (int c = 0; c < 2; ++c) {
         g.midc_max[c] = (mid_classes >> c & 1) ? 32u * MIDC_R[c] : 0u;
@@ -827,6 +834,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             g.qmid_next = h->qmid0.as<Task>(); g.qmid_next_count = counters + 1;
             g.qwide_next = h->qwide0.as<Task>(); g.qwide_next_count = counters + 16;
             for (int c = 0; c < 2; ++c) { g.qmidc_next[c] = h->qmidc[c][0].as<Task>(); g.qmidc_next_count[c] = counters + 22 + 2 * c; }
+            g.qbigl_next = h->qbigl[0].as<Task>(); g.qbigl_next_count = counters + 26;
             k_init_roots<<<(nb + 127) / 128, 128, 0, st>>>(g, nb);
             CKL();
             h->stats.kernel_launches += 5;
@@ -847,13 +855,13 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
         bool small_started = false, tiny_timed = false, sub_timed = false;
         const int blind_levels = kn.blind_levels;
         const uint64_t thin_nodes = (uint64_t)kn.thin_nodes;  // a level with at most this many nodes starts a group of blind levels
-        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1], nwide = h->h_pinned[16], nmidc[2] = {h->h_pinned[22], h->h_pinned[24]};
+        uint32_t nbig = h->h_pinned[0], nmid = h->h_pinned[1], nwide = h->h_pinned[16], nmidc[2] = {h->h_pinned[22], h->h_pinned[24]}, nbigl = h->h_pinned[26];
         double tr_gap = 0; int tr_groups = 0;
-        while (nbig > 0 || nmid > 0 || nwide > 0 || nmidc[0] > 0 || nmidc[1] > 0) {
+        while (nbig > 0 || nmid > 0 || nwide > 0 || nmidc[0] > 0 || nmidc[1] > 0 || nbigl > 0) {
             const auto t_level = now();
-            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid + nwide + nmidc[0] + nmidc[1] <= thin_nodes;
+            const bool thin = blind_levels > 1 && (uint64_t)nbig + nmid + nwide + nmidc[0] + nmidc[1] + nbigl <= thin_nodes;
             const int J = thin ? blind_levels : 1;
-            uint64_t ub_big = nbig, ub_mid = nmid, ub_wide = nwide, ub_midc[2] = {nmidc[0], nmidc[1]};
+            uint64_t ub_big = nbig, ub_mid = nmid, ub_wide = nwide, ub_midc[2] = {nmidc[0], nmidc[1]}, ub_bigl = nbigl;
             for (int j = 0; j < J; ++j) {
                 Task* qcur = cur ? h->qbig1.as<Task>() : h->qbig0.as<Task>();
                 Task* qmcur = cur ? h->qmid1.as<Task>() : h->qmid0.as<Task>();
@@ -875,6 +883,12 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                     cmc[c] = j ? counters + 22 + 2 * c + cur : nullptr;
                 }
                 if (g.wide_max) CK(cudaMemsetAsync(g.qwide_next_count, 0, 4, st));
+                Task* qblcur = h->qbigl[cur].as<Task>();
+                g.qbigl_next = h->qbigl[cur ^ 1].as<Task>();
+                g.qbigl_next_count = counters + 26 + (cur ^ 1);
+                if (g.bigl) CK(cudaMemsetAsync(g.qbigl_next_count, 0, 4, st));
+                const uint32_t gbl = g.bigl ? (uint32_t)std::min<uint64_t>(ub_bigl, g.qbig_cap) : 0u;
+                const uint32_t* cbl = j ? counters + 26 + cur : nullptr;
                 const uint32_t gw = g.wide_max ? (uint32_t)std::min<uint64_t>(ub_wide, g.qwide_cap) : 0u;
                 const uint32_t* cw = j ? counters + 16 + cur : nullptr;
                 const uint32_t gb = (uint32_t)std::min<uint64_t>(ub_big, g.qbig_cap);
@@ -886,6 +900,11 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                     if (g.criterion == 1u) k_grow_big<BIG_THREADS, 1><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
                     else if (reg) k_grow_big<BIG_THREADS, 2><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
                     else k_grow_big<BIG_THREADS><<<gb, BIG_THREADS, big_smem, st>>>(g, qcur, gb, cb);
+                    CKL();
+                    h->stats.kernel_launches++; h->stats.launches_grow_big++;
+                }
+                if (gbl) {
+                    k_grow_big<BIG_THREADS, 0, true><<<gbl, BIG_THREADS, bigl_smem, st>>>(g, qblcur, gbl, cbl);
                     CKL();
                     h->stats.kernel_launches++; h->stats.launches_grow_big++;
                 }
@@ -922,8 +941,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
                 CK(cudaEventRecord(h->ev_lvl[j][2], st));
                 h->stats.levels++;
                 cur ^= 1;
-                const uint64_t nb2 = 2 * ub_big, nw2 = 2 * (ub_big + ub_wide), nm2 = 2 * (ub_big + ub_wide + ub_mid), nmc = 2 * (ub_big + ub_wide + ub_mid + ub_midc[0] + ub_midc[1]);
-                ub_big = nb2; ub_wide = nw2; ub_mid = nm2; ub_midc[0] = ub_midc[1] = nmc;  // (a child of any queued node can land in either class)
+                const uint64_t ub_cta = ub_big + ub_bigl;  // parents of the CTA tier, either queue
+                const uint64_t nb2 = 2 * ub_big, nbl2 = 2 * ub_cta, nw2 = 2 * (ub_cta + ub_wide), nm2 = 2 * (ub_cta + ub_wide + ub_mid), nmc = 2 * (ub_cta + ub_wide + ub_mid + ub_midc[0] + ub_midc[1]);
+                ub_big = nb2; ub_bigl = nbl2; ub_wide = nw2; ub_mid = nm2; ub_midc[0] = ub_midc[1] = nmc;  // (a child of any queued node can land in either class)
                 if (++level_guard > n_cap + 8) return fail(TST_ERR_STATE, "tree growth did not terminate");
             }
             CK(cudaMemcpyAsync(h->h_pinned, counters, 128, cudaMemcpyDeviceToHost, st));
@@ -943,7 +963,8 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             nmid = h->h_pinned[2 * cur + 1];
             nwide = g.wide_max ? h->h_pinned[16 + cur] : 0u;
             for (int c = 0; c < 2; ++c) nmidc[c] = g.midc_max[c] ? h->h_pinned[22 + 2 * c + cur] : 0u;
-            if (nbig > g.qbig_cap || nmid > g.qbig_cap || nwide > g.qwide_cap || nmidc[0] > g.qbig_cap || nmidc[1] > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
+            nbigl = g.bigl ? h->h_pinned[26 + cur] : 0u;
+            if (nbigl > g.qbig_cap || nbig > g.qbig_cap || nmid > g.qbig_cap || nwide > g.qwide_cap || nmidc[0] > g.qbig_cap || nmidc[1] > g.qbig_cap) return fail(TST_ERR_OVERFLOW, "node queue overflowed");
         }
         tr_levels = ms_since(t_batch);
         phase.next("tst subtree tiers + inference");

@@ -165,6 +165,10 @@ struct GrowCtx {
     uint32_t wide_max; // 0 disables the tier
     // size classes of the warp-per-node tier: nodes of SMALL_MAX < rows <= midc_max[0] and of midc_max[0] < rows <= midc_max[1] have their own
     // (dense) queues, served by instantiations of k_grow_mid4 with 2 and 4 row slots per lane (more resident warps); 0 = class off
+    // CTA-per-node nodes that weigh < 2^16 (packed Gini) have their own queue when `bigl` is set: the LITE instantiation of k_grow_big
+    Task* qbigl_next;
+    uint32_t* qbigl_next_count;
+    uint32_t bigl;
     Task* qmidc_next[2];
     uint32_t* qmidc_next_count[2];
     uint32_t midc_max[2];
@@ -304,5 +308,6 @@ __device__ __forceinline__ void route_push(const GrowCtx& g, uint32_t rows, uint
         else if (light || !g.mid_packed || g.criterion == TST_REG) { q = g.qmid_next; cnt = g.qmid_next_count; }
         // else: too heavy for 16-bit packed counts -> CTA per node
     } else if (rows <= g.wide_max && light) { q = g.qwide_next; cnt = g.qwide_next_count; cap = g.qwide_cap; }
+    else if (light && g.bigl && t.pad0 == 0u) { q = g.qbigl_next; cnt = g.qbigl_next_count; }  // (a pre-split root keeps the generic kernel)
     queue_push(q, cnt, cap, g.stats, t);
 }

@@ -394,8 +394,13 @@ __device__ __forceinline__ void fetch_rows32(const uint8_t* __restrict__ bins, u
 #define BIG_MINB 3
 #endif
 // ---------------------------------------------------------------------------------------------
-template <int THREADS, int CRIT = 0>  // CRIT: 0 Gini, 1 squared error on ordinal levels, 2 squared error on the 16-bit target (own instantiations: the Gini one keeps its registers)
-__global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
+#ifndef BIGL_MINB
+#define BIGL_MINB 4
+#endif
+// LITE: the packed-Gini nodes only (<= 4 classes, weight < 2^16, row tile, one batch of <= 8 features, no stash, no pre-split
+// roots), from their own queue: every generic branch folds away, which is what lets the instantiation fit more CTAs per SM.
+template <int THREADS, int CRIT = 0, bool LITE = false>  // CRIT: 0 Gini, 1 squared error on ordinal levels, 2 squared error on the 16-bit target (own instantiations: the Gini one keeps its registers)
+__global__ void __launch_bounds__(THREADS, LITE ? BIGL_MINB : BIG_MINB) k_grow_big(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks, const uint32_t* __restrict__ ntasks_dev) {
     constexpr int NW = THREADS / 32;
     constexpr bool MSE = CRIT == 1, REG = CRIT == 2;
     __shared__ unsigned long long s_fP[32], s_totP, s_bestP;  // criterion 2: left cell of each feature's best split, node total, best split's left cell
@@ -425,19 +430,19 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     uint32_t* leafc = g.leafc + (uint64_t)td.arena * g.leafc_stride;
     const uint8_t* __restrict__ bins = g.bins_rm;
     const uint32_t dstride = g.dstride;
-    const bool use_tile = g.big_tile != 0;
+    const bool use_tile = LITE || g.big_tile != 0;
     // a node that weighs < 2^16 (its parent wrote the weight into the task) uses the packed histogram and scan
-    const bool packed = REG || (!MSE && g.big_packed != 0u && use_tile && C <= 4 && g.MB <= 8 && t.pad1 != 0u && t.pad1 <= 65535u);
+    const bool packed = LITE || REG || (!MSE && g.big_packed != 0u && use_tile && C <= 4 && g.MB <= 8 && t.pad1 != 0u && t.pad1 <= 65535u);
     const uint32_t HFS = packed ? BIGP_FS : (uint32_t)g.FS;  // histogram words per feature
     const uint32_t pitch = (dstride >> 2) + 1u;
-    uint32_t* s_tile = s_hist + g.MB * g.HFS_max + wid * 32u * pitch;  // this warp's rows (the histogram region holds either layout)
+    uint32_t* s_tile = s_hist + (LITE ? 8u * BIGP_FS : (uint32_t)(g.MB * g.HFS_max)) + wid * 32u * pitch;  // this warp's rows (the histogram region holds either layout)
 
     for (int f = tid; f < d; f += THREADS) s_perm[f] = (uint16_t)f;
     if (tid == 0) { s_found = 0; s_bgain = -1.0; s_bkey = 0xFFFFFFFFu; s_stop = 0; s_sj = 0xFFFFFFFFu; s_ymin = 0xFFFFFFFFu; s_ymax = 0u; s_totP = 0ull; }
     __syncthreads();
 
     // roots already split by the dense column-major kernels (tst_root.cuh) only need the partition below
-    const bool presplit = t.pad0 == 1u && g.rsplit != nullptr && (g.rsplit[t.tree].state == 1u || g.rsplit[t.tree].state == 2u);
+    const bool presplit = !LITE && t.pad0 == 1u && g.rsplit != nullptr && (g.rsplit[t.tree].state == 1u || g.rsplit[t.tree].state == 2u);
     if (presplit) {
         if (tid == 0) {
             const RootSplit& R = g.rsplit[t.tree];
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     while (pos < d) {
         if (pos >= m && s_found) break;
         const bool primary = pos < m;
-        const int nb = min(g.MB, (primary ? m : d) - pos);
+        const int nb = min(LITE ? 8 : g.MB, (primary ? m : d) - pos);
         // ---- per-node feature draw: partial Fisher-Yates keyed by (begin, depth, tree)
         if (tid == 0) {
             uint4 rnd = make_uint4(0, 0, 0, 0);
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
 
         // ---- class histogram: hist[j][bin][class] += multiplicity (SK/.../histogram.pyx:336-425 pattern)
         if (use_tile && nb <= 8) {
-            uint2* stash_w = (g.stash != nullptr && pos == 0 && t.end - t.begin <= g.stash_max_rows) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
+            uint2* stash_w = (!LITE && g.stash != nullptr && pos == 0 && t.end - t.begin <= g.stash_max_rows) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
             uint32_t featr[8];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) featr[jj] = jj < nb ? s_feat[jj] : 0u;
@@ -602,7 +607,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
                     uint32_t key = (s_feat[j] << 8) | s_fbin[j];  // ties: the feature drawn first (positions are visited in order), then lowest bin
                     if (s_fgain[j] > s_bgain) {
                         s_bgain = s_fgain[j]; s_bkey = key; s_newj = j; s_found = 1;
-                        s_sj = (pos == 0 && g.stash != nullptr && use_tile && nb <= 8 && t.end - t.begin <= g.stash_max_rows) ? (uint32_t)j : 0xFFFFFFFFu;
+                        s_sj = (!LITE && pos == 0 && g.stash != nullptr && use_tile && nb <= 8 && t.end - t.begin <= g.stash_max_rows) ? (uint32_t)j : 0xFFFFFFFFu;
                     }
                 }
             } else {
@@ -662,7 +667,7 @@ __global__ void __launch_bounds__(THREADS, BIG_MINB) k_grow_big(GrowCtx g, const
     // right rows from the back; tree structure depends only on the sets, not on the order.
     const uint32_t bf = s_bkey >> 8, bb = s_bkey & 0xFFu;
     const uint32_t sj = s_sj;
-    const uint2* stash_r = (g.stash != nullptr && sj != 0xFFFFFFFFu) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
+    const uint2* stash_r = (!LITE && g.stash != nullptr && sj != 0xFFFFFFFFu) ? g.stash + (uint64_t)t.tree * g.n_cap : nullptr;
     uint32_t lbase = 0, rbase = 0;
     int par = 0;
     constexpr int PU = 4;  // chunks per barrier

@@ -437,14 +437,14 @@ def test_random_large_configurations_bit_exact(eng, seed):
     if rng.random() < 0.4:
         pk["max_features"] = int(rng.integers(1, d + 1))
     knobs = dict(BLIND_LEVELS=int(rng.choice([1, 2, 4, 8])), THIN_NODES=int(rng.choice([0, 64, 2048, 100000])),
-                 WIDE_MAX=int(rng.choice([0, 600, 1024])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])), MID_CLASSES=int(rng.integers(0, 4)))
+                 WIDE_MAX=int(rng.choice([0, 600, 1024])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])), MID_CLASSES=int(rng.integers(0, 4)), BIG_LITE=int(rng.integers(0, 2)))
     for kk, v in knobs.items():
         eng.set_option(kk, v)
     try:
         T = int(rng.integers(2, 6))
         gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, T, C, seed=seed, keep=True, **pk)
     finally:
-        for kk, v in dict(BLIND_LEVELS=4, THIN_NODES=2048, WIDE_MAX=-1, MID_MAX=-1, TINY_MAX=-1, MID_CLASSES=-1).items():
+        for kk, v in dict(BLIND_LEVELS=4, THIN_NODES=2048, WIDE_MAX=-1, MID_MAX=-1, TINY_MAX=-1, MID_CLASSES=-1, BIG_LITE=-1).items():
             eng.set_option(kk, v)
     assert np.array_equal(gv, ov), (n, d, C, card, k, pk, knobs)
     check_stats(gst, ost)
@@ -761,6 +761,34 @@ def test_continuous_squared_error_bit_exact(eng, n, d, k, mf, ties, pk):
         gn, gc = eng.export_tree(part, t, 2)
         ot = forest.tree(part, t)
         compare_tree(gn, gc, ot.nodes, ot.counts, f"continuous regression tree({part},{t})")
+
+
+@pytest.mark.parametrize("n,d,C,mf,pk", [(30000, 16, 4, "sqrt", {}), (9000, 12, 2, 3, {}), (20000, 40, 3, 12, {}), (12000, 9, 4, None, dict(min_samples_leaf=9, min_samples_split=40)),
+                                         (15000, 20, 4, 1, dict(max_depth=7)), (8000, 64, 4, "sqrt", {})])
+def test_cta_tier_light_queue_bit_exact(eng, request, n, d, C, mf, pk):
+    """BIG_LITE: CTA-tier nodes that weigh < 2^16 leave emit_split through their own queue and run the packed-Gini-only instantiation
+    of k_grow_big (more than 8 features per node in batches of 8, fallback draws on constant columns, depth / leaf-size limits);
+    heavier nodes and pre-split roots keep the generic kernel.  WIDE_MAX = 0 sends every node above 256 rows there."""
+    rng = np.random.default_rng(n + d)
+    bins = rng.integers(0, 256, (d, n)).astype(np.uint8)
+    bins[1] = 7                      # constant column: fallback draws
+    bins[2] = bins[2] & 1            # two-valued column
+    y = ((bins[0].astype(int) + bins[3]) * C // 511).clip(0, C - 1).astype(np.uint8)
+    flip = rng.random(n) < 0.3
+    y[flip] = rng.integers(0, C, int(flip.sum()))
+    k = 2
+    fold = H.assign_folds(y, np.ones(n, np.uint8), k, C)
+    for wide in (-1, 0):
+        eng.set_option("BIG_LITE", 1)
+        eng.set_option("WIDE_MAX", wide)
+        request.addfinalizer(lambda: (eng.set_option("BIG_LITE", -1), eng.set_option("WIDE_MAX", -1)))
+        gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, 3, C, seed=9, keep=True, max_features=mf, **pk)
+        assert np.array_equal(gv, ov), (wide,)
+        check_stats(gst, ost)
+        assert gst["row_visits_big"] > 0
+        gn, gc = eng.export_tree(1, 2, C)
+        ot = forest.tree(1, 2)
+        compare_tree(gn, gc, ot.nodes, ot.counts, f"light queue wide={wide}")
 
 
 @pytest.mark.parametrize("classes", [0, 1, 2, 3])
