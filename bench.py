@@ -140,13 +140,17 @@ def measured_hbm_peak():
 
 
 def dram_traffic_per_launch(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_final_traffic.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")) as f:
-            e = json.load(f).get(kernel, {})
-            return e.get("dram_bytes_per_launch"), e.get("captured")
-    except Exception:
-        return None, None
+    """dram bytes per launch of `kernel` from the committed ncu capture of the current build's launch structure
+    (profiles/r02_final_traffic.json, made by tools/traffic_summary.py; the round-1 capture as a fallback)."""
+    for name in ("r02_final_traffic.json", "r01_final_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                e = json.load(f).get(kernel, {})
+            if e.get("dram_bytes_per_launch") is not None:
+                return e.get("dram_bytes_per_launch"), e.get("captured")
+        except Exception:
+            pass
+    return None, None
 
 
 # --------------------------------------------------------------------------------------------- reference arm
