@@ -62,6 +62,61 @@ __device__ __forceinline__ void warp_draw_primary(uint16_t* s_perm, int d, int m
     __syncwarp();
 }
 
+// The same draw without the permutation array, for m <= DRAW_SPARSE_MAX: lane i < m owns position i.  Its swap partner is
+// j_i = i + mulhi(v_i, d - i); the feature it ends up with is whatever sat at position j_i before step i, i.e. u_k of the LATEST
+// earlier step k that wrote there (j_k == j_i), else j_i itself, where u_k (the value position k held before step k) is found by
+// pointer jumping along "latest earlier step that wrote position k".  No shared-memory round trips and no serial walk by lane 0:
+// ~145 warp instructions instead of ~230, and a dependency chain of log2(m) shuffles instead of m swaps.  Writes s_perm[0..m);
+// returns j_i so that warp_draw_materialize can rebuild the whole permutation before a fallback draw continues it (rare).
+#define DRAW_SPARSE_MAX 16
+__device__ __forceinline__ uint32_t warp_draw_first(uint16_t* s_perm, int d, int m, uint32_t begin, uint32_t depth, uint32_t gid,
+                                                    uint32_t k0, uint32_t k1, uint32_t lane) {
+    if (m > DRAW_SPARSE_MAX) {
+        for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
+        __syncwarp();
+        warp_draw_primary(s_perm, d, m, begin, depth, gid, k0, k1, lane);
+        return 0u;
+    }
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if ((int)lane < ((m + 3) >> 2)) rnd = philox4x32_10(begin, depth, gid, TST_PURPOSE_FEAT | (lane << 8), k0, k1);
+    const uint32_t src = lane >> 2;
+    const uint32_t vx = __shfl_sync(0xffffffffu, rnd.x, src), vy = __shfl_sync(0xffffffffu, rnd.y, src);
+    const uint32_t vz = __shfl_sync(0xffffffffu, rnd.z, src), vw = __shfl_sync(0xffffffffu, rnd.w, src);
+    const uint32_t v = (lane & 2u) ? ((lane & 1u) ? vw : vz) : ((lane & 1u) ? vy : vx);
+    const bool mine = (int)lane < m;
+    const uint32_t j = mine ? lane + mulhi32(v, (uint32_t)d - lane) : 0xFFFFFFFFu;
+    uint32_t K = lane, Kj = 0xFFFFFFFFu;  // latest earlier step that wrote my position / my partner's position
+    for (int k = 0; k + 1 < m; ++k) {
+        const uint32_t jk = __shfl_sync(0xffffffffu, j, k);
+        if ((uint32_t)k < lane) {
+            if (jk == lane) K = (uint32_t)k;
+            if (jk == j) Kj = (uint32_t)k;
+        }
+    }
+    uint32_t u = K;  // follow the chain to the step whose position nobody wrote before: it held its own index
+    for (int s = 1; s < m; s <<= 1) u = __shfl_sync(0xffffffffu, u, u);
+    const uint32_t uk = __shfl_sync(0xffffffffu, u, Kj & 31u);
+    if (mine) s_perm[lane] = (uint16_t)(Kj != 0xFFFFFFFFu ? uk : j);
+    __syncwarp();
+    return j;
+}
+
+// s_perm[0..d) := the permutation after the m swaps of warp_draw_first (what warp_draw_primary would have left).
+__device__ __forceinline__ void warp_draw_materialize(uint16_t* s_perm, int d, int m, uint32_t j, uint32_t lane) {
+    if (m > DRAW_SPARSE_MAX) return;  // dealt on the array already
+    for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
+    __syncwarp();
+    for (int i = 0; i < m; ++i) {
+        const uint32_t ji = __shfl_sync(0xffffffffu, j, i);
+        if (lane == 0) {
+            const uint16_t fj = s_perm[ji];
+            s_perm[ji] = s_perm[i];
+            s_perm[i] = fj;
+        }
+    }
+    __syncwarp();
+}
+
 // Warp argmax of (gain desc, key asc) with three REDUX instead of a 64-bit shuffle butterfly.  Valid gains are
 // positive doubles (>= 2), whose bit patterns order like unsigned integers; key == 0xFFFFFFFF marks "no candidate".
 __device__ __forceinline__ void warp_argmax_redux(double& gn, uint32_t& key) {

@@ -214,10 +214,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_grow_mid4(GrowCtx g, const
         uint32_t i = lane + 32u * k;
         e[k] = i < r ? ent_load(ent_in + t.begin + i) : make_uint2(0u, 0u);
     }
-    for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
-    __syncwarp();
     uint4 rnd = make_uint4(0, 0, 0, 0);
-    warp_draw_primary(s_perm, d, m, t.begin, t.depth, td.gid, g.k0, g.k1, lane);  // the first m positions of the node's draw
+    const uint32_t draw_j = warp_draw_first(s_perm, d, m, t.begin, t.depth, td.gid, g.k0, g.k1, lane);  // the first m positions of the node's draw
 
     bool found = false, stop = false;
     double best_gain = -1.0;
@@ -238,6 +236,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_grow_mid4(GrowCtx g, const
     for (int i = 0; i < d; ++i) {
         if (i >= m && found) break;
         if (i >= m) {  // fallback: one more position of the draw, no prefetch possible
+            if (i == m) warp_draw_materialize(s_perm, d, m, draw_j, lane);
             if (lane == 0) {
                 if (i == m || (i & 3) == 0)
                     rnd = philox4x32_10(t.begin, t.depth, td.gid, TST_PURPOSE_FEAT | ((uint32_t)(i >> 2) << 8), g.k0, g.k1);

@@ -117,9 +117,7 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                 const unsigned long long cw_g = !gvalid ? 0ull : REG ? ((unsigned long long)ent_w(e_g) | ((unsigned long long)(ent_w(e_g) * ent_cls(e_g)) << 13))
                                                                      : ((unsigned long long)ent_w(e_g) << (13u * ent_cls(e_g)));
                 const uint8_t* __restrict__ rowp = bins + (uint64_t)e_g.x * dstride;
-                for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
-                __syncwarp();
-                warp_draw_primary(s_perm, d, m, abs_begin, depth, td.gid, g.k0, g.k1, lane);
+                const uint32_t draw_j = warp_draw_first(s_perm, d, m, abs_begin, depth, td.gid, g.k0, g.k1, lane);
                 // bin <= b  <=>  high word of P <= (b << 20) | 0xFFFFF (bits 32..51 hold class counts)
                 uint4 rnd = make_uint4(0, 0, 0, 0);
                 for (int pos0 = 0; pos0 < d;) {
@@ -127,6 +125,7 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                     const int limit = pos0 < m ? m : d;
                     const int nfc = min((int)nf, limit - pos0);
                     if (pos0 >= m) {  // fallback: extend the draw lazily (rare)
+                        if (pos0 == m) warp_draw_materialize(s_perm, d, m, draw_j, lane);
                         if (lane == 0) {
                             for (int i = pos0; i < pos0 + nfc; ++i) {
                                 if (i == pos0 || (i & 3) == 0)

@@ -61,11 +61,8 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
     uint32_t* s_bal = (uint32_t*)(s_perm + ((d + 1) / 2) * 2) + wid * MAXCH;
 
     for (uint32_t i = tid; i < r; i += THREADS) s_ent[i] = ent_load(ent_in + t.begin + i);
-    if (wid == 0) {
-        for (int f = lane; f < d; f += 32) s_perm[f] = (uint16_t)f;
-        __syncwarp();
-        warp_draw_primary(s_perm, d, m, t.begin, t.depth, td.gid, g.k0, g.k1, lane);
-    }
+    uint32_t draw_j = 0;
+    if (wid == 0) draw_j = warp_draw_first(s_perm, d, m, t.begin, t.depth, td.gid, g.k0, g.k1, lane);
     __syncthreads();
 
     // ---- the rows are fetched ONCE: 32 rows per warp and step through a row tile in the warp's histogram space (16-byte
@@ -78,7 +75,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
         const uint32_t pitch = (dstride >> 2) + 1u;
         uint32_t featr[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) featr[j] = s_perm[min(j, d - 1)];
+        for (int j = 0; j < 8; ++j) featr[j] = s_perm[min(j, m - 1)];  // (positions >= m are not dealt: their bytes are never used)
         const uint8_t* trow = (const uint8_t*)(s_hist + lane * pitch);
         for (uint32_t c0 = wid * 32u; c0 < r; c0 += THREADS) {
             const uint32_t i = c0 + lane;
@@ -174,6 +171,7 @@ __global__ void __launch_bounds__(WARPS * 32, WIDE_MINB) k_grow_wide(GrowCtx g, 
         }
         if (found || hi >= (uint32_t)d) break;
         lo = hi; hi = min((uint32_t)d, hi + WARPS);
+        if (wid == 0 && lo == (uint32_t)m) warp_draw_materialize(s_perm, d, m, draw_j, lane);
         if (tid == 0) {  // deal the next positions (Philox block i >> 2 holds the draws of positions 4 (i >> 2) ..)
             uint4 rnd = make_uint4(0, 0, 0, 0);
             for (uint32_t i = lo; i < hi; ++i) {
