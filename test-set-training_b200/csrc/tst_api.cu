@@ -718,7 +718,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const size_t big_smem = (size_t)g.MB * g.HFS_max * 4 + big_tile_bytes;
     if (big_smem > BIG_SMEM_BUDGET + big_tile_bytes) return fail(TST_ERR_UNSUPPORTED, "histogram for one feature exceeds the shared-memory budget");
     const bool small_packed = packed_ok;  // register-only warp kernel (tst_grow_small.cuh); generic one otherwise
-    const uint32_t small_per_warp = small_packed ? ((64u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u)
+    const uint32_t small_per_warp = small_packed ? small4_per_warp(d)
                                                  : (uint32_t)C * 32u + (uint32_t)C + 32u + 96u + (uint32_t)((d + 1) / 2);
     const size_t small_smem = (size_t)SMALL_WARPS * small_per_warp * 4;
     // [2p], [2p+1] big / mid queue counts of parity p, [4] small, [5] tiny, [6 + r] tiny size histogram (r <= 6), [16 + p] four-warps-per-node

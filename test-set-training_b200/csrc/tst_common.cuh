@@ -66,7 +66,7 @@ __device__ __forceinline__ void warp_draw_primary(uint16_t* s_perm, int d, int m
 // j_i = i + mulhi(v_i, d - i); the feature it ends up with is whatever sat at position j_i before step i, i.e. u_k of the LATEST
 // earlier step k that wrote there (j_k == j_i), else j_i itself, where u_k (the value position k held before step k) is found by
 // pointer jumping along "latest earlier step that wrote position k".  No shared-memory round trips and no serial walk by lane 0:
-// ~145 warp instructions instead of ~230, and a dependency chain of log2(m) shuffles instead of m swaps.  Writes s_perm[0..m);
+// ~115 warp instructions instead of ~230, and a dependency chain of one MATCH + log2(m) shuffles instead of m swaps.  Writes s_perm[0..m);
 // returns j_i so that warp_draw_materialize can rebuild the whole permutation before a fallback draw continues it (rare).
 #define DRAW_SPARSE_MAX 16
 __device__ __forceinline__ uint32_t warp_draw_first(uint16_t* s_perm, int d, int m, uint32_t begin, uint32_t depth, uint32_t gid,
@@ -85,13 +85,17 @@ __device__ __forceinline__ uint32_t warp_draw_first(uint16_t* s_perm, int d, int
     const uint32_t v = (lane & 2u) ? ((lane & 1u) ? vw : vz) : ((lane & 1u) ? vy : vx);
     const bool mine = (int)lane < m;
     const uint32_t j = mine ? lane + mulhi32(v, (uint32_t)d - lane) : 0xFFFFFFFFu;
-    uint32_t K = lane, Kj = 0xFFFFFFFFu;  // latest earlier step that wrote my position / my partner's position
-    for (int k = 0; k + 1 < m; ++k) {
-        const uint32_t jk = __shfl_sync(0xffffffffu, j, k);
-        if ((uint32_t)k < lane) {
-            if (jk == lane) K = (uint32_t)k;
-            if (jk == j) Kj = (uint32_t)k;
-        }
+    // latest earlier step that wrote my position (K) / my partner's position (Kj): ONE match over 32 keys -- lanes 0..15 present
+    // their partner j, lanes 16..31 present the position (lane - 16) as a query; equal keys meet in the match mask
+    uint32_t K = lane, Kj = 0xFFFFFFFFu;
+    {
+        const uint32_t q = lane - 16u;
+        const uint32_t key = lane < 16u ? (mine ? j : 0x10000u + lane) : ((int)q < m ? q : 0x20000u + lane);
+        const uint32_t mm = __match_any_sync(0xffffffffu, key) & 0xFFFFu;
+        const uint32_t below = mm & ((1u << (lane & 15u)) - 1u);       // steps before mine (data lane) / before the queried position
+        const uint32_t hb = below ? 31u - __clz(below) : 0xFFFFFFFFu;
+        const uint32_t kq = __shfl_sync(0xffffffffu, hb, (lane + 16u) & 31u);  // data lane i reads query lane 16 + i
+        if (lane < 16u) { Kj = hb; if (kq != 0xFFFFFFFFu) K = kq; }
     }
     uint32_t u = K;  // follow the chain to the step whose position nobody wrote before: it held its own index
     for (int s = 1; s < m; s <<= 1) u = __shfl_sync(0xffffffffu, u, u);

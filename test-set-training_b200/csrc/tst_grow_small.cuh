@@ -9,6 +9,7 @@
 // Bit-exact with oracle/hist_rf.c: candidates are the occupied bins, gain in fp64, ties -> lowest
 // (feature, bin); fallback draws take the first feature in draw order that separates the rows.
 #pragma once
+#include <type_traits>
 #include "tst_grow.cuh"
 
 __device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
@@ -35,15 +36,17 @@ __device__ __forceinline__ void warp_argmax(double& gn, uint32_t& key) {
 #define SMALL_MINB 7  // 72 registers: measured 117.4 ms per 640 trees vs 121.8 (8 CTAs, 64 registers, spills), 120 (6), 122.6 (5)
 #endif
 #define TINY_RESERVE 8u  // tiny-queue slots a warp of k_grow_small4 reserves per atomic
+__host__ __device__ constexpr uint32_t small4_per_warp(int d) { return (256u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u; }
+
 template <int WARPS, bool REG = false>  // REG: criterion 2 (continuous squared error), same register-only scheme on (weight, sum) words
 __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     extern __shared__ __align__(16) uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const int C = g.C, d = g.d, m = g.m;
-    // per-warp shared layout (words): P[32] u64 | src[32] | stack[32][3] | perm[(d+1)/2], rounded to 16 bytes
-    const uint32_t per_warp = (64u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u;
+    // per-warp shared layout (words): P[4][32] u64 | src[32] | stack[32][3] | perm[(d+1)/2], rounded to 16 bytes
+    const uint32_t per_warp = small4_per_warp(d);
     unsigned long long* s_P = (unsigned long long*)(s_mem + warp * per_warp);
-    uint32_t* s_src = s_mem + warp * per_warp + 64;
+    uint32_t* s_src = s_mem + warp * per_warp + 256;
     uint32_t* s_stack = s_src + 32;
     uint16_t* s_perm = (uint16_t*)(s_stack + 96);
     const uint8_t* __restrict__ bins = g.bins_rm;
@@ -138,6 +141,77 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                             if (pos0 == m) n_fb++;
                         }
                         __syncwarp();
+                    }
+                    if constexpr (!REG) {
+                        // T = 2 or 4 positions per group and pass while the sampled features outnumber the groups (nodes of > 8 rows
+                        // with m = 8): group gi takes positions pos0 + q nf + gi, q < T.  One broadcast loop, one estimate REDUX and one
+                        // arg-max serve them all, which divides the fixed cost of a pass (the 17..32-row nodes ran 8 passes, now 2).
+                        auto multi = [&](auto TT) {
+                            constexpr int T = decltype(TT)::value;
+                            const int nfcT = min(T * (int)nf, m - pos0);
+                            uint32_t posv[T], bv[T];
+                            bool lv[T];
+#pragma unroll
+                            for (int q = 0; q < T; ++q) {
+                                const bool v = (int)(q * nf + gi) < nfcT;
+                                posv[q] = (uint32_t)pos0 + (v ? q * nf + gi : 0u);
+                                lv[q] = gvalid && v;
+                                bv[q] = lv[q] ? (uint32_t)rowp[s_perm[posv[q]]] : 0u;
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int q = 0; q < T; ++q) s_P[32u * q + lane] = cw_g | ((unsigned long long)bv[q] << 52);
+                            __syncwarp();
+                            unsigned long long acc[T];
+#pragma unroll
+                            for (int q = 0; q < T; ++q) acc[q] = 0ull;
+                            for (uint32_t kk = 0; kk < rr; kk += 4) {
+#pragma unroll
+                                for (int q = 0; q < T; ++q) {
+                                    const ulonglong2* gp = (const ulonglong2*)(s_P + 32u * q + gbase);
+                                    const ulonglong2 a = gp[kk >> 1], c = gp[(kk >> 1) + 1];
+                                    const uint32_t cmp = (bv[q] << 20) | 0xFFFFFu;
+                                    if ((uint32_t)(a.x >> 32) <= cmp) acc[q] += a.x;
+                                    if ((uint32_t)(a.y >> 32) <= cmp) acc[q] += a.y;
+                                    if ((uint32_t)(c.x >> 32) <= cmp) acc[q] += c.x;
+                                    if ((uint32_t)(c.y >> 32) <= cmp) acc[q] += c.y;
+                                }
+                            }
+                            float ge[T], gmax = 0.0f;
+#pragma unroll
+                            for (int q = 0; q < T; ++q) {
+                                const uint32_t L0 = F13(acc[q], 0), L1 = F13(acc[q], 1), L2 = F13(acc[q], 2), L3 = F13(acc[q], 3);
+                                const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+                                const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
+                                const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+                                lv[q] = lv[q] && NL >= g.msl && NR >= g.msl;
+                                ge[q] = lv[q] ? gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR)) : 0.0f;
+                                gmax = fmaxf(gmax, ge[q]);
+                            }
+                            float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gmax)));
+                            if (found) thr = fmaxf(thr, __double2float_rd(best_gain));
+                            thr *= TST_EST_MARGIN;
+                            double gn = -1.0;
+                            uint32_t key = 0xFFFFFFFFu;
+#pragma unroll
+                            for (int q = 0; q < T; ++q) {
+                                if (lv[q] && ge[q] >= thr) {
+                                    const uint32_t L0 = F13(acc[q], 0), L1 = F13(acc[q], 1), L2 = F13(acc[q], 2), L3 = F13(acc[q], 3);
+                                    const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+                                    const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
+                                    const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+                                    const double gq = gini_gain(SL, NL, SR, NR);
+                                    if (gq > gn) { gn = gq; key = (posv[q] << 8) | bv[q]; }  // positions ascend with q: a tie stays with the feature drawn first
+                                }
+                            }
+                            warp_argmax_redux(gn, key);
+                            if (key != 0xFFFFFFFFu && gn > best_gain) {  // an earlier pass keeps a tie
+                                best_gain = gn; best_key = ((uint32_t)s_perm[key >> 8] << 8) | (key & 0xFFu); found = true;
+                            }
+                            pos0 += nfcT;
+                        };
+                        if (pos0 < m && 2 * (int)nf < m - pos0) { multi(std::integral_constant<int, 4>{}); continue; }
+                        if (pos0 < m && (int)nf < m - pos0) { multi(std::integral_constant<int, 2>{}); continue; }
                     }
                     const bool pvalid = (int)gi < nfc;
                     const uint32_t pos = (uint32_t)pos0 + (pvalid ? gi : 0u);
