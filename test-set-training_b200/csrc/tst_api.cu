@@ -150,6 +150,7 @@ struct tst_handle {
         long thin_nodes = 2048;
         int mid_classes = -1;         // size classes of the warp-per-node tier with their own queue + kernel instantiation: bit 0 = 33..64 rows
                                       // (2 row slots per lane), bit 1 = ..128 rows (4 slots); 0 = one queue for the whole tier; default: 3 for batches of >= 2^24 (tree, row) pairs, else 0
+        int small_multi = -1;         // the k_grow_small4 instantiation with 2 / 4 positions of the draw per lane group and pass: 1 on, 0 off, default: deep batches and criterion 2
         int big_lite = -1;            // light CTA-tier nodes (packed Gini) in their own queue + the LITE instantiation of k_grow_big: 1 on, 0 off, default: on for deep batches
         int wide_max = -1;            // largest node of the four-warps-per-node tier (0 = tier off; default 2048)
         int sub_rows = -1;            // row capacity of the CTA-per-subtree tier (<= 0 = tier off, the default)
@@ -213,6 +214,7 @@ static int set_option(tst_handle* h, const std::string& nm, long v) {
     else if (nm == "WIDE_MAX") kn.wide_max = (int)v;
     else if (nm == "MID_CLASSES") kn.mid_classes = (int)v;
     else if (nm == "BIG_LITE") kn.big_lite = (int)v;
+    else if (nm == "SMALL_MULTI") kn.small_multi = (int)v;
     else return -1;
     return 0;
 }
@@ -263,7 +265,7 @@ extern "C" int tst_create(tst_handle** out, int device, int rank, int world, con
     h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize; h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     // tuning / diagnostic knobs: defaults from the environment (TST_<NAME>), read once here; tst_set_option changes them later
     for (const char* nm : {"L2_PERSIST", "TRACE", "STASH", "BIG_PACKED", "ROOT_DENSE", "TINY_MAX", "MID_MAX", "STASH_MAX", "BLIND_LEVELS",
-                           "THIN_NODES", "SUB_ROWS", "WIDE_MAX", "MID_CLASSES", "BIG_LITE"}) {
+                           "THIN_NODES", "SUB_ROWS", "WIDE_MAX", "MID_CLASSES", "BIG_LITE", "SMALL_MULTI"}) {
         const std::string env = std::string("TST_") + nm;
         if (const char* v = getenv(env.c_str())) set_option(h, nm, atol(v));
     }
@@ -303,6 +305,8 @@ static int set_kernel_attrs(tst_handle* h) {
     CK(cudaFuncSetAttribute(k_grow_small<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(k_grow_small4<SMALL_WARPS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, MID_R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, 2, false, MIDC0_MINB_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CK(cudaFuncSetAttribute(k_grow_mid4<MID_WARPS, 2, true, MIDC0_MINB_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -744,6 +748,7 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
     const int mid_classes = (mid_packed && g.mid_max > SMALL_MAX) ? (kn.mid_classes >= 0 ? kn.mid_classes & 3 : (deep_levels ? 3 : 0)) : 0;
     // light nodes of the CTA tier (weight < 2^16: levels 5+ of a 1M-row tree) run the packed-Gini-only instantiation, 4 CTAs per SM
     g.bigl = (!reg && packed_ok && g.big_packed && g.big_tile && (kn.big_lite >= 0 ? kn.big_lite != 0 : deep_levels)) ? 1u : 0u;
+    const bool small_multi = kn.small_multi >= 0 ? kn.small_multi != 0 : (deep_levels || reg);
     const size_t bigl_smem = (8 * (size_t)BIGP_FS + (size_t)BIG_THREADS * ((h->dstride >> 2) + 1)) * 4;
     size_t midc_smem[2];
     for (int c = 0; c < 2; ++c) {
@@ -987,7 +992,9 @@ extern "C" int tst_fit_oof(tst_handle* h, const uint8_t* y_dev, const uint8_t* f
             uint32_t blocks = std::min<uint32_t>((nsmall + SMALL_WARPS - 1) / SMALL_WARPS, (uint32_t)h->sm_count * 64u);
             CK(cudaEventRecord(h->evs0, st));
             small_started = true;
-            if (reg) k_grow_small4<SMALL_WARPS, true><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            if (reg && small_multi) k_grow_small4<SMALL_WARPS, true, true><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            else if (reg) k_grow_small4<SMALL_WARPS, true><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
+            else if (small_packed && small_multi) k_grow_small4<SMALL_WARPS, false, true><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
             else if (small_packed) k_grow_small4<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
             else k_grow_small<SMALL_WARPS><<<blocks, SMALL_WARPS * 32, small_smem, st>>>(g, g.qsmall, nsmall);
             CKL();

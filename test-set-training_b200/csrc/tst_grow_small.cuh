@@ -38,7 +38,10 @@ __device__ __forceinline__ void warp_argmax(double& gn, uint32_t& key) {
 #define TINY_RESERVE 8u  // tiny-queue slots a warp of k_grow_small4 reserves per atomic
 __host__ __device__ constexpr uint32_t small4_per_warp(int d) { return (256u + 32u + 96u + (uint32_t)((d + 1) / 2) + 3u) & ~3u; }
 
-template <int WARPS, bool REG = false>  // REG: criterion 2 (continuous squared error), same register-only scheme on (weight, sum) words
+// REG: criterion 2 (continuous squared error), same register-only scheme on (weight, sum) words.
+// MULTI: several positions of the draw per lane group and pass (the throughput instantiation: its extra live values cost the
+// one-position path 10 % in latency-bound jobs, so the host picks it for deep batches and for criterion 2 only).
+template <int WARPS, bool REG = false, bool MULTI = false>
 __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx g, const Task* __restrict__ tasks, uint32_t ntasks) {
     extern __shared__ __align__(16) uint32_t s_mem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                         }
                         __syncwarp();
                     }
-                    if constexpr (!REG) {
+                    if constexpr (MULTI) {
                         // T = 2 or 4 positions per group and pass while the sampled features outnumber the groups (nodes of > 8 rows
                         // with m = 8): group gi takes positions pos0 + q nf + gi, q < T.  One broadcast loop, one estimate REDUX and one
                         // arg-max serve them all, which divides the fixed cost of a pass (the 17..32-row nodes ran 8 passes, now 2).
@@ -180,12 +183,19 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
                             float ge[T], gmax = 0.0f;
 #pragma unroll
                             for (int q = 0; q < T; ++q) {
-                                const uint32_t L0 = F13(acc[q], 0), L1 = F13(acc[q], 1), L2 = F13(acc[q], 2), L3 = F13(acc[q], 3);
-                                const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
-                                const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
-                                const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
-                                lv[q] = lv[q] && NL >= g.msl && NR >= g.msl;
-                                ge[q] = lv[q] ? gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR)) : 0.0f;
+                                if constexpr (REG) {
+                                    const uint32_t NL = F13(acc[q], 0), NR = N - NL;
+                                    const unsigned long long SLr = REG13_S(acc[q]), SRr = Stot - SLr;
+                                    lv[q] = lv[q] && NL >= g.msl && NR >= g.msl;
+                                    ge[q] = lv[q] ? mse_gain_estimate(__ull2float_rn(SLr), __uint2float_rn(NL), __ull2float_rn(SRr), __uint2float_rn(NR)) : 0.0f;
+                                } else {
+                                    const uint32_t L0 = F13(acc[q], 0), L1 = F13(acc[q], 1), L2 = F13(acc[q], 2), L3 = F13(acc[q], 3);
+                                    const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+                                    const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
+                                    const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+                                    lv[q] = lv[q] && NL >= g.msl && NR >= g.msl;
+                                    ge[q] = lv[q] ? gain_estimate(__uint2float_rn(SL), __uint2float_rn(NL), __uint2float_rn(SR), __uint2float_rn(NR)) : 0.0f;
+                                }
                                 gmax = fmaxf(gmax, ge[q]);
                             }
                             float thr = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(gmax)));
@@ -196,11 +206,18 @@ __global__ void __launch_bounds__(WARPS * 32, SMALL_MINB) k_grow_small4(GrowCtx 
 #pragma unroll
                             for (int q = 0; q < T; ++q) {
                                 if (lv[q] && ge[q] >= thr) {
-                                    const uint32_t L0 = F13(acc[q], 0), L1 = F13(acc[q], 1), L2 = F13(acc[q], 2), L3 = F13(acc[q], 3);
-                                    const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
-                                    const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
-                                    const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
-                                    const double gq = gini_gain(SL, NL, SR, NR);
+                                    double gq;
+                                    if constexpr (REG) {
+                                        const uint32_t NL = F13(acc[q], 0), NR = N - NL;
+                                        const unsigned long long SLr = REG13_S(acc[q]);
+                                        gq = mse_gain(SLr, NL, Stot - SLr, NR);
+                                    } else {
+                                        const uint32_t L0 = F13(acc[q], 0), L1 = F13(acc[q], 1), L2 = F13(acc[q], 2), L3 = F13(acc[q], 3);
+                                        const uint32_t NL = L0 + L1 + L2 + L3, NR = N - NL;
+                                        const uint32_t R0 = t0 - L0, R1 = t1 - L1, R2 = t2 - L2, R3 = t3 - L3;
+                                        const uint32_t SL = L0 * L0 + L1 * L1 + L2 * L2 + L3 * L3, SR = R0 * R0 + R1 * R1 + R2 * R2 + R3 * R3;
+                                        gq = gini_gain(SL, NL, SR, NR);
+                                    }
                                     if (gq > gn) { gn = gq; key = (posv[q] << 8) | bv[q]; }  // positions ascend with q: a tie stays with the feature drawn first
                                 }
                             }

@@ -195,9 +195,22 @@ def _edge_case_tables():
     return out
 
 
+@pytest.fixture(params=["auto", "deep"])
+def paths(request, eng):
+    """The throughput variants that are chosen automatically only for deep batches (>= 2^24 (tree, row) pairs) -- size-class queues
+    of the warp-per-node tier, the light queue of the CTA tier, several draw positions per pass in the warp-per-subtree kernel --
+    forced on for the small tables of these tests as well."""
+    knobs = dict(SMALL_MULTI=1, BIG_LITE=1, MID_CLASSES=3) if request.param == "deep" else {}
+    for kk, v in knobs.items():
+        eng.set_option(kk, v)
+    yield request.param
+    for kk in knobs:
+        eng.set_option(kk, -1)
+
+
 @pytest.mark.parametrize("name", ["lowcard", "dups", "oneclass", "const", "manyclass", "maxclass", "tiny"])
 @pytest.mark.parametrize("pk", [dict(), dict(max_depth=3), dict(min_samples_leaf=3, min_samples_split=8), dict(max_features=None)])
-def test_edge_cases_bit_exact(eng, name, pk):
+def test_edge_cases_bit_exact(eng, paths, name, pk):
     bins, y, C = _edge_case_tables()[name]
     n = bins.shape[1]
     k = 3
@@ -214,7 +227,7 @@ def test_edge_cases_bit_exact(eng, name, pk):
 
 
 @pytest.mark.parametrize("seed", range(24))
-def test_random_configurations_bit_exact(eng, seed):
+def test_random_configurations_bit_exact(eng, paths, seed):
     """Randomised shapes / cardinalities / parameters: every tier (CTA, warp-per-node, warp-per-subtree, packed and
     generic) is hit with node sizes straddling the 32- and 256-row tier boundaries."""
     rng = np.random.default_rng(1000 + seed)
@@ -437,14 +450,14 @@ def test_random_large_configurations_bit_exact(eng, seed):
     if rng.random() < 0.4:
         pk["max_features"] = int(rng.integers(1, d + 1))
     knobs = dict(BLIND_LEVELS=int(rng.choice([1, 2, 4, 8])), THIN_NODES=int(rng.choice([0, 64, 2048, 100000])),
-                 WIDE_MAX=int(rng.choice([0, 600, 1024])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])), MID_CLASSES=int(rng.integers(0, 4)), BIG_LITE=int(rng.integers(0, 2)))
+                 WIDE_MAX=int(rng.choice([0, 600, 1024])), MID_MAX=int(rng.choice([64, 256])), TINY_MAX=int(rng.choice([0, 3, 6])), MID_CLASSES=int(rng.integers(0, 4)), BIG_LITE=int(rng.integers(0, 2)), SMALL_MULTI=int(rng.integers(0, 2)))
     for kk, v in knobs.items():
         eng.set_option(kk, v)
     try:
         T = int(rng.integers(2, 6))
         gv, ov, gst, ost, forest = run_both(eng, bins, y, fold, k, T, C, seed=seed, keep=True, **pk)
     finally:
-        for kk, v in dict(BLIND_LEVELS=4, THIN_NODES=2048, WIDE_MAX=-1, MID_MAX=-1, TINY_MAX=-1, MID_CLASSES=-1, BIG_LITE=-1).items():
+        for kk, v in dict(BLIND_LEVELS=4, THIN_NODES=2048, WIDE_MAX=-1, MID_MAX=-1, TINY_MAX=-1, MID_CLASSES=-1, BIG_LITE=-1, SMALL_MULTI=-1).items():
             eng.set_option(kk, v)
     assert np.array_equal(gv, ov), (n, d, C, card, k, pk, knobs)
     check_stats(gst, ost)
@@ -740,7 +753,7 @@ def run_both_reg(eng, bins, yq, lev, fold, k, T, seed=0, keep=False, **pk):
 @pytest.mark.parametrize("n,d,k,mf,ties,pk", [(3000, 10, 3, 1.0, False, {}), (5000, 32, 5, 1.0, False, {}), (700, 6, 4, None, True, {}),
                                               (40000, 12, 2, 4, False, {}), (2500, 9, 3, 3, True, {}), (4000, 8, 2, "sqrt", False, dict(max_depth=6)),
                                               (1500, 14, 3, 0.5, True, dict(min_samples_leaf=4, min_samples_split=10)), (3000, 70, 2, 12, False, {})])
-def test_continuous_squared_error_bit_exact(eng, n, d, k, mf, ties, pk):
+def test_continuous_squared_error_bit_exact(eng, paths, n, d, k, mf, ties, pk):
     """Numeric answers on a continuous target (16-bit fixed point): (weight, sum y) histograms in every tier -- CTA per node,
     warp per node, warp per subtree, thread per subtree -- against the oracle: votes, counters, importances, whole trees.
     `ties`: integer-valued targets (counts), so many multi-row nodes are constant and must become leaves unsearched."""
