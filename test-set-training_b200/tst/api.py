@@ -58,11 +58,19 @@ def encode_labels(y):
     y = np.asarray(y)
     if y.dtype.kind in "ui" and y.size and int(y.min()) >= 0 and int(y.max()) < 4096:
         # small non-negative integers (the common case): a bincount is 20x cheaper than a sort-based unique at 1M rows
-        counts = np.bincount(y.ravel())
+        hi = int(y.max())
+        if hi < 16:  # a handful of classes: one vectorised compare per class beats the int64 cast inside bincount (0.7 vs 2.9 ms at 1M rows)
+            counts = np.array([np.count_nonzero(y == c) for c in range(hi + 1)])
+        else:
+            counts = np.bincount(y.ravel())
         classes = np.flatnonzero(counts).astype(y.dtype)
-        lut = np.zeros(counts.shape[0], dtype=np.int64)
-        lut[classes] = np.arange(classes.shape[0])
-        idx = lut[y.ravel()]
+        if classes.shape[0] <= _lib.MAX_CLASSES:
+            if y.dtype == np.uint8 and classes.shape[0] == counts.shape[0]:
+                return classes, np.ascontiguousarray(y.ravel())  # labels are 0 .. C-1 already: no copy (6 ms of LUT gathers at 1M rows)
+            lut = np.zeros(counts.shape[0], dtype=np.uint8)
+            lut[classes] = np.arange(classes.shape[0], dtype=np.uint8)
+            return classes, lut[y.ravel()]
+        idx = np.zeros(0, dtype=np.int64)  # too many classes: the error below
     else:
         classes, idx = np.unique(y, return_inverse=True)
     if classes.shape[0] > _lib.MAX_CLASSES:
@@ -400,12 +408,12 @@ def run_tst(X, y, k: int = 5, n_trees: int = 100, seed: int = 0, *, max_depth=No
     """k-fold x n_trees RF diagnostic.  X, y are host arrays (or device tensors); every copy is inside this call."""
     torch = _torch()
     eng = engine or get_engine()
-    classes, yi = encode_labels(y)
-    n_classes = int(classes.shape[0])
     if prebinned:
         eng.set_bins(X)
     else:
-        eng.bin(X, n_bins=n_bins)
+        eng.bin(X, n_bins=n_bins)  # large host tables: H2D + binning run on a side stream, under the label encoding below
+    classes, yi = encode_labels(y)
+    n_classes = int(classes.shape[0])
     y_dev = eng.to_dev(yi, torch.uint8)
     g_dev, n_groups = None, 1
     if group is not None:
