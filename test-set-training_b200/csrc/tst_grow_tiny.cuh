@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) k_tiny_sort(const uint4* __restrict__ in,
 }
 
 #ifndef TINY_MINB
-#define TINY_MINB 1
+#define TINY_MINB 5  // 96 registers (168 unbounded, 3 CTAs per SM): 22.1 -> 19.2 ms per 640 trees; 4 (115 registers) 19.7, 6 (80, spills) 19.4
 #endif
 template <int TMAX, bool REG = false>  // REG: criterion 2, words are weight (13 bits) | w * yq (39 bits)
 __global__ void __launch_bounds__(128, TINY_MINB) k_grow_tiny4(GrowCtx g, const uint4* __restrict__ tasks, uint32_t ntasks) {
