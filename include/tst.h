@@ -93,7 +93,7 @@ typedef struct {
     uint64_t row_visits_sub;    /* ... by the CTA-per-subtree kernel (k_grow_sub: rows cached in shared memory) */
     double ms_grow_sub;
     uint64_t launches_grow_sub;
-    uint64_t row_visits_wide;   /* ... by the four-warps-per-node kernel (k_grow_wide: 257 .. 2048-row nodes, warp-privatised histograms) */
+    uint64_t row_visits_wide;   /* ... by the four-warps-per-node kernel (k_grow_wide: 257 .. 1024-row nodes, rows staged once in shared memory, warp-privatised histograms) */
     double ms_grow_wide;
     uint64_t launches_grow_wide;
 } tst_stats;
