@@ -103,6 +103,32 @@ def test_encode_labels_class_order():
     assert classes.tolist() == ["a", "b", "c"] and idx.tolist() == [1, 0, 2, 0] and idx.dtype == np.uint8
 
 
+@pytest.mark.parametrize("y", [np.array([2, 0, 2, 1, 3, 3], dtype=np.uint8),            # 0 .. C-1 already: returned without a copy
+                               np.array([5, 5, 7, 200], dtype=np.uint8),                 # gaps
+                               np.array([0, 2, 2, 300, 4000], dtype=np.int64),           # sparse non-negative integers (bincount path)
+                               np.array([-3, 7, 7, -3, 0], dtype=np.int32),              # negative values: the sort-based path
+                               np.array([1.5, -2.0, 1.5, 9.25]),                         # floats
+                               (np.arange(1000) * 7 % 31).astype(np.uint8)])             # 31 classes
+def test_encode_labels_equals_np_unique(y):
+    """Every fast path of encode_labels is np.unique(y, return_inverse=True) (SK/ensemble/_forest.py:810-827)."""
+    from tst.api import encode_labels
+
+    classes, idx = encode_labels(y)
+    rc, ri = np.unique(y, return_inverse=True)
+    assert np.array_equal(classes, rc) and classes.dtype == rc.dtype
+    assert idx.dtype == np.uint8 and np.array_equal(idx, ri.astype(np.uint8))
+    assert np.array_equal(classes[idx], y)
+
+
+def test_encode_labels_rejects_too_many_classes():
+    from tst import _lib
+    from tst.api import encode_labels
+
+    for y in (np.arange(_lib.MAX_CLASSES + 1, dtype=np.uint8), np.arange(_lib.MAX_CLASSES + 1, dtype=np.int64) * 1000):
+        with pytest.raises(ValueError):
+            encode_labels(y)
+
+
 def test_ibp_vmin_matches_oracle_rule():
     import tst
 
