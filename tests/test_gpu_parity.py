@@ -195,12 +195,14 @@ def _edge_case_tables():
     return out
 
 
-@pytest.fixture(params=["auto", "deep"])
+@pytest.fixture(params=["auto", "deep", "plain"])
 def paths(request, eng):
     """The throughput variants that are chosen automatically only for deep batches (>= 2^24 (tree, row) pairs) -- size-class queues
     of the warp-per-node tier, the light queue of the CTA tier, several draw positions per pass in the warp-per-subtree kernel --
-    forced on for the small tables of these tests as well."""
-    knobs = dict(SMALL_MULTI=1, BIG_LITE=1, MID_CLASSES=3) if request.param == "deep" else {}
+    forced on for the small tables of these tests as well ("deep"), and all forced off ("plain": the one-position warp-per-subtree
+    kernel for criterion 2, which "auto" replaces by the multi-position one)."""
+    knobs = {"deep": dict(SMALL_MULTI=1, BIG_LITE=1, MID_CLASSES=3),
+             "plain": dict(SMALL_MULTI=0, BIG_LITE=0, MID_CLASSES=0)}.get(request.param, {})  # plain: also what criterion 2 would not pick by itself
     for kk, v in knobs.items():
         eng.set_option(kk, v)
     yield request.param
