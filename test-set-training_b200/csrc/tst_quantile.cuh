@@ -68,10 +68,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_columns(uint32_t* __restr
             for (int q = 0; q < 8; ++q) { s_base[lane * 8 + q] = ex; ex += v[q]; }
         }
         __syncthreads();
+        uint32_t key_next = tid < n ? src[tid] : 0u;  // the next tile's key is requested one tile ahead (the CTA is alone on its SM: nothing else hides the latency)
         for (int64_t t0 = 0; t0 < n; t0 += SORT_THREADS) {
             const int64_t i = t0 + tid;
             const bool ok = i < n;
-            const uint32_t key = ok ? src[i] : 0u;
+            const uint32_t key = key_next;
+            key_next = i + SORT_THREADS < n ? src[i + SORT_THREADS] : 0u;
             const uint32_t dg = (key >> shift) & 0xFFu;
             for (int q = tid; q < 256 * (NW + 2); q += SORT_THREADS) ((uint16_t*)s_wc)[q] = 0;
             __syncthreads();
